@@ -1,0 +1,212 @@
+/*
+ * paif_b200 — C ABI of the B200-native PAIF fusion hot path.
+ *
+ * The reference (LiuZhu-CV/PAIF) has no FFI of its own: its boundary for this path is
+ * the Python nn.Module interface of Network_Fusion_Searched
+ * (core/model_fusion_auto.py:599-640).  This header is the C-ABI layer underneath the
+ * drop-in module (paif_b200/fusion.py); every entry point names the reference
+ * operator it replaces.  All functions
+ *   - take plain device pointers, ints and a cudaStream_t passed as void*;
+ *   - enqueue on the caller's stream, never allocate, never synchronise
+ *     (so a whole forward / backward is CUDA-graph capturable);
+ *   - return 0 on success, a negative PAIF_E* validation code, or a positive
+ *     cudaError_t from the launch; paif_last_error_string() describes the last failure
+ *     of the calling thread.
+ * The caller (PyTorch) owns every buffer.
+ *
+ * ACTIVATION LAYOUT ("C4 map"): a C-channel fp32 feature map of a batch of B images
+ * is stored as [B][C/4][H][W][4] — 16-byte channel quads, planar per quad.  A warp
+ * that walks x reads/writes 512 contiguous bytes per quad plane, and one quad plane
+ * row is exactly the K-major, no-swizzle UMMA core-matrix operand (8 pixels x 16 B)
+ * that the tcgen05 implicit-GEMM convolution streams through shared memory.
+ * 1-channel planes are [B][H][W]; the pooled attention input is [B][H][W][4].
+ *
+ * Scalars that are learnable parameters (PReLU slopes) are passed as DEVICE pointers so
+ * that no host read-back is ever needed.
+ */
+#ifndef PAIF_B200_H
+#define PAIF_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAIF_ABI_VERSION 1
+
+#define PAIF_EINVAL   (-1)   /* bad argument (null pointer, unsupported size) */
+#define PAIF_ENOTSUP  (-2)   /* configuration not supported by this build     */
+
+/* conv engines */
+#define PAIF_ENGINE_AUTO    0
+#define PAIF_ENGINE_DIRECT  1   /* fp32 FFMA direct convolution (exact-fp32 path)          */
+#define PAIF_ENGINE_TCGEN05 2   /* tcgen05 TF32 implicit GEMM, fp32 accumulate in TMEM      */
+
+int         paif_abi_version(void);
+const char* paif_last_error_string(void);
+
+/* ------------------------------------------------------------------------------------
+ * stem_1 / stem_2: Conv2d(1,32,3,pad 1,bias=False) + PReLU(1)  — core/model_fusion_auto.py:607-614,
+ * fused with Cell_Decom.get_residue (max_c - min_c) — :517-521.
+ * img: 1-channel image with arbitrary element strides (the wrappers pass a channel-last
+ * strided view for vis).  w: [32][9].  feat: C4 map (32 ch).  residue: [B][H][W]. */
+int paif_stem_forward(const float* img, long long stride_b, long long stride_y, long long stride_x,
+                      const float* w, const float* slope,
+                      float* feat, float* residue, int B, int H, int W, void* stream);
+
+/* GuidedFilter(4, eps)(residue, feat) for eps in {1e-3, 1e-4} — core/model_fusion_auto.py:522-535
+ * + third-party guided_filter_pytorch (box filter radius 4, clipped borders).
+ * Writes the two low-frequency maps; HF = feat - LF is folded into the 1x1 conv weights. */
+int paif_gf_decomp_forward(const float* feat, const float* residue, float* lf1, float* lf2,
+                           int C, int B, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Generic dense "same"-padded stride-1 convolution over 1..3 concatenated C4 source maps
+ * (torch.cat along channels is a K-loop over sources) with a fused epilogue.  Replaces
+ * BasicConv / conv3x3 / nn.Conv2d call sites of ResidualDenseBlock (operations_m.py:435-449),
+ * ECABasicBlock (:368-393), ResidualModule (:451-464), Cell_Decom.conv1x1_{lf,hf}
+ * (core/model_fusion_auto.py:501-502) and their dgrad (weights transposed + flipped).
+ *
+ * epilogue, per output element v = accumulator:
+ *   v = v*ch_scale[c] + ch_shift[c]            (bias / eval-mode BatchNorm; NULL = skip)
+ *   v += pre_res[0] + pre_res[1]               (gradient accumulation before a mask)
+ *   out_pre = v                                (optional, saved for backward)
+ *   if mask_src: v *= (mask_src > 0 ? 1 : *mask_slope)      (PReLU' of a saved tensor)
+ *   else if slope: v = v > 0 ? v : v * *slope               (PReLU)
+ *   v *= post_scale
+ *   v += post_res[0] + post_res[1] + post_res[2]            (residual adds)
+ *   out = v ; out_act2 = PReLU(v, *slope2) (optional) ;
+ *   chan_partials[b][tile][c] = sum over the tile's pixels of v (optional, deterministic)
+ */
+typedef struct PaifConvDesc {
+    int B, H, W;
+    int nsrc;                 /* 1..3 sources                                      */
+    int cin_per_src;          /* channels per source map (multiple of 4; 32)       */
+    int cout;                 /* 32 (16 also accepted by the direct engine)        */
+    int kh, kw, dil;          /* odd kernel, padding = dil*(k-1)/2                 */
+    int engine;               /* PAIF_ENGINE_*                                     */
+    const float* src[3];
+    const float* weight;      /* direct engine: [nsrc][kh*kw][cin_per_src][cout]   */
+    const void*  weight_mma;  /* tcgen05 engine: UMMA-packed image, see DESIGN.md  */
+    const float* ch_scale;
+    const float* ch_shift;
+    const float* pre_res[2];
+    float*       out_pre;
+    const float* mask_src;
+    const float* mask_slope;
+    const float* slope;
+    float        post_scale;
+    const float* post_res[3];
+    float*       out;
+    float*       out_act2;
+    const float* slope2;
+    float*       chan_partials;
+} PaifConvDesc;
+
+int paif_conv_forward(const PaifConvDesc* desc, void* stream);
+/* number of per-image tiles the chosen engine writes into chan_partials ([B][tiles][cout]) */
+int paif_conv_num_tiles(int H, int W, int engine);
+
+/* ------------------------------------------------------------------------------------
+ * Depthwise k x k dilated convolution on a C4 map — the groups=C BasicConv inside DilConv
+ * (operations_m.py:499) and its transpose.  out = dw(relu_in ? max(x,0) : x);
+ * then optional  out *= (mask_src > 0)  and  out += post_res.   w: [C][k*k]. */
+int paif_dwconv_forward(const float* x, const float* w, int relu_in,
+                        const float* mask_src, const float* post_res, float* out,
+                        int C, int k, int dil, int B, int H, int W, void* stream);
+
+/* 2-arg ChannelPool — core/model_fusion_auto.py:1352-1355.
+ * pooled[B][H][W][4] = (max_c ir, mean_c ir, max_c vis, mean_c vis). */
+int paif_channel_pool(const float* ir_f, const float* vis_f, float* pooled,
+                      int C, int B, int H, int W, void* stream);
+
+/* spatial_attn_layer_M (BasicConv(4,1,k) + sigmoid) and the blend
+ * scale*ir + (1-scale)*vis — core/model_fusion_auto.py:1358-1368, :631-632.
+ * w: [4][k*k].  scale_out: [B][H][W] (saved for backward, may be NULL). */
+int paif_spa_blend_forward(const float* pooled, const float* w, int k,
+                           const float* ir_f, const float* vis_f,
+                           float* agg, float* scale_out, int C, int B, int H, int W, void* stream);
+
+/* eca_layer (operations_m.py:340-367): reduce per-tile channel sums (fixed order), mean,
+ * Conv1d(1,1,k,pad (k-1)/2, bias=False) across channels, sigmoid.  e: [B][C]. */
+int paif_eca_scale(const float* chan_partials, int tiles, const float* w1d, int k,
+                   float* e, int C, int B, int H, int W, void* stream);
+/* ECABasicBlock tail: out = PReLU(o * e[b][c] + x) (+ post_res) — operations_m.py:389-393 */
+int paif_eca_apply(const float* o, const float* x, const float* e, const float* slope,
+                   const float* post_res, float* out, int C, int B, int H, int W, void* stream);
+
+/* stem_out (Conv 32->16 3x3, Conv 16->1 3x3, PReLU) + tanh — core/model_fusion_auto.py:615-620,634.
+ * The two bias-free convolutions are merged into one 5x5 32->1 stencil; zero padding of the
+ * 16-channel intermediate is honoured exactly through 9 border-class weight sets
+ * wm[3][3][25][C] (class = (y==0?0 : y==H-1?2 : 1, same for x)).
+ * pre_out (optional): pre-activation saved for backward.  out: [B][H][W]. */
+int paif_out_forward(const float* feat, const float* wm, const float* slope,
+                     float* out, float* pre_out, int C, int B, int H, int W, void* stream);
+
+/* ====================================================================================
+ * backward-to-input (autograd of the above, attack/attack.py:501); weight gradients are
+ * intentionally not produced.
+ * ==================================================================================== */
+
+/* adjoint of paif_out_forward: gs = g * (1 - out^2) * PReLU'(pre); gfeat = stencil^T(gs).
+ * Optional second output gfeat_masked = gfeat * PReLU'(mask_src) (feeds the next dgrad). */
+int paif_out_backward(const float* g, const float* out, const float* pre_out,
+                      const float* wm, const float* slope,
+                      float* gfeat, const float* mask_src, const float* mask_slope, float* gfeat_masked,
+                      int C, int B, int H, int W, void* stream);
+
+/* out = g * PReLU'(mask_src; *mask_slope) * scale   (elementwise on C4 maps) */
+int paif_mask_scale(const float* g, const float* mask_src, const float* mask_slope, float scale,
+                    float* out, int C, int B, int H, int W, void* stream);
+
+/* out = a + b (+ c)  elementwise over n floats (n % 4 == 0) — residual adds that could not be
+ * fused into a producer's epilogue (Cell_Chain.forward, core/model_fusion_auto.py:445). */
+int paif_add_maps(const float* a, const float* b, const float* c, float* out, long long n, void* stream);
+
+/* ECA backward, pass 1: w = o*e + x; gw = gu * PReLU'(w); partial sums of gw*o per (b, tile, c). */
+int paif_eca_bwd_pass1(const float* gu, const float* o, const float* x, const float* e,
+                       const float* slope, float* gw, float* partials,
+                       int C, int B, int H, int W, void* stream);
+int paif_eca_bwd_tiles(int H, int W);
+/* ECA backward, scalar part: ge = sum gw*o; gm = conv1d^T(ge * e(1-e)) / (H*W).  gm: [B][C] */
+int paif_eca_bwd_scale(const float* partials, int tiles, const float* e, const float* w1d, int k,
+                       float* gm, int C, int B, int H, int W, void* stream);
+/* ECA backward, pass 2: go = gw * e[b][c] + gm[b][c] */
+int paif_eca_bwd_pass2(const float* gw, const float* e, const float* gm, float* go,
+                       int C, int B, int H, int W, void* stream);
+
+/* adjoint of the blend + spatial attention + ChannelPool. */
+int paif_spa_blend_backward_pre(const float* gagg, const float* ir_f, const float* vis_f,
+                                const float* scale, float* gpre, int C, int B, int H, int W, void* stream);
+int paif_spa_blend_backward(const float* gagg, const float* ir_f, const float* vis_f,
+                            const float* scale, const float* gpre, const float* w, int k,
+                            float* g_ir_f, float* g_vis_f, int C, int B, int H, int W, void* stream);
+
+/* adjoint of paif_gf_decomp_forward w.r.t. feat (source) and residue (guide).
+ * glf1/glf2: gradients w.r.t. the two LF maps.  gfeat: C4 map (written).
+ * gres_partial: [C/4][B][H][W] per-quad partial guide gradients (summed by the stem backward). */
+int paif_gf_decomp_backward(const float* feat, const float* residue,
+                            const float* glf1, const float* glf2,
+                            float* gfeat, float* gres_partial,
+                            int C, int B, int H, int W, void* stream);
+
+/* stem backward, pass 1: total = sum of up to 4 gradient maps + route(sum_q gres_partial) to the
+ * arg-max / arg-min channel of feat (first index on ties); gpre = total * PReLU'(feat). */
+int paif_stem_backward_pre(const float* feat, const float* slope,
+                           const float* g0, const float* g1, const float* g2, const float* g3,
+                           const float* gres_partial, float* gpre,
+                           int C, int B, int H, int W, void* stream);
+/* stem backward, pass 2: gimg = conv3x3^T(gpre) (32 -> 1); gimg: contiguous [B][H][W]. */
+int paif_stem_backward(const float* gpre, const float* w, float* gimg,
+                       int C, int B, int H, int W, void* stream);
+
+/* ====================================================================================
+ * evaluation metric: 9x9 confusion matrix (sklearn.metrics.confusion_matrix(labels=0..n-1),
+ * robust_test.py:207-211) accumulated on the GPU as int64; the caller all-reduces it (NCCL).
+ * conf: [n][n] int64, rows = label, cols = prediction; labels/preds outside 0..n-1 ignored. */
+int paif_confusion_accumulate(const long long* label, const long long* pred, long long count,
+                              int num_classes, long long* conf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAIF_B200_H */

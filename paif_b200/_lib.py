@@ -1,0 +1,102 @@
+"""ctypes binding of the C-ABI library ``libpaif_b200.so`` (include/paif_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing it is built in-tree with
+nvcc; if that fails the import raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpaif_b200.so")
+
+ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
+
+_f = C.c_void_p      # device pointers travel as integers
+_i = C.c_int
+_ll = C.c_longlong
+
+
+class ConvDesc(C.Structure):
+    """Mirror of ``PaifConvDesc`` (include/paif_b200.h)."""
+    _fields_ = [
+        ("B", _i), ("H", _i), ("W", _i),
+        ("nsrc", _i), ("cin_per_src", _i), ("cout", _i),
+        ("kh", _i), ("kw", _i), ("dil", _i), ("engine", _i),
+        ("src", _f * 3),
+        ("weight", _f), ("weight_mma", _f),
+        ("ch_scale", _f), ("ch_shift", _f),
+        ("pre_res", _f * 2),
+        ("out_pre", _f),
+        ("mask_src", _f), ("mask_slope", _f),
+        ("slope", _f),
+        ("post_scale", C.c_float),
+        ("post_res", _f * 3),
+        ("out", _f), ("out_act2", _f), ("slope2", _f),
+        ("chan_partials", _f),
+    ]
+
+
+# name -> argtypes (restype is int unless noted); must list EVERY symbol of the header.
+SIGNATURES = {
+    "paif_abi_version": [],
+    "paif_last_error_string": [],
+    "paif_stem_forward": [_f, _ll, _ll, _ll, _f, _f, _f, _f, _i, _i, _i, _f],
+    "paif_gf_decomp_forward": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_conv_forward": [C.POINTER(ConvDesc), _f],
+    "paif_conv_num_tiles": [_i, _i, _i],
+    "paif_dwconv_forward": [_f, _f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
+    "paif_channel_pool": [_f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_spa_blend_forward": [_f, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_eca_scale": [_f, _i, _f, _i, _f, _i, _i, _i, _i, _f],
+    "paif_eca_apply": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_out_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_out_backward": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_mask_scale": [_f, _f, _f, C.c_float, _f, _i, _i, _i, _i, _f],
+    "paif_add_maps": [_f, _f, _f, _f, _ll, _f],
+    "paif_eca_bwd_pass1": [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_eca_bwd_tiles": [_i, _i],
+    "paif_eca_bwd_scale": [_f, _i, _f, _f, _i, _f, _i, _i, _i, _i, _f],
+    "paif_eca_bwd_pass2": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_spa_blend_backward_pre": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_spa_blend_backward": [_f, _f, _f, _f, _f, _f, _i, _f, _f, _i, _i, _i, _i, _f],
+    "paif_gf_decomp_backward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_stem_backward_pre": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
+}
+
+_lib = None
+
+
+class PaifError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if needed) the C-ABI library; raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) or (_build.needs_build() and os.environ.get("PAIF_NO_REBUILD") != "1"):
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = C.c_char_p if name == "paif_last_error_string" else _i
+    if lib.paif_abi_version() != 1:
+        raise PaifError("libpaif_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().paif_last_error_string()
+        raise PaifError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,57 @@
+// C-ABI glue: version, error string, convolution engine dispatch.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace paif {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int conv_direct_launch(const PaifConvDesc& d, cudaStream_t stream);
+int conv_direct_tiles(int H, int W);
+int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream);
+int conv_tc_tiles(int H, int W);
+bool conv_tc_supported(const PaifConvDesc& d);
+
+}  // namespace paif
+
+using namespace paif;
+
+extern "C" int paif_abi_version(void) { return PAIF_ABI_VERSION; }
+extern "C" const char* paif_last_error_string(void) { return g_err; }
+
+extern "C" int paif_conv_forward(const PaifConvDesc* d, void* stream) {
+    PAIF_REQUIRE(d != nullptr, "null descriptor");
+    PAIF_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "bad shape");
+    PAIF_REQUIRE(d->nsrc >= 1 && d->nsrc <= 3, "nsrc must be 1..3");
+    PAIF_REQUIRE(d->cin_per_src > 0 && d->cin_per_src % 4 == 0, "cin_per_src must be a multiple of 4");
+    PAIF_REQUIRE((d->kh & 1) && (d->kw & 1) && d->kh >= 1 && d->kh <= 7 && d->kw >= 1 && d->kw <= 7, "odd kernel <= 7");
+    PAIF_REQUIRE(d->dil >= 1 && d->dil <= 2, "dilation 1 or 2");
+    PAIF_REQUIRE(d->out != nullptr, "null output");
+    for (int i = 0; i < d->nsrc; ++i) PAIF_REQUIRE(d->src[i] != nullptr, "null source");
+    PAIF_REQUIRE(d->B <= 65535, "B exceeds grid.z");
+    int engine = d->engine;
+    if (engine == PAIF_ENGINE_AUTO) engine = (d->weight_mma && conv_tc_supported(*d)) ? PAIF_ENGINE_TCGEN05 : PAIF_ENGINE_DIRECT;
+    if (engine == PAIF_ENGINE_DIRECT) {
+        PAIF_REQUIRE(d->weight != nullptr, "direct engine needs weight");
+        return conv_direct_launch(*d, (cudaStream_t)stream);
+    }
+    if (engine == PAIF_ENGINE_TCGEN05) {
+        PAIF_REQUIRE(d->weight_mma != nullptr, "tcgen05 engine needs weight_mma");
+        if (!conv_tc_supported(*d)) { set_error("paif_conv_forward: shape not supported by the tcgen05 engine"); return PAIF_ENOTSUP; }
+        return conv_tc_launch(*d, (cudaStream_t)stream);
+    }
+    set_error("paif_conv_forward: unknown engine %d", engine);
+    return PAIF_EINVAL;
+}
+
+extern "C" int paif_conv_num_tiles(int H, int W, int engine) {
+    if (engine == PAIF_ENGINE_TCGEN05) return conv_tc_tiles(H, W);
+    return conv_direct_tiles(H, W);
+}

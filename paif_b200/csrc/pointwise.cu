@@ -1,0 +1,611 @@
+// Bandwidth-bound fused kernels of the PAIF fusion path (everything that is not a dense
+// convolution or the guided filter).  All work on C4 maps ([B][C/4][H][W][4]); a warp walks x so
+// every quad-plane access is a 512-byte coalesced transaction.
+#include "common.cuh"
+
+namespace paif {
+
+#define PIX_SETUP()                                            \
+    const int x = blockIdx.x * 32 + threadIdx.x;               \
+    const int y = blockIdx.y * 8 + threadIdx.y;                \
+    const size_t plane = (size_t)H * W;                        \
+    const size_t pix = (size_t)y * W + x;
+
+static inline dim3 pix_grid(int W, int H, int Z) { return dim3(cdiv(W, 32), cdiv(H, 8), Z); }
+
+// ------------------------------------------------------------------------------------------
+// depthwise dilated conv (DilConv's groups=C BasicConv, operations_m.py:499), one thread per
+// (pixel, quad).  w: [C][k*k].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const float* __restrict__ xin, const float* __restrict__ w, int relu_in,
+              const float* __restrict__ mask_src, const float* __restrict__ post_res,
+              float* __restrict__ out, int Q, int k, int dil, int H, int W) {
+    __shared__ float4 sw[49];
+    const int q = blockIdx.z % Q, b = blockIdx.z / Q;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int taps = k * k;
+    if (tid < taps)
+        sw[tid] = make_float4(w[(q * 4 + 0) * taps + tid], w[(q * 4 + 1) * taps + tid],
+                              w[(q * 4 + 2) * taps + tid], w[(q * 4 + 3) * taps + tid]);
+    __syncthreads();
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float4* xp = reinterpret_cast<const float4*>(xin) + ((size_t)b * Q + q) * plane;
+    const int pad = dil * (k - 1) / 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ty = 0; ty < k; ++ty) {
+        const int yy = y + ty * dil - pad;
+        if (yy < 0 || yy >= H) continue;
+        for (int tx = 0; tx < k; ++tx) {
+            const int xx = x + tx * dil - pad;
+            if (xx < 0 || xx >= W) continue;
+            float4 v = xp[(size_t)yy * W + xx];
+            if (relu_in) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            const float4 ww = sw[ty * k + tx];
+            acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+            acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+        }
+    }
+    const size_t off = ((size_t)b * Q + q) * plane + pix;
+    if (mask_src) {
+        const float4 m = reinterpret_cast<const float4*>(mask_src)[off];
+        acc.x = m.x > 0.f ? acc.x : 0.f; acc.y = m.y > 0.f ? acc.y : 0.f;
+        acc.z = m.z > 0.f ? acc.z : 0.f; acc.w = m.w > 0.f ? acc.w : 0.f;
+    }
+    if (post_res) acc = f4_add(acc, reinterpret_cast<const float4*>(post_res)[off]);
+    reinterpret_cast<float4*>(out)[off] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// 2-arg ChannelPool (core/model_fusion_auto.py:1352-1355)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+channel_pool_kernel(const float* __restrict__ a, const float* __restrict__ v,
+                    float* __restrict__ pooled, int Q, int H, int W) {
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float4* ap = reinterpret_cast<const float4*>(a) + (size_t)b * Q * plane + pix;
+    const float4* vp = reinterpret_cast<const float4*>(v) + (size_t)b * Q * plane + pix;
+    float amax = -INFINITY, asum = 0.f, vmax = -INFINITY, vsum = 0.f;
+    for (int q = 0; q < Q; ++q) {
+        const float4 t = ap[q * plane];
+        amax = fmaxf(fmaxf(amax, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+        asum += (t.x + t.y) + (t.z + t.w);
+        const float4 u = vp[q * plane];
+        vmax = fmaxf(fmaxf(vmax, fmaxf(u.x, u.y)), fmaxf(u.z, u.w));
+        vsum += (u.x + u.y) + (u.z + u.w);
+    }
+    const float inv = 1.f / (float)(Q * 4);
+    reinterpret_cast<float4*>(pooled)[(size_t)b * plane + pix] = make_float4(amax, asum * inv, vmax, vsum * inv);
+}
+
+// ------------------------------------------------------------------------------------------
+// spatial_attn_layer_M + blend (core/model_fusion_auto.py:1358-1368, :631-632)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spa_blend_kernel(const float* __restrict__ pooled, const float* __restrict__ w, int k,
+                 const float* __restrict__ a, const float* __restrict__ v,
+                 float* __restrict__ agg, float* __restrict__ scale_out, int Q, int H, int W) {
+    __shared__ float4 sw[49];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int taps = k * k;
+    if (tid < taps) sw[tid] = make_float4(w[tid], w[taps + tid], w[2 * taps + tid], w[3 * taps + tid]);
+    __syncthreads();
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float4* pp = reinterpret_cast<const float4*>(pooled) + (size_t)b * plane;
+    const int pad = (k - 1) / 2;
+    float acc = 0.f;
+    for (int ty = 0; ty < k; ++ty) {
+        const int yy = y + ty - pad;
+        if (yy < 0 || yy >= H) continue;
+        for (int tx = 0; tx < k; ++tx) {
+            const int xx = x + tx - pad;
+            if (xx < 0 || xx >= W) continue;
+            const float4 p = pp[(size_t)yy * W + xx];
+            const float4 ww = sw[ty * k + tx];
+            acc = fmaf(p.x, ww.x, acc); acc = fmaf(p.y, ww.y, acc);
+            acc = fmaf(p.z, ww.z, acc); acc = fmaf(p.w, ww.w, acc);
+        }
+    }
+    const float s = sigmoid_f(acc);
+    if (scale_out) scale_out[(size_t)b * plane + pix] = s;
+    const float4* ap = reinterpret_cast<const float4*>(a) + (size_t)b * Q * plane + pix;
+    const float4* vp = reinterpret_cast<const float4*>(v) + (size_t)b * Q * plane + pix;
+    float4* op = reinterpret_cast<float4*>(agg) + (size_t)b * Q * plane + pix;
+    const float s1 = 1.f - s;
+    for (int q = 0; q < Q; ++q) {
+        const float4 t = ap[q * plane], u = vp[q * plane];
+        op[q * plane] = make_float4(s * t.x + s1 * u.x, s * t.y + s1 * u.y, s * t.z + s1 * u.z, s * t.w + s1 * u.w);
+    }
+}
+
+// adjoint, pass 1: gpre = (sum_c G_c (a_c - v_c)) * s (1 - s)
+__global__ void __launch_bounds__(256)
+spa_blend_bwd_pre_kernel(const float* __restrict__ G, const float* __restrict__ a, const float* __restrict__ v,
+                         const float* __restrict__ scale, float* __restrict__ gpre, int Q, int H, int W) {
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const size_t base = (size_t)b * Q * plane + pix;
+    float acc = 0.f;
+    for (int q = 0; q < Q; ++q) {
+        const float4 g = reinterpret_cast<const float4*>(G)[base + q * plane];
+        const float4 t = reinterpret_cast<const float4*>(a)[base + q * plane];
+        const float4 u = reinterpret_cast<const float4*>(v)[base + q * plane];
+        acc = fmaf(g.x, t.x - u.x, acc); acc = fmaf(g.y, t.y - u.y, acc);
+        acc = fmaf(g.z, t.z - u.z, acc); acc = fmaf(g.w, t.w - u.w, acc);
+    }
+    const float s = scale[(size_t)b * plane + pix];
+    gpre[(size_t)b * plane + pix] = acc * s * (1.f - s);
+}
+
+// adjoint, pass 2: transpose of the k x k conv (1 -> 4), routing through max / mean, blend terms.
+__global__ void __launch_bounds__(256)
+spa_blend_bwd_kernel(const float* __restrict__ G, const float* __restrict__ a, const float* __restrict__ v,
+                     const float* __restrict__ scale, const float* __restrict__ gpre,
+                     const float* __restrict__ w, int k,
+                     float* __restrict__ ga, float* __restrict__ gv, int Q, int H, int W) {
+    __shared__ float4 sw[49];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int taps = k * k;
+    if (tid < taps) sw[tid] = make_float4(w[tid], w[taps + tid], w[2 * taps + tid], w[3 * taps + tid]);
+    __syncthreads();
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const int pad = (k - 1) / 2;
+    const float* gp = gpre + (size_t)b * plane;
+    float4 gpool = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ty = 0; ty < k; ++ty) {
+        const int yy = y - (ty - pad);
+        if (yy < 0 || yy >= H) continue;
+        for (int tx = 0; tx < k; ++tx) {
+            const int xx = x - (tx - pad);
+            if (xx < 0 || xx >= W) continue;
+            const float gval = gp[(size_t)yy * W + xx];
+            const float4 ww = sw[ty * k + tx];
+            gpool.x = fmaf(gval, ww.x, gpool.x); gpool.y = fmaf(gval, ww.y, gpool.y);
+            gpool.z = fmaf(gval, ww.z, gpool.z); gpool.w = fmaf(gval, ww.w, gpool.w);
+        }
+    }
+    const size_t base = (size_t)b * Q * plane + pix;
+    // arg-max channels (first index on ties, as torch.max(dim))
+    int ia = 0, iv = 0;
+    float ma = -INFINITY, mv = -INFINITY;
+    for (int q = 0; q < Q; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(a)[base + q * plane];
+        const float4 u = reinterpret_cast<const float4*>(v)[base + q * plane];
+        const float tt[4] = {t.x, t.y, t.z, t.w}, uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (tt[j] > ma) { ma = tt[j]; ia = q * 4 + j; }
+            if (uu[j] > mv) { mv = uu[j]; iv = q * 4 + j; }
+        }
+    }
+    const float s = scale[(size_t)b * plane + pix], s1 = 1.f - s;
+    const float invC = 1.f / (float)(Q * 4);
+    const float ameanv = gpool.y * invC, vmeanv = gpool.w * invC;
+    for (int q = 0; q < Q; ++q) {
+        const float4 g = reinterpret_cast<const float4*>(G)[base + q * plane];
+        float ra[4] = {s * g.x + ameanv, s * g.y + ameanv, s * g.z + ameanv, s * g.w + ameanv};
+        float rv[4] = {s1 * g.x + vmeanv, s1 * g.y + vmeanv, s1 * g.z + vmeanv, s1 * g.w + vmeanv};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (q * 4 + j == ia) ra[j] += gpool.x;
+            if (q * 4 + j == iv) rv[j] += gpool.z;
+        }
+        reinterpret_cast<float4*>(ga)[base + q * plane] = make_float4(ra[0], ra[1], ra[2], ra[3]);
+        reinterpret_cast<float4*>(gv)[base + q * plane] = make_float4(rv[0], rv[1], rv[2], rv[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// ECA (operations_m.py:340-393)
+// ------------------------------------------------------------------------------------------
+__global__ void eca_scale_kernel(const float* __restrict__ partials, int tiles, const float* __restrict__ w1d,
+                                 int k, float* __restrict__ e, int C, float inv_hw) {
+    extern __shared__ float sm[];   // [C]
+    const int b = blockIdx.x, c = threadIdx.x;
+    float s = 0.f;
+    for (int t = 0; t < tiles; ++t) s += partials[((size_t)b * tiles + t) * C + c];   // fixed order
+    sm[c] = s * inv_hw;
+    __syncthreads();
+    const int pad = (k - 1) / 2;
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const int cc = c + j - pad;
+        if (cc >= 0 && cc < C) acc = fmaf(w1d[j], sm[cc], acc);
+    }
+    e[(size_t)b * C + c] = sigmoid_f(acc);
+}
+
+__global__ void __launch_bounds__(256)
+eca_apply_kernel(const float* __restrict__ o, const float* __restrict__ xin, const float* __restrict__ e,
+                 const float* __restrict__ slope_p, const float* __restrict__ post_res,
+                 float* __restrict__ out, int Q, int H, int W) {
+    const int q = blockIdx.z % Q, b = blockIdx.z / Q;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float a = *slope_p;
+    const float4 ev = reinterpret_cast<const float4*>(e)[(size_t)b * Q + q];
+    const size_t off = ((size_t)b * Q + q) * plane + pix;
+    const float4 ov = reinterpret_cast<const float4*>(o)[off];
+    const float4 xv = reinterpret_cast<const float4*>(xin)[off];
+    float4 r = make_float4(prelu_f(fmaf(ov.x, ev.x, xv.x), a), prelu_f(fmaf(ov.y, ev.y, xv.y), a),
+                           prelu_f(fmaf(ov.z, ev.z, xv.z), a), prelu_f(fmaf(ov.w, ev.w, xv.w), a));
+    if (post_res) r = f4_add(r, reinterpret_cast<const float4*>(post_res)[off]);
+    reinterpret_cast<float4*>(out)[off] = r;
+}
+
+// backward pass 1: gw = gu * PReLU'(o e + x); per-(b, tile, c) sums of gw * o.  Tile = 32 x 64 px.
+constexpr int ECAB_ROWS = 64;
+__global__ void __launch_bounds__(256)
+eca_bwd_pass1_kernel(const float* __restrict__ gu, const float* __restrict__ o, const float* __restrict__ xin,
+                     const float* __restrict__ e, const float* __restrict__ slope_p,
+                     float* __restrict__ gw, float* __restrict__ partials, int Q, int H, int W) {
+    __shared__ float red[8][32];
+    const int b = blockIdx.z;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const size_t plane = (size_t)H * W;
+    const float a = *slope_p;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tiles = gridDim.x * gridDim.y, tile = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int q = 0; q < Q; ++q) {
+        const float4 ev = reinterpret_cast<const float4*>(e)[(size_t)b * Q + q];
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < ECAB_ROWS / 8; ++i) {
+            const int y = blockIdx.y * ECAB_ROWS + i * 8 + threadIdx.y;
+            if (x < W && y < H) {
+                const size_t off = ((size_t)b * Q + q) * plane + (size_t)y * W + x;
+                const float4 ov = reinterpret_cast<const float4*>(o)[off];
+                const float4 xv = reinterpret_cast<const float4*>(xin)[off];
+                const float4 g = reinterpret_cast<const float4*>(gu)[off];
+                float4 r;
+                r.x = g.x * dprelu_f(fmaf(ov.x, ev.x, xv.x), a);
+                r.y = g.y * dprelu_f(fmaf(ov.y, ev.y, xv.y), a);
+                r.z = g.z * dprelu_f(fmaf(ov.z, ev.z, xv.z), a);
+                r.w = g.w * dprelu_f(fmaf(ov.w, ev.w, xv.w), a);
+                reinterpret_cast<float4*>(gw)[off] = r;
+                s.x = fmaf(r.x, ov.x, s.x); s.y = fmaf(r.y, ov.y, s.y);
+                s.z = fmaf(r.z, ov.z, s.z); s.w = fmaf(r.w, ov.w, s.w);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s.x += __shfl_xor_sync(0xffffffffu, s.x, d); s.y += __shfl_xor_sync(0xffffffffu, s.y, d);
+            s.z += __shfl_xor_sync(0xffffffffu, s.z, d); s.w += __shfl_xor_sync(0xffffffffu, s.w, d);
+        }
+        if (lane == 0) { red[warp][q * 4 + 0] = s.x; red[warp][q * 4 + 1] = s.y; red[warp][q * 4 + 2] = s.z; red[warp][q * 4 + 3] = s.w; }
+    }
+    __syncthreads();
+    const int tid = warp * 32 + lane;
+    if (tid < Q * 4) {
+        float t = 0.f;
+#pragma unroll
+        for (int wi = 0; wi < 8; ++wi) t += red[wi][tid];
+        partials[((size_t)b * tiles + tile) * (Q * 4) + tid] = t;
+    }
+}
+
+__global__ void eca_bwd_scale_kernel(const float* __restrict__ partials, int tiles, const float* __restrict__ e,
+                                     const float* __restrict__ w1d, int k, float* __restrict__ gm,
+                                     int C, float inv_hw) {
+    extern __shared__ float sm[];   // d[C]
+    const int b = blockIdx.x, c = threadIdx.x;
+    float s = 0.f;
+    for (int t = 0; t < tiles; ++t) s += partials[((size_t)b * tiles + t) * C + c];
+    const float ev = e[(size_t)b * C + c];
+    sm[c] = s * ev * (1.f - ev);
+    __syncthreads();
+    const int pad = (k - 1) / 2;
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const int cc = c - j + pad;
+        if (cc >= 0 && cc < C) acc = fmaf(w1d[j], sm[cc], acc);
+    }
+    gm[(size_t)b * C + c] = acc * inv_hw;
+}
+
+__global__ void __launch_bounds__(256)
+eca_bwd_pass2_kernel(const float* __restrict__ gw, const float* __restrict__ e, const float* __restrict__ gm,
+                     float* __restrict__ go, int Q, int H, int W) {
+    const int q = blockIdx.z % Q, b = blockIdx.z / Q;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float4 ev = reinterpret_cast<const float4*>(e)[(size_t)b * Q + q];
+    const float4 mv = reinterpret_cast<const float4*>(gm)[(size_t)b * Q + q];
+    const size_t off = ((size_t)b * Q + q) * plane + pix;
+    const float4 g = reinterpret_cast<const float4*>(gw)[off];
+    reinterpret_cast<float4*>(go)[off] =
+        make_float4(fmaf(g.x, ev.x, mv.x), fmaf(g.y, ev.y, mv.y), fmaf(g.z, ev.z, mv.z), fmaf(g.w, ev.w, mv.w));
+}
+
+// ------------------------------------------------------------------------------------------
+// stem_out + tanh as one 5x5 32->1 stencil with 9 border classes (see include/paif_b200.h)
+// ------------------------------------------------------------------------------------------
+constexpr int OUT_C = 32;
+__device__ __forceinline__ int border_class(int p, int n) { return p == 0 ? 0 : (p == n - 1 ? 2 : 1); }
+
+__global__ void __launch_bounds__(256)
+out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
+                   float* __restrict__ out, float* __restrict__ pre_out, int H, int W) {
+    extern __shared__ __align__(16) float swm[];   // [9][25][32]
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < 9 * 25 * OUT_C; i += 256) swm[i] = wm[i];
+    __syncthreads();
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const int cls = border_class(y, H) * 3 + border_class(x, W);
+    const float4* fp = reinterpret_cast<const float4*>(feat) + (size_t)b * (OUT_C / 4) * plane;
+    float acc = 0.f;
+    for (int ty = 0; ty < 5; ++ty) {
+        const int yy = y + ty - 2;
+        if (yy < 0 || yy >= H) continue;
+        for (int tx = 0; tx < 5; ++tx) {
+            const int xx = x + tx - 2;
+            if (xx < 0 || xx >= W) continue;
+            const float4* wv = reinterpret_cast<const float4*>(swm + ((size_t)cls * 25 + ty * 5 + tx) * OUT_C);
+#pragma unroll
+            for (int q = 0; q < OUT_C / 4; ++q) {
+                const float4 v = fp[q * plane + (size_t)yy * W + xx];
+                const float4 ww = wv[q];
+                acc = fmaf(v.x, ww.x, acc); acc = fmaf(v.y, ww.y, acc);
+                acc = fmaf(v.z, ww.z, acc); acc = fmaf(v.w, ww.w, acc);
+            }
+        }
+    }
+    if (pre_out) pre_out[(size_t)b * plane + pix] = acc;
+    out[(size_t)b * plane + pix] = tanhf(prelu_f(acc, *slope_p));
+}
+
+__global__ void __launch_bounds__(256)
+out_backward_kernel(const float* __restrict__ g, const float* __restrict__ outv, const float* __restrict__ pre,
+                    const float* __restrict__ wm, const float* __restrict__ slope_p,
+                    float* __restrict__ gfeat, const float* __restrict__ mask_src,
+                    const float* __restrict__ mask_slope, float* __restrict__ gfeat_masked, int H, int W) {
+    extern __shared__ __align__(16) float swm[];   // [9][25][32]
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < 9 * 25 * OUT_C; i += 256) swm[i] = wm[i];
+    __syncthreads();
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float a = *slope_p;
+    float acc[OUT_C];
+#pragma unroll
+    for (int c = 0; c < OUT_C; ++c) acc[c] = 0.f;
+    for (int ty = 0; ty < 5; ++ty) {
+        const int yy = y - (ty - 2);          // the output pixel p = q - t that used tap t on q
+        if (yy < 0 || yy >= H) continue;
+        for (int tx = 0; tx < 5; ++tx) {
+            const int xx = x - (tx - 2);
+            if (xx < 0 || xx >= W) continue;
+            const size_t pi = (size_t)b * plane + (size_t)yy * W + xx;
+            const float o = outv[pi];
+            const float gs = g[pi] * (1.f - o * o) * dprelu_f(pre[pi], a);
+            const int cls = border_class(yy, H) * 3 + border_class(xx, W);
+            const float4* wv = reinterpret_cast<const float4*>(swm + ((size_t)cls * 25 + ty * 5 + tx) * OUT_C);
+#pragma unroll
+            for (int q = 0; q < OUT_C / 4; ++q) {
+                const float4 ww = wv[q];
+                acc[q * 4 + 0] = fmaf(gs, ww.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(gs, ww.y, acc[q * 4 + 1]);
+                acc[q * 4 + 2] = fmaf(gs, ww.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(gs, ww.w, acc[q * 4 + 3]);
+            }
+        }
+    }
+    const size_t base = (size_t)b * (OUT_C / 4) * plane + pix;
+    const float ma = mask_slope ? *mask_slope : 0.f;
+#pragma unroll
+    for (int q = 0; q < OUT_C / 4; ++q) {
+        const float4 r = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        reinterpret_cast<float4*>(gfeat)[base + q * plane] = r;
+        if (gfeat_masked) {
+            const float4 m = reinterpret_cast<const float4*>(mask_src)[base + q * plane];
+            reinterpret_cast<float4*>(gfeat_masked)[base + q * plane] =
+                make_float4(r.x * dprelu_f(m.x, ma), r.y * dprelu_f(m.y, ma), r.z * dprelu_f(m.z, ma), r.w * dprelu_f(m.w, ma));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mask_scale_kernel(const float* __restrict__ g, const float* __restrict__ mask_src, const float* __restrict__ mask_slope,
+                  float scale, float* __restrict__ out, size_t n4) {
+    const float ma = mask_slope ? *mask_slope : 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(g)[i];
+        if (mask_src) {
+            const float4 m = reinterpret_cast<const float4*>(mask_src)[i];
+            v.x *= dprelu_f(m.x, ma); v.y *= dprelu_f(m.y, ma); v.z *= dprelu_f(m.z, ma); v.w *= dprelu_f(m.w, ma);
+        }
+        reinterpret_cast<float4*>(out)[i] = f4_scale(v, scale);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+add_maps_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                float* __restrict__ out, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = f4_add(reinterpret_cast<const float4*>(a)[i], reinterpret_cast<const float4*>(b)[i]);
+        if (c) v = f4_add(v, reinterpret_cast<const float4*>(c)[i]);
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// confusion matrix (robust_test.py:207-211): integer counts, shared-memory histogram per CTA,
+// 64-bit integer atomics -> bit-exact regardless of scheduling.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+confusion_kernel(const long long* __restrict__ label, const long long* __restrict__ pred, long long count,
+                 int n, unsigned long long* __restrict__ conf) {
+    extern __shared__ unsigned int hist[];   // [n*n]
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const long long l = label[i], p = pred[i];
+        if (l >= 0 && l < n && p >= 0 && p < n) atomicAdd(&hist[(int)l * n + (int)p], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x)
+        if (hist[i]) atomicAdd(&conf[i], (unsigned long long)hist[i]);
+}
+
+}  // namespace paif
+
+using namespace paif;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int paif_dwconv_forward(const float* x, const float* w, int relu_in, const float* mask_src,
+                                   const float* post_res, float* out, int C, int k, int dil,
+                                   int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(x && w && out, "null pointer");
+    PAIF_REQUIRE(C % 4 == 0 && k >= 1 && k <= 7 && (k & 1), "unsupported C / kernel size");
+    PAIF_REQUIRE((long long)B * (C / 4) <= 65535, "B*C/4 exceeds grid.z");
+    dwconv_kernel<<<pix_grid(W, H, B * (C / 4)), dim3(32, 8), 0, ST>>>(x, w, relu_in, mask_src, post_res, out,
+                                                                    C / 4, k, dil, H, W);
+    return check_launch("paif_dwconv_forward");
+}
+
+extern "C" int paif_channel_pool(const float* ir_f, const float* vis_f, float* pooled,
+                                 int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(ir_f && vis_f && pooled, "null pointer");
+    PAIF_REQUIRE(C % 4 == 0, "C must be a multiple of 4");
+    channel_pool_kernel<<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(ir_f, vis_f, pooled, C / 4, H, W);
+    return check_launch("paif_channel_pool");
+}
+
+extern "C" int paif_spa_blend_forward(const float* pooled, const float* w, int k, const float* ir_f,
+                                      const float* vis_f, float* agg, float* scale_out,
+                                      int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(pooled && w && ir_f && vis_f && agg, "null pointer");
+    PAIF_REQUIRE(C % 4 == 0 && k >= 1 && k <= 7 && (k & 1), "unsupported C / kernel size");
+    spa_blend_kernel<<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(pooled, w, k, ir_f, vis_f, agg, scale_out, C / 4, H, W);
+    return check_launch("paif_spa_blend_forward");
+}
+
+extern "C" int paif_spa_blend_backward_pre(const float* gagg, const float* ir_f, const float* vis_f,
+                                           const float* scale, float* gpre, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(gagg && ir_f && vis_f && scale && gpre, "null pointer");
+    spa_blend_bwd_pre_kernel<<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(gagg, ir_f, vis_f, scale, gpre, C / 4, H, W);
+    return check_launch("paif_spa_blend_backward_pre");
+}
+
+extern "C" int paif_spa_blend_backward(const float* gagg, const float* ir_f, const float* vis_f,
+                                       const float* scale, const float* gpre, const float* w, int k,
+                                       float* g_ir_f, float* g_vis_f, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(gagg && ir_f && vis_f && scale && gpre && w && g_ir_f && g_vis_f, "null pointer");
+    PAIF_REQUIRE(k >= 1 && k <= 7 && (k & 1), "unsupported kernel size");
+    spa_blend_bwd_kernel<<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(gagg, ir_f, vis_f, scale, gpre, w, k,
+                                                                  g_ir_f, g_vis_f, C / 4, H, W);
+    return check_launch("paif_spa_blend_backward");
+}
+
+extern "C" int paif_eca_scale(const float* chan_partials, int tiles, const float* w1d, int k, float* e,
+                              int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(chan_partials && w1d && e, "null pointer");
+    PAIF_REQUIRE(C <= 1024 && tiles > 0, "bad C / tiles");
+    eca_scale_kernel<<<B, C, C * sizeof(float), ST>>>(chan_partials, tiles, w1d, k, e, C, 1.f / ((float)H * (float)W));
+    return check_launch("paif_eca_scale");
+}
+
+extern "C" int paif_eca_apply(const float* o, const float* x, const float* e, const float* slope,
+                              const float* post_res, float* out, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(o && x && e && slope && out, "null pointer");
+    eca_apply_kernel<<<pix_grid(W, H, B * (C / 4)), dim3(32, 8), 0, ST>>>(o, x, e, slope, post_res, out, C / 4, H, W);
+    return check_launch("paif_eca_apply");
+}
+
+extern "C" int paif_eca_bwd_tiles(int H, int W) { return cdiv(W, 32) * cdiv(H, ECAB_ROWS); }
+
+extern "C" int paif_eca_bwd_pass1(const float* gu, const float* o, const float* x, const float* e,
+                                  const float* slope, float* gw, float* partials,
+                                  int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(gu && o && x && e && slope && gw && partials, "null pointer");
+    PAIF_REQUIRE(C == 32, "C must be 32");
+    dim3 grid(cdiv(W, 32), cdiv(H, ECAB_ROWS), B);
+    eca_bwd_pass1_kernel<<<grid, dim3(32, 8), 0, ST>>>(gu, o, x, e, slope, gw, partials, C / 4, H, W);
+    return check_launch("paif_eca_bwd_pass1");
+}
+
+extern "C" int paif_eca_bwd_scale(const float* partials, int tiles, const float* e, const float* w1d, int k,
+                                  float* gm, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(partials && e && w1d && gm, "null pointer");
+    eca_bwd_scale_kernel<<<B, C, C * sizeof(float), ST>>>(partials, tiles, e, w1d, k, gm, C, 1.f / ((float)H * (float)W));
+    return check_launch("paif_eca_bwd_scale");
+}
+
+extern "C" int paif_eca_bwd_pass2(const float* gw, const float* e, const float* gm, float* go,
+                                  int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(gw && e && gm && go, "null pointer");
+    eca_bwd_pass2_kernel<<<pix_grid(W, H, B * (C / 4)), dim3(32, 8), 0, ST>>>(gw, e, gm, go, C / 4, H, W);
+    return check_launch("paif_eca_bwd_pass2");
+}
+
+static int out_smem_attr() {
+    static bool done = false;
+    if (done) return 0;
+    const int bytes = 9 * 25 * OUT_C * sizeof(float);
+    cudaError_t e1 = cudaFuncSetAttribute(out_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e2 = cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("out kernel smem attr failed"); return (int)(e1 ? e1 : e2); }
+    done = true;
+    return 0;
+}
+
+extern "C" int paif_out_forward(const float* feat, const float* wm, const float* slope, float* out, float* pre_out,
+                                int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(feat && wm && slope && out, "null pointer");
+    PAIF_REQUIRE(C == OUT_C, "C must be 32");
+    PAIF_REQUIRE(H >= 2 && W >= 2, "H, W must be >= 2");
+    if (int r = out_smem_attr()) return r;
+    out_forward_kernel<<<pix_grid(W, H, B), dim3(32, 8), 9 * 25 * OUT_C * sizeof(float), ST>>>(feat, wm, slope, out, pre_out, H, W);
+    return check_launch("paif_out_forward");
+}
+
+extern "C" int paif_out_backward(const float* g, const float* out, const float* pre_out, const float* wm,
+                                 const float* slope, float* gfeat, const float* mask_src, const float* mask_slope,
+                                 float* gfeat_masked, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(g && out && pre_out && wm && slope && gfeat, "null pointer");
+    PAIF_REQUIRE(C == OUT_C, "C must be 32");
+    PAIF_REQUIRE(!gfeat_masked || mask_src, "gfeat_masked needs mask_src");
+    if (int r = out_smem_attr()) return r;
+    out_backward_kernel<<<pix_grid(W, H, B), dim3(32, 8), 9 * 25 * OUT_C * sizeof(float), ST>>>(
+        g, out, pre_out, wm, slope, gfeat, mask_src, mask_slope, gfeat_masked, H, W);
+    return check_launch("paif_out_backward");
+}
+
+extern "C" int paif_mask_scale(const float* g, const float* mask_src, const float* mask_slope, float scale,
+                               float* out, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(g && out, "null pointer");
+    const size_t n4 = (size_t)B * (C / 4) * H * W;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    mask_scale_kernel<<<blocks, 256, 0, ST>>>(g, mask_src, mask_slope, scale, out, n4);
+    return check_launch("paif_mask_scale");
+}
+
+extern "C" int paif_add_maps(const float* a, const float* b, const float* c, float* out, long long n, void* stream) {
+    PAIF_REQUIRE(a && b && out, "null pointer");
+    PAIF_REQUIRE(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+    if (n == 0) return 0;
+    const size_t n4 = (size_t)n / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    add_maps_kernel<<<blocks, 256, 0, ST>>>(a, b, c, out, n4);
+    return check_launch("paif_add_maps");
+}
+
+extern "C" int paif_confusion_accumulate(const long long* label, const long long* pred, long long count,
+                                         int num_classes, long long* conf, void* stream) {
+    PAIF_REQUIRE(label && pred && conf, "null pointer");
+    PAIF_REQUIRE(num_classes > 0 && num_classes <= 64 && count >= 0, "bad num_classes / count");
+    if (count == 0) return 0;
+    long long want = (count + 255) / 256;
+    const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+    confusion_kernel<<<blocks, 256, num_classes * num_classes * sizeof(unsigned int), ST>>>(
+        label, pred, count, num_classes, reinterpret_cast<unsigned long long*>(conf));
+    return check_launch("paif_confusion_accumulate");
+}

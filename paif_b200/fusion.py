@@ -1,0 +1,756 @@
+"""Drop-in replacement for PAIF's ``Network_Fusion_Searched``
+(reference core/model_fusion_auto.py:599-640) running on hand-written sm_100a kernels
+through the C ABI in ``include/paif_b200.h``.
+
+Same constructor ``(C, criterion, genotype_feature, steps=4, multiplier=3)``, same
+``state_dict`` keys / shapes (45 for the shipped ``fusion_at`` genotype, so reference
+checkpoints load with ``strict=True``), same ``forward(ir, vis) -> [B,1,H,W]`` and
+``_loss``; gradients flow to ``ir`` and ``vis`` (backward-to-input only — the PGD loop of
+attack/attack.py:417-514 never reads weight gradients).
+
+The nn.Modules below are *parameter containers* that mirror the reference's module tree
+(names, construction order and therefore default initialisation); none of their
+``nn.Conv2d`` children is ever called.  The arithmetic runs in ``_Runtime`` via ctypes
+calls into ``libpaif_b200.so``.  There is no PyTorch/CPU fallback: a missing library or a
+CPU tensor raises.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ConvDesc
+
+_RDB_SCALE = 0.333333       # literal constant, operations_m.py:449
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def basicconv_padding(k, d):
+    """BasicConv padding table, operations_m.py:121-132."""
+    return {(3, 1): 1, (3, 2): 2, (5, 1): 2, (5, 2): 4, (7, 1): 3, (7, 2): 6}.get((k, d), 0)
+
+
+def _check_same_padding(k, d, what):
+    if basicconv_padding(k, d) != d * (k - 1) // 2:
+        # the reference gives such a (k, d) padding 0, which breaks its own residual adds
+        raise NotImplementedError("%s: kernel %d dilation %d is not shape-preserving in the reference" % (what, k, d))
+
+
+# ----------------------------------------------------------------------------------------
+# weight packing (device-side torch ops, re-run only when a parameter changes)
+# ----------------------------------------------------------------------------------------
+class _ConvW:
+    """Packed weights of one dense convolution for both engines."""
+
+    def __init__(self, w, nsrc, k, dil):
+        cout, cin_total, kh, kw = w.shape
+        assert kh == k and kw == k and cin_total % nsrc == 0
+        self.k, self.dil, self.nsrc, self.cout = k, dil, nsrc, cout
+        self.cps = cin_total // nsrc
+        # direct engine: [nsrc][taps][cin_per_src][cout]
+        self.direct = w.reshape(cout, nsrc, self.cps, kh * kw).permute(1, 3, 2, 0).contiguous().float()
+        self.mma = None
+
+
+def _dgrad_groups(w, k, dil, scale=None):
+    """dgrad of conv(w) as forward convs: one _ConvW per group of 32 input channels.
+    gx[ci](q) = sum_{co,t} w[co][ci][flip t] * (scale[co] * gy[co])(q + off_t)."""
+    wf = w.flip(-1, -2)
+    if scale is not None:
+        wf = wf * scale.view(-1, 1, 1, 1)
+    cin_total = w.shape[1]
+    return [_ConvW(wf[:, g:g + 32].transpose(0, 1).contiguous(), 1, k, dil) for g in range(0, cin_total, 32)]
+
+
+def _bn_fold(bn):
+    s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return s.float().contiguous(), (bn.bias - bn.running_mean * s).float().contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# runtime: thin wrappers over the C ABI
+# ----------------------------------------------------------------------------------------
+class _Runtime:
+    def __init__(self, B, H, W, C, device, engine, save):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.device = device
+        self.engine = engine
+        self.save = save
+        self.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        self.launches = 0
+
+    # buffers ---------------------------------------------------------------------------
+    def new_map(self, C=None):
+        C = self.C if C is None else C
+        return torch.empty((self.B, C // 4, self.H, self.W, 4), device=self.device, dtype=torch.float32)
+
+    def new_plane(self, ch=None):
+        shape = (self.B, self.H, self.W) if ch is None else (self.B, self.H, self.W, ch)
+        return torch.empty(shape, device=self.device, dtype=torch.float32)
+
+    def call(self, name, *args):
+        self.launches += 1
+        _lib.call(name, *args, self.stream)
+
+    # kernels ---------------------------------------------------------------------------
+    def conv(self, srcs, cw, *, ch_scale=None, ch_shift=None, pre_res=(), want_pre=False, mask_src=None,
+             mask_slope=None, slope=None, post_scale=1.0, post_res=(), act2_slope=None, want_partials=False):
+        d = ConvDesc()
+        d.B, d.H, d.W = self.B, self.H, self.W
+        d.nsrc, d.cin_per_src, d.cout = cw.nsrc, cw.cps, cw.cout
+        d.kh = d.kw = cw.k
+        d.dil = cw.dil
+        engine = self.engine
+        if engine == _lib.ENGINE_AUTO:
+            engine = _lib.ENGINE_TCGEN05 if cw.mma is not None else _lib.ENGINE_DIRECT
+        d.engine = engine
+        assert len(srcs) == cw.nsrc
+        for i, s in enumerate(srcs):
+            d.src[i] = s.data_ptr()
+        d.weight = cw.direct.data_ptr()
+        d.weight_mma = _ptr(cw.mma)
+        d.ch_scale, d.ch_shift = _ptr(ch_scale), _ptr(ch_shift)
+        assert len(pre_res) <= 2 and len(post_res) <= 3
+        for i, r in enumerate(pre_res):
+            d.pre_res[i] = r.data_ptr()
+        for i, r in enumerate(post_res):
+            d.post_res[i] = r.data_ptr()
+        out = self.new_map(cw.cout)
+        d.out = out.data_ptr()
+        pre = act2 = partials = None
+        if want_pre:
+            pre = self.new_map(cw.cout)
+            d.out_pre = pre.data_ptr()
+        d.mask_src, d.mask_slope = _ptr(mask_src), _ptr(mask_slope)
+        d.slope = _ptr(slope)
+        d.post_scale = post_scale
+        if act2_slope is not None:
+            act2 = self.new_map(cw.cout)
+            d.out_act2, d.slope2 = act2.data_ptr(), act2_slope.data_ptr()
+        if want_partials:
+            tiles = _lib.load().paif_conv_num_tiles(self.H, self.W, engine)
+            partials = torch.empty((self.B, tiles, cw.cout), device=self.device, dtype=torch.float32)
+            d.chan_partials = partials.data_ptr()
+        self.call("paif_conv_forward", ctypes.byref(d))
+        return out, pre, act2, partials
+
+    def add(self, a, b, c=None):
+        out = torch.empty_like(a)
+        self.call("paif_add_maps", a.data_ptr(), b.data_ptr(), _ptr(c), out.data_ptr(), a.numel())
+        return out
+
+    def add_all(self, x, extras):
+        extras = list(extras)
+        while extras:
+            take, extras = extras[:2], extras[2:]
+            x = self.add(x, take[0], take[1] if len(take) > 1 else None)
+        return x
+
+    def mask_scale(self, g, mask_src, mask_slope, scale):
+        out = torch.empty_like(g)
+        self.call("paif_mask_scale", g.data_ptr(), _ptr(mask_src), _ptr(mask_slope), scale, out.data_ptr(),
+                  g.shape[1] * 4, self.B, self.H, self.W)
+        return out
+
+    def dwconv(self, x, w, k, dil, relu_in, mask_src=None, post_res=None):
+        out = torch.empty_like(x)
+        self.call("paif_dwconv_forward", x.data_ptr(), w.data_ptr(), int(relu_in), _ptr(mask_src), _ptr(post_res),
+                  out.data_ptr(), self.C, k, dil, self.B, self.H, self.W)
+        return out
+
+
+# ----------------------------------------------------------------------------------------
+# parameter containers mirroring operations_m.py (names and construction order preserved)
+# ----------------------------------------------------------------------------------------
+class BasicConv(nn.Module):
+    """operations_m.py:114-145 (bn / relu sub-modules exist only when requested)."""
+
+    def __init__(self, in_planes, out_planes, kernel_size, dilation=1, groups=1, relu=True, bn=False, bias=False):
+        super().__init__()
+        self.out_channels = out_planes
+        self.conv = nn.Conv2d(in_planes, out_planes, kernel_size=kernel_size, stride=1,
+                              padding=basicconv_padding(kernel_size, dilation), dilation=dilation,
+                              groups=groups, bias=bias)
+        self.bn = nn.BatchNorm2d(out_planes, eps=1e-5, momentum=0.01, affine=True) if bn else None
+        self.relu = nn.PReLU() if relu else None
+
+
+class _Primitive(nn.Module):
+    max_extras = 0       # residual maps the forward epilogue can absorb
+    max_extra_add = 0    # gradient maps the backward epilogue can absorb
+
+    def forward(self, x):
+        raise RuntimeError("paif_b200 primitives run only inside Network_Fusion_Searched.forward")
+
+
+class ResidualDenseBlock(_Primitive):
+    """operations_m.py:435-449."""
+    max_extras, max_extra_add = 2, 1
+
+    def __init__(self, in_channels, kernel_size, dialtions=1, bias=False):
+        super().__init__()
+        _check_same_padding(kernel_size, dialtions, "Denseblocks")
+        self.k, self.d = kernel_size, dialtions
+        self.conv1 = BasicConv(in_channels, in_channels, kernel_size, dilation=dialtions, relu=False)
+        self.conv2 = BasicConv(in_channels * 2, in_channels, kernel_size, dilation=dialtions, relu=False)
+        self.conv3 = BasicConv(in_channels * 3, in_channels, kernel_size, dilation=dialtions, relu=False)
+        self.lrelu = nn.PReLU()
+
+    def pack(self, need_bwd):
+        k, d = self.k, self.d
+        p = {"w": [_ConvW(c.conv.weight.detach(), n, k, d)
+                   for n, c in ((1, self.conv1), (2, self.conv2), (3, self.conv3))],
+             "a": self.lrelu.weight.detach()}
+        if need_bwd:
+            p["wd"] = [_dgrad_groups(c.conv.weight.detach(), k, d) for c in (self.conv1, self.conv2, self.conv3)]
+        return p
+
+    def fwd(self, rt, p, x, extras):
+        a = p["a"]
+        x1 = rt.conv([x], p["w"][0], slope=a)[0]
+        x2 = rt.conv([x, x1], p["w"][1], slope=a)[0]
+        out, pre3, _, _ = rt.conv([x, x1, x2], p["w"][2], slope=a, post_scale=_RDB_SCALE,
+                                  post_res=[x] + list(extras), want_pre=rt.save)
+        return out, (x1, x2, pre3)
+
+    def bwd(self, rt, p, rec, g, extra_add):
+        x1, x2, pre3 = rec
+        a, wd = p["a"], p["wd"]
+        g3 = rt.mask_scale(g, pre3, a, _RDB_SCALE)
+        gxa = rt.conv([g3], wd[2][0])[0]
+        gx1a = rt.conv([g3], wd[2][1])[0]
+        g2 = rt.conv([g3], wd[2][2], mask_src=x2, mask_slope=a)[0]
+        gxb = rt.conv([g2], wd[1][0], post_res=[gxa])[0]
+        g1 = rt.conv([g2], wd[1][1], pre_res=[gx1a], mask_src=x1, mask_slope=a)[0]
+        return rt.conv([g1], wd[0][0], post_res=[gxb, g] + list(extra_add))[0]
+
+
+class DilConv(_Primitive):
+    """operations_m.py:494-506 (BN in eval mode, folded to scale/shift)."""
+    max_extras, max_extra_add = 2, 0
+
+    def __init__(self, C_in, C_out, kernel_size, dilation, affine=True):
+        super().__init__()
+        _check_same_padding(kernel_size, dilation, "DilConv")
+        self.k, self.d = kernel_size, dilation
+        self.op = nn.Sequential(
+            nn.ReLU(inplace=False),
+            BasicConv(C_in, C_out, kernel_size, dilation=dilation, relu=False, groups=C_in),
+            nn.Conv2d(C_in, C_out, kernel_size=1, padding=0, bias=False),
+            nn.BatchNorm2d(C_out, affine=affine),
+        )
+
+    def pack(self, need_bwd):
+        dw = self.op[1].conv.weight.detach()
+        C = dw.shape[0]
+        s, sh = _bn_fold(self.op[3])
+        p = {"dw": dw.reshape(C, -1).contiguous().float(), "pw": _ConvW(self.op[2].weight.detach(), 1, 1, 1),
+             "s": s, "sh": sh}
+        if need_bwd:
+            p["dw_t"] = dw.flip(-1, -2).reshape(C, -1).contiguous().float()
+            p["pw_d"] = _dgrad_groups(self.op[2].weight.detach(), 1, 1, scale=s)[0]
+        return p
+
+    def fwd(self, rt, p, x, extras):
+        t = rt.dwconv(x, p["dw"], self.k, self.d, relu_in=True)
+        out = rt.conv([t], p["pw"], ch_scale=p["s"], ch_shift=p["sh"], post_res=[x] + list(extras))[0]
+        return out, ()
+
+    def bwd(self, rt, p, rec, g, extra_add, x=None):
+        u = rt.conv([g], p["pw_d"])[0]
+        return rt.dwconv(u, p["dw_t"], self.k, self.d, relu_in=False, mask_src=x, post_res=g)
+
+
+class eca_layer(nn.Module):
+    """operations_m.py:340-367 (parameter container)."""
+
+    def __init__(self, channel, c_out, stride, k_size=3):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.conv = nn.Conv1d(1, 1, kernel_size=k_size, padding=(k_size - 1) // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+
+class ECABasicBlock(_Primitive):
+    """operations_m.py:368-393."""
+    max_extras, max_extra_add = 1, 3
+
+    def __init__(self, inplanes, planes, kernel=3, dilation=1, stride=1, reduction=64, with_norm=False):
+        super().__init__()
+        _check_same_padding(kernel, 1, "ECAattention")
+        self.k = kernel
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.conv2 = BasicConv(inplanes, inplanes, kernel, relu=False)
+        self.se = eca_layer(planes, planes, stride, k_size=kernel)
+        self.relu = nn.PReLU()
+
+    def pack(self, need_bwd):
+        p = {"w1": _ConvW(self.conv1.weight.detach(), 1, 3, 1),
+             "w2": _ConvW(self.conv2.conv.weight.detach(), 1, self.k, 1),
+             "w1d": self.se.conv.weight.detach().reshape(-1).contiguous().float(),
+             "a": self.relu.weight.detach()}
+        if need_bwd:
+            p["w1_d"] = _dgrad_groups(self.conv1.weight.detach(), 3, 1)[0]
+            p["w2_d"] = _dgrad_groups(self.conv2.conv.weight.detach(), self.k, 1)[0]
+        return p
+
+    def fwd(self, rt, p, x, extras):
+        a = p["a"]
+        x0, _, px0, _ = rt.conv([x], p["w1"], act2_slope=a)
+        o, _, _, partials = rt.conv([px0], p["w2"], want_partials=True)
+        e = torch.empty((rt.B, rt.C), device=rt.device, dtype=torch.float32)
+        rt.call("paif_eca_scale", partials.data_ptr(), partials.shape[1], p["w1d"].data_ptr(), self.k,
+                e.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        out = rt.new_map()
+        rt.call("paif_eca_apply", o.data_ptr(), x0.data_ptr(), e.data_ptr(), a.data_ptr(),
+                _ptr(extras[0]) if extras else None, out.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        return out, (x0, o, e)
+
+    def bwd(self, rt, p, rec, g, extra_add):
+        x0, o, e = rec
+        a = p["a"]
+        lib = _lib.load()
+        tiles = lib.paif_eca_bwd_tiles(rt.H, rt.W)
+        gw = rt.new_map()
+        partials = torch.empty((rt.B, tiles, rt.C), device=rt.device, dtype=torch.float32)
+        rt.call("paif_eca_bwd_pass1", g.data_ptr(), o.data_ptr(), x0.data_ptr(), e.data_ptr(), a.data_ptr(),
+                gw.data_ptr(), partials.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        gm = torch.empty((rt.B, rt.C), device=rt.device, dtype=torch.float32)
+        rt.call("paif_eca_bwd_scale", partials.data_ptr(), tiles, e.data_ptr(), p["w1d"].data_ptr(), self.k,
+                gm.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        go = rt.new_map()
+        rt.call("paif_eca_bwd_pass2", gw.data_ptr(), e.data_ptr(), gm.data_ptr(), go.data_ptr(),
+                rt.C, rt.B, rt.H, rt.W)
+        gx0 = rt.conv([go], p["w2_d"], mask_src=x0, mask_slope=a, post_res=[gw])[0]
+        return rt.conv([gx0], p["w1_d"], post_res=list(extra_add))[0]
+
+
+class ResidualModule(_Primitive):
+    """operations_m.py:451-464.  The bias-free 3x3(dil 2) and 1x1 convolutions that follow the
+    k x k convolution have no activation between them and are merged into one 3x3(dil 2)."""
+    max_extras, max_extra_add = 2, 2
+
+    def __init__(self, in_channels, kernel_size, dialtions=1, bias=False):
+        super().__init__()
+        _check_same_padding(kernel_size, dialtions, "Residualblocks")
+        self.k, self.d = kernel_size, dialtions
+        self.op = nn.Sequential(
+            BasicConv(in_channels, in_channels, kernel_size, dilation=dialtions, relu=False),
+            nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=2, dilation=2, bias=False),
+            nn.Conv2d(in_channels, in_channels, kernel_size=1, padding=0, bias=False),
+            nn.BatchNorm2d(in_channels),
+            nn.PReLU(),
+        )
+
+    def pack(self, need_bwd):
+        w0 = self.op[0].conv.weight.detach()
+        wm = torch.einsum('om,mikl->oikl', self.op[2].weight.detach()[:, :, 0, 0].double(),
+                          self.op[1].weight.detach().double()).float()
+        s, sh = _bn_fold(self.op[3])
+        p = {"w0": _ConvW(w0, 1, self.k, self.d), "wm": _ConvW(wm, 1, 3, 2), "s": s, "sh": sh,
+             "a": self.op[4].weight.detach()}
+        if need_bwd:
+            p["w0_d"] = _dgrad_groups(w0, self.k, self.d)[0]
+            p["wm_d"] = _dgrad_groups(wm, 3, 2, scale=s)[0]
+        return p
+
+    def fwd(self, rt, p, x, extras):
+        t1 = rt.conv([x], p["w0"])[0]
+        out, pre, _, _ = rt.conv([t1], p["wm"], ch_scale=p["s"], ch_shift=p["sh"], slope=p["a"],
+                                 post_res=[x] + list(extras), want_pre=rt.save)
+        return out, (pre,)
+
+    def bwd(self, rt, p, rec, g, extra_add, g_masked=None):
+        (pre,) = rec
+        gm = g_masked if g_masked is not None else rt.mask_scale(g, pre, p["a"], 1.0)
+        gt1 = rt.conv([gm], p["wm_d"])[0]
+        return rt.conv([gt1], p["w0_d"], post_res=[g] + list(extra_add))[0]
+
+
+def _not_on_path(name):
+    def make(*a, **k):
+        raise NotImplementedError(
+            "primitive %r is in the reference's OPS table (operations_m.py:9-18) but not implemented by "
+            "paif_b200 (only the shipped fusion_at genotype's primitives are)" % name)
+    return make
+
+
+# OPS, operations_m.py:9-18 (the `affine` flag is dropped there too)
+OPS = {
+    'Denseblocks': lambda C, kernel, dialtion, affine: ResidualDenseBlock(C, kernel, dialtion),
+    'Residualblocks': lambda C, kernel, dialtion, affine: ResidualModule(C, kernel, dialtion),
+    'ECAattention': lambda C, kernel, dialtion, affine: ECABasicBlock(C, C, kernel, dialtion),
+    'SPAattention': _not_on_path('SPAattention'),
+    'DilConv': lambda C, kernel, dialtion, affine: DilConv(C, C, kernel, dialtion),
+    'SepConv': _not_on_path('SepConv'),
+    'SelAttention': _not_on_path('SelAttention'),
+}
+
+
+class MixedOp(nn.Module):
+    """core/model_fusion_auto.py:397-415 (name grammar ``Name_k[_d]``)."""
+
+    def __init__(self, C, primitive):
+        super().__init__()
+        self._ops = nn.ModuleList()
+        kernel, dilation = 3, 1
+        parts = primitive.split('_')
+        name, kernel = parts[0], int(parts[1])
+        if primitive.find('attention') == -1:
+            dilation = int(parts[2])
+        self.primitive = primitive
+        self._op = OPS[name](C, kernel, dilation, False)
+
+
+class Cell_Chain(nn.Module):
+    """core/model_fusion_auto.py:418-445: out = inp + op_k(...op_1(inp)) (indices/concat unused)."""
+
+    def __init__(self, C, type, concat):
+        super().__init__()
+        op_names, indices = zip(*type)
+        assert len(op_names) == len(indices)
+        self._steps = len(op_names)
+        self._concat = concat
+        self.multiplier = len(concat)
+        self._ops = nn.ModuleList()
+        for name in op_names:
+            self._ops += [MixedOp(C, name)]
+        self._indices = indices
+
+    def pack(self, need_bwd):
+        return [m._op.pack(need_bwd) for m in self._ops]
+
+    def fwd(self, rt, packs, x, extras):
+        """returns (inp + ops(inp) + sum(extras), records)."""
+        s, recs = x, []
+        n = len(self._ops)
+        for i, m in enumerate(self._ops):
+            op = m._op
+            want = ([x] + list(extras)) if i == n - 1 else []
+            fused, rest = want[:op.max_extras], want[op.max_extras:]
+            inp = s
+            s, rec = op.fwd(rt, packs[i], s, fused)
+            if rest:
+                s = rt.add_all(s, rest)
+            recs.append((inp if rt.save else None, rec))
+        return s, recs
+
+    def bwd(self, rt, packs, recs, g):
+        """gradient w.r.t. the chain input (the chain residual included); extras' gradient is g."""
+        gs = g
+        for i in reversed(range(len(self._ops))):
+            op = self._ops[i]._op
+            inp, rec = recs[i]
+            want = [g] if i == 0 else []
+            fused, rest = want[:op.max_extra_add], want[op.max_extra_add:]
+            if isinstance(op, DilConv):
+                gs = op.bwd(rt, packs[i], rec, gs, fused, x=inp)
+            else:
+                gs = op.bwd(rt, packs[i], rec, gs, fused)
+            if rest:
+                gs = rt.add_all(gs, rest)
+        return gs
+
+
+class ChannelPool(nn.Module):
+    """2-arg ChannelPool, core/model_fusion_auto.py:1352-1355 (fused into the runtime)."""
+
+
+class spatial_attn_layer_M(nn.Module):
+    """core/model_fusion_auto.py:1358-1368."""
+
+    def __init__(self, kernel_size=5):
+        super().__init__()
+        self.compress = ChannelPool()
+        self.spatial = BasicConv(4, 1, kernel_size, relu=False)
+
+
+class Cell_Decom(nn.Module):
+    """core/model_fusion_auto.py:492-535."""
+
+    def __init__(self, C, types, concat):
+        super().__init__()
+        self._C = C
+        self.radiux = [4]
+        self.eps_list = [0.001, 0.0001]
+        self._ops_1 = nn.ModuleList()
+        self._ops_2 = nn.ModuleList()
+        self.conv1x1_lf = nn.Conv2d(C * 4, C, kernel_size=1, bias=True)
+        self.conv1x1_hf = nn.Conv2d(C * 4, C, kernel_size=1, bias=True)
+        self._steps = len(concat)
+        self.relu = nn.PReLU()      # present in the state_dict, unused by forward (reference quirk)
+        self.chain = Cell_Chain(C, types[0], concat)
+        self.chain2 = Cell_Chain(C, types[1], concat)
+
+
+def _fold_decomp_1x1(w):
+    """conv1x1(cat[LF1, LF2, z-LF1, z-LF2]) == conv1x1'(cat[LF1, LF2, z]) (core/model_fusion_auto.py:512, :533-534)."""
+    C = w.shape[0]
+    w = w.detach()[:, :, 0, 0].double()
+    wa = w[:, 0:C] - w[:, 2 * C:3 * C]
+    wb = w[:, C:2 * C] - w[:, 3 * C:4 * C]
+    wc = w[:, 2 * C:3 * C] + w[:, 3 * C:4 * C]
+    return torch.cat([wa, wb, wc], 1).float().reshape(C, 3 * C, 1, 1)
+
+
+def _merge_stem_out(w1, w2):
+    """Merge Conv(C->C/2,3x3,pad1) and Conv(C/2->1,3x3,pad1) (core/model_fusion_auto.py:615-618) into 5x5
+    stencils wm[3][3][25][C]; class (cy, cx) excludes the second conv's taps that would read its
+    zero padding: cy==0 drops dy2=-1, cy==2 drops dy2=+1 (same for x)."""
+    w1 = w1.detach().double()          # [M][C][3][3]
+    w2 = w2.detach().double()[0]       # [M][3][3]
+    C = w1.shape[1]
+    wm = torch.zeros(3, 3, 5, 5, C, dtype=torch.float64, device=w1.device)
+    for cy in range(3):
+        for cx in range(3):
+            for ty2 in range(3):
+                if (cy == 0 and ty2 == 0) or (cy == 2 and ty2 == 2):
+                    continue
+                for tx2 in range(3):
+                    if (cx == 0 and tx2 == 0) or (cx == 2 and tx2 == 2):
+                        continue
+                    # tap t = t1 + t2: rows ty2..ty2+2, cols tx2..tx2+2 of the 5x5 window
+                    contrib = torch.einsum('m,mikl->kli', w2[:, ty2, tx2], w1)
+                    wm[cy, cx, ty2:ty2 + 3, tx2:tx2 + 3] += contrib
+    return wm.reshape(3, 3, 25, C).float().contiguous()
+
+
+class Network_Fusion_Searched(nn.Module):
+    """Drop-in for core/model_fusion_auto.py:599-640."""
+
+    def __init__(self, C, criterion, genotype_feature, steps=4, multiplier=3):
+        super().__init__()
+        if C != 32:
+            raise NotImplementedError("paif_b200 kernels are built for C = 32 (the only width the reference ships)")
+        self._C = C
+        self._criterion = criterion
+        self._steps = steps
+        self._multiplier = multiplier
+        self._genotype = genotype_feature
+        self.stem_1 = nn.Sequential(nn.Conv2d(1, C, 3, padding=1, bias=False), nn.PReLU())
+        self.stem_2 = nn.Sequential(nn.Conv2d(1, C, 3, padding=1, bias=False), nn.PReLU())
+        self.stem_out = nn.Sequential(
+            nn.Conv2d(C, C // 2, 3, padding=1, bias=False),
+            nn.Conv2d(C // 2, 1, 3, padding=1, bias=False),
+            nn.PReLU(),
+        )
+        self.tanh = nn.Tanh()
+        self.spa = spatial_attn_layer_M()
+        self.decompation = Cell_Decom(C, [self._genotype.normal_1, self._genotype.normal_2],
+                                      self._genotype.normal_1_concat)
+        self.chain = Cell_Chain(C, self._genotype.normal_3, self._genotype.normal_1_concat)
+        #: 'auto' | 'direct' (exact fp32 FFMA) | 'tcgen05' (TF32 tensor cores, fp32 accumulate)
+        self.conv_engine = 'auto'
+        self._pack_cache = None
+        self.last_launches = 0
+
+    # -------------------------------------------------------------------------------------
+    def _pack_key(self, need_bwd):
+        ts = list(self.parameters()) + list(self.buffers())
+        return (need_bwd,) + tuple((t.data_ptr(), t._version) for t in ts)
+
+    def _packed(self, need_bwd):
+        key = self._pack_key(need_bwd)
+        if self._pack_cache is not None and self._pack_cache[0] == key:
+            return self._pack_cache[1]
+        if self._pack_cache is not None and self._pack_cache[0][1:] == key[1:] and self._pack_cache[0][0]:
+            return self._pack_cache[1]      # a backward-capable pack also serves forward-only calls
+        with torch.no_grad():
+            d = self.decompation
+            p = {
+                "stem_w": [s[0].weight.detach().reshape(self._C, 9).contiguous().float() for s in (self.stem_1, self.stem_2)],
+                "stem_a": [s[1].weight.detach() for s in (self.stem_1, self.stem_2)],
+                "c1x1": [_ConvW(_fold_decomp_1x1(c.weight), 3, 1, 1) for c in (d.conv1x1_lf, d.conv1x1_hf)],
+                "c1x1_b": [c.bias.detach().float().contiguous() for c in (d.conv1x1_lf, d.conv1x1_hf)],
+                "chain_ir": d.chain.pack(need_bwd), "chain_vis": d.chain2.pack(need_bwd),
+                "chain": self.chain.pack(need_bwd),
+                "spa_w": self.spa.spatial.conv.weight.detach().reshape(4, -1).contiguous().float(),
+                "spa_k": self.spa.spatial.conv.weight.shape[-1],
+                "out_wm": _merge_stem_out(self.stem_out[0].weight, self.stem_out[1].weight),
+                "out_a": self.stem_out[2].weight.detach(),
+            }
+            if need_bwd:
+                p["c1x1_d"] = [_dgrad_groups(_fold_decomp_1x1(c.weight), 1, 1) for c in (d.conv1x1_lf, d.conv1x1_hf)]
+                slopes = [t for n, t in self.named_parameters() if t.numel() == 1 and n != 'decompation.relu.weight']
+                if slopes and not bool((torch.cat([t.detach().reshape(1) for t in slopes]) > 0).all()):
+                    raise NotImplementedError("backward-to-input needs every PReLU slope > 0 "
+                                              "(masks are rebuilt from saved activations)")
+        self._pack_cache = (key, p)
+        return p
+
+    def _engine(self):
+        return {'auto': _lib.ENGINE_AUTO, 'direct': _lib.ENGINE_DIRECT, 'tcgen05': _lib.ENGINE_TCGEN05}[self.conv_engine]
+
+    # -------------------------------------------------------------------------------------
+    def _run_forward(self, ir, vis, save):
+        """ir, vis: [B,1,H,W] fp32 CUDA views (any strides).  Returns (out[B,1,H,W], saved)."""
+        B, _, H, W = ir.shape
+        p = self._packed(save)
+        rt = _Runtime(B, H, W, self._C, ir.device, self._engine(), save)
+        C = self._C
+        feats, guides = [], []
+        for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
+            f, g = rt.new_map(), rt.new_plane()
+            rt.call("paif_stem_forward", img.data_ptr(), img.stride(0), img.stride(2), img.stride(3),
+                    w.data_ptr(), a.data_ptr(), f.data_ptr(), g.data_ptr(), B, H, W)
+            feats.append(f)
+            guides.append(g)
+        d = self.decompation
+        branch_out, branch_recs = [], []
+        for i, (chain, packs) in enumerate(((d.chain, p["chain_ir"]), (d.chain2, p["chain_vis"]))):
+            lf1, lf2 = rt.new_map(), rt.new_map()
+            rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), lf1.data_ptr(),
+                    lf2.data_ptr(), C, B, H, W)
+            x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i])[0]
+            del lf1, lf2
+            o, recs = chain.fwd(rt, packs, x, [feats[i]])
+            branch_out.append(o)
+            branch_recs.append(recs)
+        a_f, v_f = branch_out
+        pooled = rt.new_plane(4)
+        rt.call("paif_channel_pool", a_f.data_ptr(), v_f.data_ptr(), pooled.data_ptr(), C, B, H, W)
+        agg = rt.new_map()
+        scale = rt.new_plane() if save else None
+        rt.call("paif_spa_blend_forward", pooled.data_ptr(), p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(),
+                v_f.data_ptr(), agg.data_ptr(), _ptr(scale), C, B, H, W)
+        f2, recs3 = self.chain.fwd(rt, p["chain"], agg, [])
+        out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
+        pre_out = rt.new_plane() if save else None
+        rt.call("paif_out_forward", f2.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(), out.data_ptr(),
+                _ptr(pre_out), C, B, H, W)
+        self.last_launches = rt.launches
+        saved = None
+        if save:
+            saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
+                         scale=scale, recs3=recs3, out=out, pre_out=pre_out, packed=p)
+        return out, saved
+
+    def _run_backward(self, saved, g):
+        """g: [B,1,H,W] contiguous fp32.  Returns (g_ir, g_vis) as [B,H,W] planes."""
+        B, H, W, C = saved["B"], saved["H"], saved["W"], self._C
+        p = saved["packed"]
+        rt = _Runtime(B, H, W, C, g.device, self._engine(), False)
+        # stem_out + tanh; if the last op of the final chain is a ResidualModule its PReLU' mask is fused here
+        gf2 = rt.new_map()
+        last = self.chain._ops[-1]._op
+        gmasked = None
+        if isinstance(last, ResidualModule):
+            pre = saved["recs3"][-1][1][0]
+            gmasked = rt.new_map()
+            rt.call("paif_out_backward", g.data_ptr(), saved["out"].data_ptr(), saved["pre_out"].data_ptr(),
+                    p["out_wm"].data_ptr(), p["out_a"].data_ptr(), gf2.data_ptr(), pre.data_ptr(),
+                    p["chain"][-1]["a"].data_ptr(), gmasked.data_ptr(), C, B, H, W)
+        else:
+            rt.call("paif_out_backward", g.data_ptr(), saved["out"].data_ptr(), saved["pre_out"].data_ptr(),
+                    p["out_wm"].data_ptr(), p["out_a"].data_ptr(), gf2.data_ptr(), None, None, None, C, B, H, W)
+        g_agg = self._chain3_bwd(rt, p, saved, gf2, gmasked)
+        a_f, v_f, scale = saved["a_f"], saved["v_f"], saved["scale"]
+        gpre = rt.new_plane()
+        rt.call("paif_spa_blend_backward_pre", g_agg.data_ptr(), a_f.data_ptr(), v_f.data_ptr(), scale.data_ptr(),
+                gpre.data_ptr(), C, B, H, W)
+        g_a, g_v = rt.new_map(), rt.new_map()
+        rt.call("paif_spa_blend_backward", g_agg.data_ptr(), a_f.data_ptr(), v_f.data_ptr(), scale.data_ptr(),
+                gpre.data_ptr(), p["spa_w"].data_ptr(), p["spa_k"], g_a.data_ptr(), g_v.data_ptr(), C, B, H, W)
+        d = self.decompation
+        grads = []
+        for i, (chain, packs, gb) in enumerate(((d.chain, p["chain_ir"], g_a), (d.chain2, p["chain_vis"], g_v))):
+            gx = chain.bwd(rt, packs, saved["branch_recs"][i], gb)      # grad w.r.t. the 1x1 conv output
+            wd = p["c1x1_d"][i]
+            glf1 = rt.conv([gx], wd[0])[0]
+            glf2 = rt.conv([gx], wd[1])[0]
+            gz = rt.conv([gx], wd[2])[0]
+            gfeat = rt.new_map()
+            gres = torch.empty((C // 4, B, H, W), device=g.device, dtype=torch.float32)
+            rt.call("paif_gf_decomp_backward", saved["feats"][i].data_ptr(), saved["guides"][i].data_ptr(),
+                    glf1.data_ptr(), glf2.data_ptr(), gfeat.data_ptr(), gres.data_ptr(), C, B, H, W)
+            gstem = rt.new_map()
+            rt.call("paif_stem_backward_pre", saved["feats"][i].data_ptr(), p["stem_a"][i].data_ptr(),
+                    gb.data_ptr(), gz.data_ptr(), gfeat.data_ptr(), None, gres.data_ptr(), gstem.data_ptr(),
+                    C, B, H, W)
+            gimg = rt.new_plane()
+            rt.call("paif_stem_backward", gstem.data_ptr(), p["stem_w"][i].data_ptr(), gimg.data_ptr(), C, B, H, W)
+            grads.append(gimg)
+        self.last_launches = rt.launches
+        return grads[0], grads[1]
+
+    def _chain3_bwd(self, rt, p, saved, gf2, gmasked):
+        chain, packs, recs = self.chain, p["chain"], saved["recs3"]
+        if gmasked is None:
+            return chain.bwd(rt, packs, recs, gf2)
+        # same as Cell_Chain.bwd, with the fused mask handed to the trailing ResidualModule
+        gs = gf2
+        n = len(chain._ops)
+        for i in reversed(range(n)):
+            op = chain._ops[i]._op
+            inp, rec = recs[i]
+            want = [gf2] if i == 0 else []
+            fused, rest = want[:op.max_extra_add], want[op.max_extra_add:]
+            if i == n - 1:
+                gs = op.bwd(rt, packs[i], rec, gs, fused, g_masked=gmasked)
+            elif isinstance(op, DilConv):
+                gs = op.bwd(rt, packs[i], rec, gs, fused, x=inp)
+            else:
+                gs = op.bwd(rt, packs[i], rec, gs, fused)
+            if rest:
+                gs = rt.add_all(gs, rest)
+        return gs
+
+    # -------------------------------------------------------------------------------------
+    def forward(self, ir, vis):
+        if self.training:
+            raise RuntimeError("paif_b200.Network_Fusion_Searched supports eval() mode only (BatchNorm batch "
+                               "statistics are out of scope; the reference scripts always call .eval())")
+        if not (ir.is_cuda and vis.is_cuda):
+            raise RuntimeError("paif_b200 has no CPU path: inputs must be CUDA tensors")
+        if next(self.parameters()).device != ir.device:
+            raise RuntimeError("module parameters and inputs live on different devices")
+        if ir.dim() != 4 or vis.dim() != 4 or ir.shape[0] != vis.shape[0] or ir.shape[2:] != vis.shape[2:]:
+            raise ValueError("expected ir [B,>=1,H,W] and vis [B,>=1,H,W] of the same batch and size")
+        if ir.shape[2] <= 9 or ir.shape[3] <= 9:
+            raise AssertionError("guided filter (radius 4) needs H, W > 9")
+        if ir.dtype != torch.float32:
+            ir = ir.float()
+        if vis.dtype != torch.float32:
+            vis = vis.float()
+        with torch.cuda.device(ir.device):
+            return _FusionFn.apply(ir, vis, self)
+
+    def _loss(self, ir, vis, mask):
+        logits = self(ir, vis)
+        return self._criterion(ir, vis, logits, mask)
+
+
+class _FusionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ir, vis, net):
+        need = torch.is_grad_enabled() and (ir.requires_grad or vis.requires_grad)
+        out, saved = net._run_forward(ir[:, 0:1], vis[:, 0:1], need)
+        ctx.net, ctx.saved = net, saved
+        ctx.shapes = (ir.shape, vis.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        net, saved = ctx.net, ctx.saved
+        if saved is None:
+            return None, None, None
+        g = g.contiguous().float()
+        with torch.cuda.device(g.device):
+            g_ir, g_vis = net._run_backward(saved, g)
+        ctx.saved = None
+        outs = []
+        for gi, shape, need in ((g_ir, ctx.shapes[0], ctx.needs_input_grad[0]),
+                                (g_vis, ctx.shapes[1], ctx.needs_input_grad[1])):
+            if not need:
+                outs.append(None)
+            elif shape[1] == 1:
+                outs.append(gi.view(shape))
+            else:
+                full = torch.zeros(shape, device=gi.device, dtype=gi.dtype)
+                full[:, 0] = gi
+                outs.append(full)
+        return outs[0], outs[1], None

@@ -1,0 +1,153 @@
+"""GPU: each CUDA kernel, called through the C ABI, against the CPU oracle / plain torch fp32 ops
+on small seeded inputs (ragged sizes on purpose: not multiples of any tile)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fusion_oracle as fo
+from paif_b200 import _lib, fusion
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def to_c4(t):
+    B, C, H, W = t.shape
+    return t.reshape(B, C // 4, 4, H, W).permute(0, 1, 3, 4, 2).contiguous()
+
+
+def from_c4(t):
+    B, Q, H, W, _ = t.shape
+    return t.permute(0, 1, 4, 2, 3).reshape(B, Q * 4, H, W)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rt(B, H, W, engine=_lib.ENGINE_DIRECT, save=False):
+    return fusion._Runtime(B, H, W, 32, torch.device(DEV), engine, save)
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 56), (1, 33, 47), (1, 11, 130)])
+def test_stem_and_residue(shape):
+    B, H, W = shape
+    torch.manual_seed(0)
+    img = torch.rand(B, 3, H, W)
+    w = torch.randn(32, 1, 3, 3) * 0.3
+    a = torch.tensor([0.2])
+    ref = F.prelu(F.conv2d(img[:, 0:1], w, None, 1, 1), a)
+    ref_res = fo.get_residue(ref)
+    v = img.to(DEV).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)[:, 0:1]   # strided view
+    feat = torch.empty(B, 8, H, W, 4, device=DEV)
+    res = torch.empty(B, H, W, device=DEV)
+    _lib.call("paif_stem_forward", v.data_ptr(), v.stride(0), v.stride(2), v.stride(3),
+              w.to(DEV).reshape(32, 9).contiguous().data_ptr(), a.to(DEV).data_ptr(),
+              feat.data_ptr(), res.data_ptr(), B, H, W, stream())
+    assert (from_c4(feat).cpu() - ref).abs().max().item() < 1e-5
+    assert (res.cpu() - ref_res[:, 0]).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("shape,smooth", [((2, 40, 56), False), ((1, 33, 47), True), ((1, 10, 70), False)])
+def test_guided_filter_decomposition(shape, smooth):
+    B, H, W = shape
+    torch.manual_seed(1)
+    z = torch.rand(B, 32, H, W)
+    if smooth:
+        z = F.avg_pool2d(z, 9, 1, 4)
+    res = fo.get_residue(z)
+    LF, _ = fo.decomposition(z)
+    zc = to_c4(z).to(DEV)
+    lf1, lf2 = torch.empty_like(zc), torch.empty_like(zc)
+    _lib.call("paif_gf_decomp_forward", zc.data_ptr(), res[:, 0].contiguous().to(DEV).data_ptr(),
+              lf1.data_ptr(), lf2.data_ptr(), 32, B, H, W, stream())
+    e1 = (from_c4(lf1).cpu() - LF[:, :32]).abs().max().item()
+    e2 = (from_c4(lf2).cpu() - LF[:, 32:]).abs().max().item()
+    assert e1 < 2e-5 and e2 < 2e-5, (e1, e2)
+
+
+@pytest.mark.parametrize("k,dil,nsrc", [(3, 1, 1), (3, 1, 3), (3, 2, 1), (7, 1, 1), (1, 1, 3), (5, 2, 2)])
+def test_conv_direct_with_epilogue(k, dil, nsrc):
+    B, H, W = 2, 21, 139
+    torch.manual_seed(2)
+    xs = [torch.randn(B, 32, H, W) for _ in range(nsrc)]
+    w = torch.randn(32, 32 * nsrc, k, k) * 0.1
+    cs, sh = torch.rand(32) + 0.5, torch.randn(32) * 0.1
+    a = torch.tensor([0.3])
+    r1, r2 = torch.randn(B, 32, H, W), torch.randn(B, 32, H, W)
+    pad = dil * (k - 1) // 2
+    pre = F.conv2d(torch.cat(xs, 1), w, None, 1, pad, dil) * cs.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    ref = F.prelu(pre, a) * 0.5 + r1 + r2
+    r = rt(B, H, W, save=True)
+    cw = fusion._ConvW(w.to(DEV), nsrc, k, dil)
+    out, opre, act2, parts = r.conv([to_c4(x).to(DEV) for x in xs], cw, ch_scale=cs.to(DEV), ch_shift=sh.to(DEV),
+                                    slope=a.to(DEV), post_scale=0.5, post_res=[to_c4(r1).to(DEV), to_c4(r2).to(DEV)],
+                                    want_pre=True, act2_slope=a.to(DEV), want_partials=True)
+    tol = 2e-4 if k == 7 else 5e-5
+    assert (from_c4(out).cpu() - ref).abs().max().item() < tol
+    assert (from_c4(opre).cpu() - pre).abs().max().item() < tol
+    assert (from_c4(act2).cpu() - F.prelu(ref, a)).abs().max().item() < tol
+    sums = parts.sum(1).cpu()
+    assert (sums - ref.sum((2, 3))).abs().max().item() < 2e-2
+
+
+def test_conv_direct_backward_style_epilogue():
+    B, H, W = 1, 17, 40
+    torch.manual_seed(3)
+    x = torch.randn(B, 32, H, W)
+    w = torch.randn(32, 32, 3, 3) * 0.1
+    p1, m = torch.randn(B, 32, H, W), torch.randn(B, 32, H, W)
+    a = torch.tensor([0.25])
+    ref = (F.conv2d(x, w, None, 1, 1) + p1) * torch.where(m > 0, torch.ones_like(m), a.expand_as(m))
+    r = rt(B, H, W)
+    out = r.conv([to_c4(x).to(DEV)], fusion._ConvW(w.to(DEV), 1, 3, 1), pre_res=[to_c4(p1).to(DEV)],
+                 mask_src=to_c4(m).to(DEV), mask_slope=a.to(DEV))[0]
+    assert (from_c4(out).cpu() - ref).abs().max().item() < 5e-5
+
+
+def test_dwconv_pool_spa_out():
+    B, H, W = 2, 19, 45
+    torch.manual_seed(4)
+    x, y = torch.randn(B, 32, H, W), torch.randn(B, 32, H, W)
+    r = rt(B, H, W)
+    # depthwise dilated conv with ReLU on the input
+    wd = torch.randn(32, 1, 3, 3)
+    ref = F.conv2d(F.relu(x), wd, None, 1, 2, 2, groups=32)
+    got = r.dwconv(to_c4(x).to(DEV), wd.reshape(32, 9).to(DEV), 3, 2, True)
+    assert (from_c4(got).cpu() - ref).abs().max().item() < 1e-5
+    # channel pool + spatial attention + blend
+    sd = {"spa.spatial.conv.weight": torch.randn(1, 4, 5, 5) * 0.2}
+    s = fo.spatial_attn(sd, x, y)
+    ref = s * x + (1 - s) * y
+    xc, yc = to_c4(x).to(DEV), to_c4(y).to(DEV)
+    pooled = torch.empty(B, H, W, 4, device=DEV)
+    _lib.call("paif_channel_pool", xc.data_ptr(), yc.data_ptr(), pooled.data_ptr(), 32, B, H, W, stream())
+    agg, sc = torch.empty_like(xc), torch.empty(B, H, W, device=DEV)
+    _lib.call("paif_spa_blend_forward", pooled.data_ptr(),
+              sd["spa.spatial.conv.weight"].reshape(4, 25).to(DEV).data_ptr(), 5, xc.data_ptr(), yc.data_ptr(),
+              agg.data_ptr(), sc.data_ptr(), 32, B, H, W, stream())
+    assert (sc.cpu() - s[:, 0]).abs().max().item() < 1e-5
+    assert (from_c4(agg).cpu() - ref).abs().max().item() < 1e-5
+    # merged stem_out + PReLU + tanh
+    w1, w2, a = torch.randn(16, 32, 3, 3) * 0.1, torch.randn(1, 16, 3, 3) * 0.1, torch.tensor([0.25])
+    ref = torch.tanh(F.prelu(F.conv2d(F.conv2d(x, w1, None, 1, 1), w2, None, 1, 1), a))
+    wm = fusion._merge_stem_out(w1, w2).to(DEV)
+    out, pre = torch.empty(B, 1, H, W, device=DEV), torch.empty(B, H, W, device=DEV)
+    _lib.call("paif_out_forward", xc.data_ptr(), wm.data_ptr(), a.to(DEV).data_ptr(), out.data_ptr(),
+              pre.data_ptr(), 32, B, H, W, stream())
+    assert (out.cpu() - ref).abs().max().item() < 2e-5
+
+
+def test_confusion_matrix_kernel_is_exact():
+    g = torch.Generator().manual_seed(5)
+    label = torch.randint(0, 10, (3, 97, 131), generator=g)
+    label[0, :5] = 255                                          # ignore_index of the loss
+    pred = torch.randint(0, 9, (3, 97, 131), generator=g)
+    ref = fo.confusion_matrix(label, pred, 9)
+    conf = torch.zeros(9, 9, dtype=torch.int64, device=DEV)
+    for _ in range(2):
+        _lib.call("paif_confusion_accumulate", label.to(DEV).data_ptr(), pred.to(DEV).data_ptr(), label.numel(), 9,
+                  conf.data_ptr(), stream())
+    assert torch.equal(conf.cpu(), 2 * ref)

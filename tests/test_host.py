@@ -1,0 +1,126 @@
+"""CPU: host-side logic of the drop-in — state_dict compatibility, default-init equality with the
+reference, weight folding algebra, C-ABI library loads and exports every declared symbol."""
+import ctypes
+import io
+import contextlib
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import paif_b200
+from paif_b200 import _lib, fusion
+from paif_testutil import ROOT, load_golden
+
+
+def _net(seed=0):
+    torch.manual_seed(seed)
+    return paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    ref_sd = load_golden("seed0_default_2x40x56")["state_dict"]
+    sd = _net().state_dict()
+    assert list(sd.keys()) == list(ref_sd.keys())
+    for k in sd:
+        assert sd[k].shape == ref_sd[k].shape and sd[k].dtype == ref_sd[k].dtype, k
+
+
+def test_default_init_is_bitwise_the_reference_init():
+    # same module tree and construction order => same RNG stream as core/model_fusion_auto.py:600-623
+    ref_sd = load_golden("seed0_default_2x40x56")["state_dict"]
+    sd = _net(0).state_dict()
+    for k in sd:
+        assert torch.equal(sd[k], ref_sd[k]), k
+
+
+def test_reference_checkpoint_loads_strict():
+    g = load_golden("seed1_random_1x48x72")
+    net = _net(5)
+    net.load_state_dict(g["state_dict"], strict=True)
+
+
+def test_ctor_contract():
+    net = _net()
+    assert net._C == 32 and net._steps == 4 and net._multiplier == 3 and net._criterion is None
+    assert hasattr(net, "_loss") and len(list(net.parameters())) == 39
+    with pytest.raises(NotImplementedError):
+        paif_b200.Network_Fusion_Searched(16, None, paif_b200.fusion_at)
+    bad = paif_b200.fusion_at._replace(normal_3=[('SepConv_3_1', 0)])
+    with pytest.raises(NotImplementedError):
+        paif_b200.Network_Fusion_Searched(32, None, bad)
+
+
+def test_no_cpu_path_and_eval_only():
+    net = _net()
+    x = torch.rand(1, 1, 16, 16)
+    with pytest.raises(RuntimeError):
+        net(x, x)                    # training mode
+    net.eval()
+    with pytest.raises(RuntimeError):
+        net(x, x)                    # CPU tensors
+
+
+def test_decomp_1x1_fold_is_exact():
+    torch.manual_seed(0)
+    w = torch.randn(32, 128, 1, 1, dtype=torch.float64)
+    lf1, lf2, z = (torch.randn(2, 32, 5, 7, dtype=torch.float64) for _ in range(3))
+    ref = F.conv2d(torch.cat([lf1, lf2, z - lf1, z - lf2], 1), w)
+    got = F.conv2d(torch.cat([lf1, lf2, z], 1), fusion._fold_decomp_1x1(w.float()).double())
+    assert (ref - got).abs().max().item() < 1e-5
+
+
+def test_stem_out_merge_matches_two_padded_convs():
+    torch.manual_seed(0)
+    w1 = torch.randn(16, 32, 3, 3)
+    w2 = torch.randn(1, 16, 3, 3)
+    x = torch.randn(1, 32, 9, 11, dtype=torch.float64)
+    ref = F.conv2d(F.conv2d(x, w1.double(), None, 1, 1), w2.double(), None, 1, 1)[0, 0]
+    wm = fusion._merge_stem_out(w1, w2).double().reshape(3, 3, 5, 5, 32)
+    xp = F.pad(x, (2, 2, 2, 2))[0]
+    H, W = 9, 11
+    got = torch.zeros(H, W, dtype=torch.float64)
+    for y in range(H):
+        for xx in range(W):
+            cy = 0 if y == 0 else (2 if y == H - 1 else 1)
+            cx = 0 if xx == 0 else (2 if xx == W - 1 else 1)
+            win = xp[:, y:y + 5, xx:xx + 5]                      # [C,5,5]
+            got[y, xx] = (win.permute(1, 2, 0) * wm[cy, cx]).sum()
+    assert (ref - got).abs().max().item() < 1e-4
+
+
+def test_dgrad_groups_are_the_conv_transpose():
+    torch.manual_seed(0)
+    w = torch.randn(32, 64, 3, 3, dtype=torch.float64)
+    x = torch.randn(1, 64, 8, 9, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, None, 1, 2, 2)
+    g = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, g)
+    groups = fusion._dgrad_groups(w.float(), 3, 2)
+    for gi, cw in enumerate(groups):
+        # unpack direct layout [1][taps][cin][cout] back to OIHW and run it as a forward conv
+        wd = cw.direct[0].double().permute(2, 1, 0).reshape(32, 32, 3, 3)
+        got = F.conv2d(g, wd, None, 1, 2, 2)
+        assert (got - gx[:, 32 * gi:32 * gi + 32]).abs().max().item() < 1e-4
+
+
+def test_install_rebinds_reference_symbol():
+    import types
+    m = types.ModuleType("fake_core_model_fusion_auto")
+    m.Network_Fusion_Searched = object
+    paif_b200.install(m)
+    assert m.Network_Fusion_Searched is paif_b200.Network_Fusion_Searched
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "paif_b200.h")).read()
+    declared = set(re.findall(r"\b(paif_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), "library lacks %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.paif_abi_version() == 1
+    assert ctypes.sizeof(_lib.ConvDesc) > 0
