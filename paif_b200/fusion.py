@@ -82,6 +82,8 @@ class _Runtime:
         self.save = save
         self.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         self.launches = 0
+        self.profile = None          # optional list: (name, meta, start_event, end_event) per launch
+        self._meta = None
 
     # buffers ---------------------------------------------------------------------------
     def new_map(self, C=None):
@@ -94,7 +96,15 @@ class _Runtime:
 
     def call(self, name, *args):
         self.launches += 1
+        if self.profile is None:
+            _lib.call(name, *args, self.stream)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         _lib.call(name, *args, self.stream)
+        e1.record()
+        self.profile.append((name, self._meta, e0, e1))
+        self._meta = None
 
     # kernels ---------------------------------------------------------------------------
     def conv(self, srcs, cw, *, ch_scale=None, ch_shift=None, pre_res=(), want_pre=False, mask_src=None,
@@ -135,6 +145,8 @@ class _Runtime:
             tiles = _lib.load().paif_conv_num_tiles(self.H, self.W, engine)
             partials = torch.empty((self.B, tiles, cw.cout), device=self.device, dtype=torch.float32)
             d.chan_partials = partials.data_ptr()
+        self._meta = {"k": cw.k, "dil": cw.dil, "cin": cw.nsrc * cw.cps, "cout": cw.cout, "engine": engine,
+                      "flops": 2.0 * cw.cout * cw.nsrc * cw.cps * cw.k * cw.k * self.B * self.H * self.W}
         self.call("paif_conv_forward", ctypes.byref(d))
         return out, pre, act2, partials
 
@@ -547,6 +559,8 @@ class Network_Fusion_Searched(nn.Module):
         self.conv_engine = 'auto'
         self._pack_cache = None
         self.last_launches = 0
+        #: set to a list to collect (name, meta, start_event, end_event) for every kernel launch
+        self.profile = None
 
     # -------------------------------------------------------------------------------------
     def _pack_key(self, need_bwd):
@@ -591,6 +605,7 @@ class Network_Fusion_Searched(nn.Module):
         B, _, H, W = ir.shape
         p = self._packed(save)
         rt = _Runtime(B, H, W, self._C, ir.device, self._engine(), save)
+        rt.profile = self.profile
         C = self._C
         feats, guides = [], []
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
@@ -634,6 +649,7 @@ class Network_Fusion_Searched(nn.Module):
         B, H, W, C = saved["B"], saved["H"], saved["W"], self._C
         p = saved["packed"]
         rt = _Runtime(B, H, W, C, g.device, self._engine(), False)
+        rt.profile = self.profile
         # stem_out + tanh; if the last op of the final chain is a ResidualModule its PReLU' mask is fused here
         gf2 = rt.new_map()
         last = self.chain._ops[-1]._op
@@ -727,7 +743,7 @@ class Network_Fusion_Searched(nn.Module):
 class _FusionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ir, vis, net):
-        need = torch.is_grad_enabled() and (ir.requires_grad or vis.requires_grad)
+        need = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])   # False under no_grad
         out, saved = net._run_forward(ir[:, 0:1], vis[:, 0:1], need)
         ctx.net, ctx.saved = net, saved
         ctx.shapes = (ir.shape, vis.shape)

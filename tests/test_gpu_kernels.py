@@ -43,9 +43,9 @@ def test_stem_and_residue(shape):
     v = img.to(DEV).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)[:, 0:1]   # strided view
     feat = torch.empty(B, 8, H, W, 4, device=DEV)
     res = torch.empty(B, H, W, device=DEV)
+    wd, ad = w.to(DEV).reshape(32, 9).contiguous(), a.to(DEV)      # keep alive: raw pointers below
     _lib.call("paif_stem_forward", v.data_ptr(), v.stride(0), v.stride(2), v.stride(3),
-              w.to(DEV).reshape(32, 9).contiguous().data_ptr(), a.to(DEV).data_ptr(),
-              feat.data_ptr(), res.data_ptr(), B, H, W, stream())
+              wd.data_ptr(), ad.data_ptr(), feat.data_ptr(), res.data_ptr(), B, H, W, stream())
     assert (from_c4(feat).cpu() - ref).abs().max().item() < 1e-5
     assert (res.cpu() - ref_res[:, 0]).abs().max().item() < 1e-5
 
@@ -58,14 +58,19 @@ def test_guided_filter_decomposition(shape, smooth):
     if smooth:
         z = F.avg_pool2d(z, 9, 1, 4)
     res = fo.get_residue(z)
-    LF, _ = fo.decomposition(z)
+    LF, _ = fo.decomposition(z)                      # fp32 oracle (cumsum box filter, as the reference)
+    LF64, _ = fo.decomposition(z.double())           # same algorithm in fp64: the exact answer
     zc = to_c4(z).to(DEV)
     lf1, lf2 = torch.empty_like(zc), torch.empty_like(zc)
-    _lib.call("paif_gf_decomp_forward", zc.data_ptr(), res[:, 0].contiguous().to(DEV).data_ptr(),
+    resd = res[:, 0].contiguous().to(DEV)
+    _lib.call("paif_gf_decomp_forward", zc.data_ptr(), resd.data_ptr(),
               lf1.data_ptr(), lf2.data_ptr(), 32, B, H, W, stream())
-    e1 = (from_c4(lf1).cpu() - LF[:, :32]).abs().max().item()
-    e2 = (from_c4(lf2).cpu() - LF[:, 32:]).abs().max().item()
-    assert e1 < 2e-5 and e2 < 2e-5, (e1, e2)
+    got = torch.cat([from_c4(lf1), from_c4(lf2)], 1).cpu()
+    e32 = (got - LF).abs().max().item()
+    e64 = (got.double() - LF64).abs().max().item()
+    ref_noise = (LF.double() - LF64).abs().max().item()          # the fp32 reference's own rounding error
+    assert e32 < 1e-4, e32
+    assert e64 < max(2e-5, 2 * ref_noise), (e64, ref_noise)
 
 
 @pytest.mark.parametrize("k,dil,nsrc", [(3, 1, 1), (3, 1, 3), (3, 2, 1), (7, 1, 1), (1, 1, 3), (5, 2, 2)])
@@ -125,8 +130,8 @@ def test_dwconv_pool_spa_out():
     pooled = torch.empty(B, H, W, 4, device=DEV)
     _lib.call("paif_channel_pool", xc.data_ptr(), yc.data_ptr(), pooled.data_ptr(), 32, B, H, W, stream())
     agg, sc = torch.empty_like(xc), torch.empty(B, H, W, device=DEV)
-    _lib.call("paif_spa_blend_forward", pooled.data_ptr(),
-              sd["spa.spatial.conv.weight"].reshape(4, 25).to(DEV).data_ptr(), 5, xc.data_ptr(), yc.data_ptr(),
+    wspa = sd["spa.spatial.conv.weight"].reshape(4, 25).to(DEV)
+    _lib.call("paif_spa_blend_forward", pooled.data_ptr(), wspa.data_ptr(), 5, xc.data_ptr(), yc.data_ptr(),
               agg.data_ptr(), sc.data_ptr(), 32, B, H, W, stream())
     assert (sc.cpu() - s[:, 0]).abs().max().item() < 1e-5
     assert (from_c4(agg).cpu() - ref).abs().max().item() < 1e-5
@@ -135,7 +140,8 @@ def test_dwconv_pool_spa_out():
     ref = torch.tanh(F.prelu(F.conv2d(F.conv2d(x, w1, None, 1, 1), w2, None, 1, 1), a))
     wm = fusion._merge_stem_out(w1, w2).to(DEV)
     out, pre = torch.empty(B, 1, H, W, device=DEV), torch.empty(B, H, W, device=DEV)
-    _lib.call("paif_out_forward", xc.data_ptr(), wm.data_ptr(), a.to(DEV).data_ptr(), out.data_ptr(),
+    ad = a.to(DEV)
+    _lib.call("paif_out_forward", xc.data_ptr(), wm.data_ptr(), ad.data_ptr(), out.data_ptr(),
               pre.data_ptr(), 32, B, H, W, stream())
     assert (out.cpu() - ref).abs().max().item() < 2e-5
 
@@ -147,7 +153,8 @@ def test_confusion_matrix_kernel_is_exact():
     pred = torch.randint(0, 9, (3, 97, 131), generator=g)
     ref = fo.confusion_matrix(label, pred, 9)
     conf = torch.zeros(9, 9, dtype=torch.int64, device=DEV)
+    ld, pd = label.to(DEV), pred.to(DEV)
     for _ in range(2):
-        _lib.call("paif_confusion_accumulate", label.to(DEV).data_ptr(), pred.to(DEV).data_ptr(), label.numel(), 9,
+        _lib.call("paif_confusion_accumulate", ld.data_ptr(), pd.data_ptr(), label.numel(), 9,
                   conf.data_ptr(), stream())
     assert torch.equal(conf.cpu(), 2 * ref)
