@@ -72,7 +72,8 @@ struct GfSmem {
     float out[2][GF_T * GF_T * 4];        // LF1 / LF2, [pixel][4 channels]
 };
 
-__device__ __forceinline__ void gf_load_region(GfSmem& s, const float* feat, const float* residue,
+template <class S>
+__device__ __forceinline__ void gf_load_region(S& s, const float* feat, const float* residue,
                                                int b, int q, int Q, int H, int W, int x0, int y0) {
     const size_t plane = (size_t)H * W;
     const float4* zp = reinterpret_cast<const float4*>(feat) + ((size_t)b * Q + q) * plane;
@@ -92,7 +93,8 @@ __device__ __forceinline__ void gf_load_region(GfSmem& s, const float* feat, con
 }
 
 // mean_g, 1/(var+eps) on the 40x40 region (zero outside the image).
-__device__ __forceinline__ void gf_guide_stats(GfSmem& s, int H, int W, int x0, int y0) {
+template <class S>
+__device__ __forceinline__ void gf_guide_stats(S& s, int H, int W, int x0, int y0) {
     box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&s.g[r * GF_R8 + c]); },
           s.tmp, GF_R4, GF_R8, GF_R4);
     __syncthreads();
@@ -125,7 +127,8 @@ __device__ __forceinline__ void gf_guide_stats(GfSmem& s, int H, int W, int x0, 
 }
 
 // A1,b1,A2,b2 of channel ch on the 40x40 region -> s.ab (zero outside the image); also s.mz.
-__device__ __forceinline__ void gf_channel_ab(GfSmem& s, int ch, int H, int W, int x0, int y0) {
+template <class S>
+__device__ __forceinline__ void gf_channel_ab(S& s, int ch, int H, int W, int x0, int y0) {
     const float* z = s.z[ch];
     box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&z[r * GF_R8 + c]); },
           s.tmp, GF_R4, GF_R8, GF_R4);
@@ -206,6 +209,179 @@ gf_forward_kernel(const float* __restrict__ feat, const float* __restrict__ resi
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// adjoint (SURVEY.md 8a "Guided-filter adjoint"; checked there against autograd in fp64)
+// ------------------------------------------------------------------------------------------
+struct GfBwdSmem {
+    float g[GF_R8 * GF_R8];
+    float z[4][GF_R8 * GF_R8];
+    float tmp[GF_R8 * GF_R4];
+    float mx[GF_R4 * GF_R4];
+    float iv1[GF_R4 * GF_R4];
+    float iv2[GF_R4 * GF_R4];
+    float mz[GF_R4 * GF_R4];
+    float ab[4][GF_R4 * GF_R4];      // A1, b1, A2, b2 (forward recompute)
+    float gl[2][GF_R8 * GF_R8];      // incoming dL/dLF_eps of the current channel
+    float gab[4][GF_R4 * GF_R4];     // dL/dA1', dL/db1, dL/dA2', dL/db2 ; slots 0/1 reused for g_cov/N, g_my/N
+    float gvar[GF_R4 * GF_R4];
+    float gmx[GF_R4 * GF_R4];
+    float gx[GF_T * GF_T];           // guide gradient accumulated over this quad's channels
+    float gy[GF_T * GF_T * 4];
+};
+
+__device__ __forceinline__ float f4_get(const float4& v, int j) {
+    return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+}
+
+__global__ void __launch_bounds__(GF_NT)
+gf_backward_kernel(const float* __restrict__ feat, const float* __restrict__ residue,
+                   const float* __restrict__ glf1, const float* __restrict__ glf2,
+                   float* __restrict__ gfeat, float* __restrict__ gres_partial, int Q, int B, int H, int W) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GfBwdSmem& s = *reinterpret_cast<GfBwdSmem*>(smem_raw);
+    const int x0 = blockIdx.x * GF_T, y0 = blockIdx.y * GF_T;
+    const int q = blockIdx.z % Q, b = blockIdx.z / Q;
+    const size_t plane = (size_t)H * W;
+
+    gf_load_region(s, feat, residue, b, q, Q, H, W, x0, y0);
+    for (int i = threadIdx.x; i < GF_R4 * GF_R4; i += GF_NT) { s.gvar[i] = 0.f; s.gmx[i] = 0.f; }
+    for (int i = threadIdx.x; i < GF_T * GF_T; i += GF_NT) s.gx[i] = 0.f;
+    __syncthreads();
+    gf_guide_stats(s, H, W, x0, y0);
+
+    const float4* g1p = reinterpret_cast<const float4*>(glf1) + ((size_t)b * Q + q) * plane;
+    const float4* g2p = reinterpret_cast<const float4*>(glf2) + ((size_t)b * Q + q) * plane;
+
+    for (int ch = 0; ch < 4; ++ch) {
+        gf_channel_ab(s, ch, H, W, x0, y0);
+        for (int i = threadIdx.x; i < GF_R8 * GF_R8; i += GF_NT) {
+            const int r = i / GF_R8, c = i - r * GF_R8;
+            const int y = y0 - 8 + r, x = x0 - 8 + c;
+            float a = 0.f, d = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                a = f4_get(g1p[(size_t)y * W + x], ch);
+                d = f4_get(g2p[(size_t)y * W + x], ch);
+            }
+            s.gl[0][i] = a; s.gl[1][i] = d;
+        }
+        __syncthreads();
+        // pointwise term sum_e gLF_e * mean_A_e on the tile
+#pragma unroll 1
+        for (int e = 0; e < 2; ++e) {
+            const float* src = s.ab[2 * e];
+            box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&src[r * GF_R4 + c]); },
+                  s.tmp, GF_T, GF_R4, GF_T);
+            __syncthreads();
+            const float* gl = s.gl[e];
+            box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) {
+                const int y = y0 + r, x = x0 + c;
+                if (y < H && x < W) {
+                    const float mA = __fdiv_rn(v, win_count(y, H) * win_count(x, W));
+                    s.gx[r * GF_T + c] += gl[(r + 8) * GF_R8 + c + 8] * mA;
+                }
+            });
+            __syncthreads();
+        }
+        // dL/dA' = box(gLF x / N), dL/db = box(gLF / N)   (N of the pixel that owns mean_A / mean_b)
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const float* gl = s.gl[k >> 1];
+            const bool withx = (k & 1) == 0;
+            box_h([&](int r, int c) {
+                      const float4 v = *reinterpret_cast<const float4*>(&gl[r * GF_R8 + c]);
+                      const float4 xg = *reinterpret_cast<const float4*>(&s.g[r * GF_R8 + c]);
+                      const int y = y0 - 8 + r, x = x0 - 8 + c;
+                      const float ny = fmaxf(win_count(y, H), 1.f);
+                      float4 o;
+                      o.x = __fdiv_rn(withx ? v.x * xg.x : v.x, ny * fmaxf(win_count(x + 0, W), 1.f));
+                      o.y = __fdiv_rn(withx ? v.y * xg.y : v.y, ny * fmaxf(win_count(x + 1, W), 1.f));
+                      o.z = __fdiv_rn(withx ? v.z * xg.z : v.z, ny * fmaxf(win_count(x + 2, W), 1.f));
+                      o.w = __fdiv_rn(withx ? v.w * xg.w : v.w, ny * fmaxf(win_count(x + 3, W), 1.f));
+                      return o;
+                  },
+                  s.tmp, GF_R4, GF_R8, GF_R4);
+            __syncthreads();
+            float* dst = s.gab[k];
+            box_v(s.tmp, GF_R4, GF_R4, GF_R4, [&](int r, int c, float v) { dst[r * GF_R4 + c] = v; });
+            __syncthreads();
+        }
+        // pointwise chain rule on the halo-4 region
+        for (int i = threadIdx.x; i < GF_R4 * GF_R4; i += GF_NT) {
+            const int r = i / GF_R4, c = i - r * GF_R4;
+            const int y = y0 - 4 + r, x = x0 - 4 + c;
+            float t = 0.f, u = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                const float mxv = s.mx[i], my = s.mz[i], A1 = s.ab[0][i], A2 = s.ab[2][i];
+                const float i1 = s.iv1[i], i2 = s.iv2[i];
+                const float gb1 = s.gab[1][i], gb2 = s.gab[3][i];
+                const float gA1 = s.gab[0][i] - gb1 * mxv, gA2 = s.gab[2][i] - gb2 * mxv;
+                const float gcov = gA1 * i1 + gA2 * i2;
+                s.gvar[i] -= gA1 * A1 * i1 + gA2 * A2 * i2;
+                const float gmy = gb1 + gb2 - gcov * mxv;
+                s.gmx[i] -= gb1 * A1 + gb2 * A2 + gcov * my;
+                const float n = win_count(y, H) * win_count(x, W);
+                t = __fdiv_rn(gcov, n);
+                u = __fdiv_rn(gmy, n);
+            }
+            s.gab[0][i] = t; s.gab[1][i] = u;
+        }
+        __syncthreads();
+        {
+            const float* src = s.gab[0];
+            box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&src[r * GF_R4 + c]); },
+                  s.tmp, GF_T, GF_R4, GF_T);
+            __syncthreads();
+            const float* zc = s.z[ch];
+            box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) {
+                const int ci = (r + 8) * GF_R8 + c + 8;
+                s.gy[(r * GF_T + c) * 4 + ch] = v * s.g[ci];
+                s.gx[r * GF_T + c] += v * zc[ci];
+            });
+            __syncthreads();
+            const float* src2 = s.gab[1];
+            box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&src2[r * GF_R4 + c]); },
+                  s.tmp, GF_T, GF_R4, GF_T);
+            __syncthreads();
+            box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) { s.gy[(r * GF_T + c) * 4 + ch] += v; });
+            __syncthreads();
+        }
+    }
+    // var = box(x^2)/N - mx^2 ; mx = box(x)/N
+    for (int i = threadIdx.x; i < GF_R4 * GF_R4; i += GF_NT) {
+        const int r = i / GF_R4, c = i - r * GF_R4;
+        const int y = y0 - 4 + r, x = x0 - 4 + c;
+        float gv = 0.f, gm = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float n = win_count(y, H) * win_count(x, W);
+            gm = __fdiv_rn(s.gmx[i] - 2.f * s.mx[i] * s.gvar[i], n);
+            gv = __fdiv_rn(s.gvar[i], n);
+        }
+        s.gvar[i] = gv; s.gmx[i] = gm;
+    }
+    __syncthreads();
+    box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&s.gvar[r * GF_R4 + c]); }, s.tmp, GF_T, GF_R4, GF_T);
+    __syncthreads();
+    box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) {
+        s.gx[r * GF_T + c] += 2.f * s.g[(r + 8) * GF_R8 + c + 8] * v;
+    });
+    __syncthreads();
+    box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&s.gmx[r * GF_R4 + c]); }, s.tmp, GF_T, GF_R4, GF_T);
+    __syncthreads();
+    box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) { s.gx[r * GF_T + c] += v; });
+    __syncthreads();
+
+    float4* gyp = reinterpret_cast<float4*>(gfeat) + ((size_t)b * Q + q) * plane;
+    float* gxp = gres_partial + ((size_t)q * B + b) * plane;
+    for (int i = threadIdx.x; i < GF_T * GF_T; i += GF_NT) {
+        const int r = i / GF_T, c = i - r * GF_T;
+        const int y = y0 + r, x = x0 + c;
+        if (y < H && x < W) {
+            gyp[(size_t)y * W + x] = *reinterpret_cast<const float4*>(&s.gy[i * 4]);
+            gxp[(size_t)y * W + x] = s.gx[i];
+        }
+    }
+}
+
 }  // namespace paif
 
 using namespace paif;
@@ -231,6 +407,20 @@ extern "C" int paif_gf_decomp_forward(const float* feat, const float* residue, f
 
 extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, const float* glf1, const float* glf2,
                                        float* gfeat, float* gres_partial, int C, int B, int H, int W, void* stream) {
-    set_error("paif_gf_decomp_backward: not implemented yet");
-    return PAIF_ENOTSUP;
+    PAIF_REQUIRE(feat && residue && glf1 && glf2 && gfeat && gres_partial, "null pointer");
+    PAIF_REQUIRE(C > 0 && C % 4 == 0, "C must be a multiple of 4");
+    PAIF_REQUIRE(H > 9 && W > 9, "guided filter needs H, W > 2r+1 = 9");
+    const int Q = C / 4;
+    PAIF_REQUIRE((long long)B * Q <= 65535, "B*C/4 exceeds grid.z");
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t err = cudaFuncSetAttribute(gf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)sizeof(GfBwdSmem));
+        if (err != cudaSuccess) { set_error("gf bwd smem attr: %s", cudaGetErrorString(err)); return (int)err; }
+        attr_done = true;
+    }
+    dim3 grid(cdiv(W, GF_T), cdiv(H, GF_T), B * Q);
+    gf_backward_kernel<<<grid, GF_NT, sizeof(GfBwdSmem), (cudaStream_t)stream>>>(feat, residue, glf1, glf2, gfeat,
+                                                                               gres_partial, Q, B, H, W);
+    return check_launch("paif_gf_decomp_backward");
 }

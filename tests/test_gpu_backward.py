@@ -1,0 +1,98 @@
+"""GPU: backward-to-input (what attack/attack.py:501's loss.backward() needs from the fusion net)
+against the reference's autograd gradients stored in the golden fixtures and against autograd of the
+CPU oracle.  The gradient is ill-conditioned (arg-max/min guide, PReLU kinks, 1/(var+eps)), so the gate
+is rel-L2 + sign agreement, not max-abs."""
+import ctypes
+
+import pytest
+import torch
+
+import paif_b200
+from oracle import fusion_oracle as fo
+from paif_b200 import _lib
+from paif_testutil import GOLDEN_CASES, load_golden, strided_vis
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def to_c4(t):
+    B, C, H, W = t.shape
+    return t.reshape(B, C // 4, 4, H, W).permute(0, 1, 3, 4, 2).contiguous()
+
+
+def from_c4(t):
+    B, Q, H, W, _ = t.shape
+    return t.permute(0, 1, 4, 2, 3).reshape(B, Q * 4, H, W)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def sign_agreement(a, b):
+    m = b.abs() > 1e-3 * b.abs().max()
+    return (torch.sign(a[m]) == torch.sign(b[m])).float().mean().item()
+
+
+@pytest.mark.parametrize("shape,smooth", [((1, 40, 56), False), ((2, 33, 47), True)])
+def test_guided_filter_adjoint(shape, smooth):
+    B, H, W = shape
+    torch.manual_seed(3)
+    z = torch.rand(B, 32, H, W, dtype=torch.float64)
+    if smooth:
+        z = torch.nn.functional.avg_pool2d(z, 9, 1, 4)
+    guide = fo.get_residue(z).detach().requires_grad_(True)
+    zr = z.clone().requires_grad_(True)
+    lf1 = fo.guided_filter(guide, zr, 4, 1e-3)
+    lf2 = fo.guided_filter(guide, zr, 4, 1e-4)
+    g1, g2 = torch.randn_like(lf1), torch.randn_like(lf2)
+    gz, gg = torch.autograd.grad([lf1, lf2], [zr, guide], [g1, g2])
+    zc, gc = to_c4(z.float()).to(DEV), guide.detach().float()[:, 0].contiguous().to(DEV)
+    g1c, g2c = to_c4(g1.float()).to(DEV), to_c4(g2.float()).to(DEV)
+    gfeat = torch.empty_like(zc)
+    gres = torch.empty(8, B, H, W, device=DEV)
+    _lib.call("paif_gf_decomp_backward", zc.data_ptr(), gc.data_ptr(), g1c.data_ptr(), g2c.data_ptr(),
+              gfeat.data_ptr(), gres.data_ptr(), 32, B, H, W, stream())
+    e_z = rel_l2(from_c4(gfeat).cpu().double(), gz)
+    e_g = rel_l2(gres.sum(0).cpu().double(), gg[:, 0])
+    assert e_z < 2e-3 and e_g < 2e-3, (e_z, e_g)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_input_gradients_match_reference_golden(case):
+    g = load_golden(case)
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+    net.load_state_dict(g["state_dict"], strict=True)
+    net = net.to(DEV).eval()
+    net.conv_engine = "direct"
+    ir = g["ir"].to(DEV).requires_grad_(True)
+    vis_full = g["vis"].to(DEV).requires_grad_(True)
+    out = net(ir, strided_vis(vis_full))
+    assert (out.detach().cpu() - g["out"]).abs().max().item() < 5e-5
+    out.backward(g["grad_out"].to(DEV))
+    g_ir, g_vis = ir.grad.cpu(), vis_full.grad.cpu()
+    assert g_vis[:, 1:].abs().max().item() == 0.0          # only Y gets gradient
+    for got, ref in ((g_ir, g["grad_ir"]), (g_vis[:, 0:1], g["grad_vis"][:, 0:1])):
+        r, s = rel_l2(got, ref), sign_agreement(got, ref)
+        assert r < 1e-2 and s > 0.999, (case, r, s)
+
+
+def test_no_grad_forward_saves_nothing_and_grad_only_where_needed():
+    g = load_golden("seed0_default_2x40x56")
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+    net.load_state_dict(g["state_dict"])
+    net = net.to(DEV).eval()
+    ir = g["ir"].to(DEV).requires_grad_(True)
+    vis = g["vis"].to(DEV)                                  # no grad wanted for vis
+    out = net(ir, vis)
+    out.sum().backward()
+    assert ir.grad is not None and vis.grad is None
+    with torch.no_grad():
+        out2 = net(ir, vis)
+    assert not out2.requires_grad and torch.equal(out2, out.detach())
+    assert all(p.grad is None for p in net.parameters())    # weight gradients are intentionally not produced
