@@ -103,6 +103,10 @@ typedef struct PaifConvDesc {
 } PaifConvDesc;
 
 int paif_conv_forward(const PaifConvDesc* desc, void* stream);
+/* tcgen05 engine weight image (PaifConvDesc.weight_mma): fp32 values rounded to TF32 (round to nearest),
+ * [K-group of KQ channel quads][tap][KQ/2][2 (16-byte chunk)][32 cout][4 cin]; KQ = paif_conv_tc_kq()
+ * (8, or 4 when the weights must be split into passes; 0 = shape not supported by the engine). */
+int paif_conv_tc_kq(int nsrc, int k, int dil);
 /* number of per-image tiles the chosen engine writes into chan_partials ([B][tiles][cout]) */
 int paif_conv_num_tiles(int H, int W, int engine);
 

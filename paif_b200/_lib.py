@@ -46,6 +46,7 @@ SIGNATURES = {
     "paif_gf_decomp_forward": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_conv_forward": [C.POINTER(ConvDesc), _f],
     "paif_conv_num_tiles": [_i, _i, _i],
+    "paif_conv_tc_kq": [_i, _i, _i],
     "paif_dwconv_forward": [_f, _f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "paif_channel_pool": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_spa_blend_forward": [_f, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i, _f],

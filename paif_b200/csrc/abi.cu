@@ -18,6 +18,7 @@ int conv_direct_tiles(int H, int W);
 int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream);
 int conv_tc_tiles(int H, int W);
 bool conv_tc_supported(const PaifConvDesc& d);
+int conv_tc_kq(int nsrc, int k, int dil);
 
 }  // namespace paif
 
@@ -54,4 +55,9 @@ extern "C" int paif_conv_forward(const PaifConvDesc* d, void* stream) {
 extern "C" int paif_conv_num_tiles(int H, int W, int engine) {
     if (engine == PAIF_ENGINE_TCGEN05) return conv_tc_tiles(H, W);
     return conv_direct_tiles(H, W);
+}
+
+extern "C" int paif_conv_tc_kq(int nsrc, int k, int dil) {
+    if (nsrc < 1 || nsrc > 3 || k < 1 || k > 7 || !(k & 1) || dil < 1 || dil > 2) return 0;
+    return conv_tc_kq(nsrc, k, dil);
 }

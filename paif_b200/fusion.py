@@ -53,7 +53,19 @@ class _ConvW:
         self.cps = cin_total // nsrc
         # direct engine: [nsrc][taps][cin_per_src][cout]
         self.direct = w.reshape(cout, nsrc, self.cps, kh * kw).permute(1, 3, 2, 0).contiguous().float()
+        # tcgen05 engine: TF32-rounded UMMA B tiles (layout documented at paif_conv_tc_kq in the header)
         self.mma = None
+        kq = _lib.load().paif_conv_tc_kq(nsrc, k, dil) if (cout == 32 and self.cps == 32) else 0
+        if kq:
+            G = cin_total // (kq * 4)
+            wt = _round_tf32(w.float()).reshape(cout, G, kq // 2, 2, 4, kh * kw)
+            self.mma = wt.permute(1, 5, 2, 3, 0, 4).contiguous()
+
+
+def _round_tf32(w):
+    """fp32 -> nearest TF32 (10-bit mantissa), kept in an fp32 container."""
+    i = w.contiguous().view(torch.int32)
+    return ((i + 0x1000) & -8192).view(torch.float32)
 
 
 def _dgrad_groups(w, k, dil, scale=None):

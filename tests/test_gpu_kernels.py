@@ -158,3 +158,31 @@ def test_confusion_matrix_kernel_is_exact():
         _lib.call("paif_confusion_accumulate", ld.data_ptr(), pd.data_ptr(), label.numel(), 9,
                   conf.data_ptr(), stream())
     assert torch.equal(conf.cpu(), 2 * ref)
+
+
+@pytest.mark.parametrize("B,H,W,k,dil,nsrc", [(1, 20, 128, 3, 1, 1), (2, 37, 200, 3, 1, 1), (1, 40, 300, 3, 1, 3),
+                                               (1, 33, 130, 3, 2, 1), (1, 40, 256, 7, 1, 1), (2, 21, 139, 1, 1, 3),
+                                               (1, 70, 640, 3, 1, 2), (1, 24, 150, 5, 1, 1)])
+def test_conv_tcgen05_matches_direct_engine(B, H, W, k, dil, nsrc):
+    """TF32 tensor-core engine vs torch fp64 and vs the exact-fp32 direct engine, with a full epilogue."""
+    torch.manual_seed(6)
+    xs = [torch.randn(B, 32, H, W) for _ in range(nsrc)]
+    w = torch.randn(32, 32 * nsrc, k, k) * 0.1
+    r1 = torch.randn(B, 32, H, W)
+    a = torch.tensor([0.3])
+    pre = F.conv2d(torch.cat(xs, 1).double(), w.double(), None, 1, dil * (k - 1) // 2, dil).float()
+    ref = F.prelu(pre, a) * 0.5 + r1
+    cw = fusion._ConvW(w.to(DEV), nsrc, k, dil)
+    assert cw.mma is not None
+    xc, r1c, ad = [to_c4(x).to(DEV) for x in xs], to_c4(r1).to(DEV), a.to(DEV)
+    res = {}
+    for eng in (_lib.ENGINE_DIRECT, _lib.ENGINE_TCGEN05):
+        out, opre, _, parts = rt(B, H, W, eng).conv(xc, cw, slope=ad, post_scale=0.5, post_res=[r1c], want_pre=True,
+                                                     want_partials=True)
+        res[eng] = (from_c4(out).cpu(), from_c4(opre).cpu(), parts.sum(1).cpu())
+    scale = pre.abs().max().item()
+    tf32 = 2.0 ** -10                                # TF32 operand truncation bound per product
+    assert (res[_lib.ENGINE_TCGEN05][0] - ref).abs().max().item() < 2 * tf32 * scale
+    assert (res[_lib.ENGINE_TCGEN05][1] - pre).abs().max().item() < 2 * tf32 * scale
+    assert (res[_lib.ENGINE_DIRECT][0] - ref).abs().max().item() < 1e-4 * max(1.0, scale)
+    assert (res[_lib.ENGINE_TCGEN05][2] - ref.sum((2, 3))).abs().max().item() < 1e-3 * H * W

@@ -10,7 +10,7 @@ from paif_testutil import GOLDEN_CASES, load_golden, strided_vis
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-ENGINES = [("direct", 5e-5)]
+ENGINES = [("direct", 5e-5), ("tcgen05", 1e-3)]      # (conv engine, max-abs gate on the fused image)
 
 
 def build(sd, engine):
