@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05"])
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", action="store_true", help="print the per-launch CUDA-event table of one step to stderr")
     return ap.parse_args()
 
 
@@ -208,6 +209,16 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.summary() if sampler else None
 
+    if args.table and rank == 0:
+        per = len(prof) // args.steps
+        tot = sum(a.elapsed_time(b) for (_, _, a, b) in prof[-per:])
+        for (n, m, a, b) in prof[-per:]:
+            t = a.elapsed_time(b)
+            extra = ""
+            if m:
+                extra = " k%d d%d cin%d  %.1f TFLOP/s" % (m["k"], m["dil"], m["cin"], m["flops"] / (t * 1e-3) / 1e12)
+            sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
+        sys.stderr.write("sum of launches %.3f ms (step %.3f ms)\n" % (tot, ms / args.steps))
     # dominant kernel: the dense-conv engine (all conv launches of the timed steps)
     conv = [(m, a.elapsed_time(b)) for (n, m, a, b) in prof if n == "paif_conv_forward"]
     other_ms = sum(a.elapsed_time(b) for (n, m, a, b) in prof if n != "paif_conv_forward")

@@ -7,14 +7,17 @@
 //    operand (8 consecutive pixels x 16 B = one core matrix, SBO = 128 B, LBO = plane pitch), so a tap
 //    (dy,dx) is just a 16*dx-byte shift of the descriptor start address: no im2col, no staging.
 //  * One CTA owns a 128-pixel-wide column strip x RCH rows.  Producer warps stream halo'd input rows
-//    (cp.async, zero-fill = conv padding) through a shared-memory ring; each input row is used by all
+//    (cp.async.bulk, one contiguous copy per quad plane) through a shared-memory ring; each input row is used by all
 //    k*k taps on arrival: tap row dy accumulates into the TMEM accumulator of output row (ri - dy*dil + pad).
 //    Accumulators form a 16-slot ring in TMEM (512 columns), so input is read once (+x/y halo).
 //  * Weights (TF32-rounded, pre-packed as UMMA B tiles) stay resident in shared memory; when they do
 //    not fit (7x7: 196 KB) K is split into passes over <=16 rows whose accumulators stay in TMEM.
-//  * Warp roles: 0-3 epilogue (TMEM -> registers -> fused epilogue -> coalesced quad stores),
-//    4 MMA issuer (one elected thread) + TMEM allocator, 5-8 producers.  mbarrier pipelines:
-//    full/empty per ring stage, acc_full/acc_empty per accumulator slot, wfull/wempty for weights.
+//  * Warp roles: 0-7 epilogue in two groups that alternate output rows (TMEM -> registers -> fused
+//    epilogue -> coalesced quad stores), 8 MMA issuer (one elected thread) + TMEM allocator, 9 producer
+//    (one elected thread issuing cp.async.bulk row copies that complete on the stage's mbarrier).
+//    mbarrier pipelines: full/empty per ring stage, acc_full/acc_empty per accumulator slot,
+//    wfull/wempty for the weight slab.  Zero padding: rows outside the image are skipped (no copy, no
+//    MMA), columns outside the image are zeroed once per stage and never overwritten.
 #include "conv_epilogue.cuh"
 
 namespace paif {
@@ -22,9 +25,9 @@ namespace paif {
 constexpr int TC_TW = 128;            // pixels per MMA (M)
 constexpr int TC_SLOTS = 16;          // TMEM accumulator ring (16 x 32 columns = 512)
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 4;
-constexpr int TC_NT = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;   // 288
-constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;
+constexpr int TC_EPI_WARPS = 8;                                   // two groups of 4 (TMEM lane quarters)
+constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_PROD_WARP = TC_EPI_WARPS + 1;
+constexpr int TC_NT = (TC_EPI_WARPS + 2) * 32;                    // 320
 constexpr int TC_SMEM_BUDGET = 222 * 1024;
 constexpr int TC_WSLAB_MAX = 110 * 1024;
 
@@ -86,12 +89,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// one elected lane of a converged warp (the rest of the warp-uniform control flow stays in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (async proxy)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -158,37 +169,51 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     const int x0 = blockIdx.x * TC_TW, r0 = blockIdx.y * g.RCH, b = blockIdx.z;
     const int nrows = min(g.RCH, g.H - r0);
     const int k = g.k, dil = g.dil, pad = P.pad, taps = k * k;
-    const int nin = nrows + 2 * pad;                           // input rows streamed per pass
-    const int units_per_pass = nin * P.gpp;
+    const int nin = nrows + 2 * pad;                           // input rows touched per pass
+    // valid x range of the halo'd row segment: columns [poff, poff + npx) of the RW-wide smem row
+    const int xs = max(0, x0 - pad), xe = min(g.W, x0 + TC_TW + pad);
+    const int poff = xs - (x0 - pad), npx = xe - xs;
 
     if (tid == 0) {
-        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), TC_PROD_THREADS); mbar_init(smem_u32(&bars->empty[i]), 1); }
-        for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), TC_EPI_WARPS * 32); }
-        mbar_init(smem_u32(&bars->wfull), TC_PROD_THREADS);
+        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 128); }
+        mbar_init(smem_u32(&bars->wfull), 1);
         mbar_init(smem_u32(&bars->wempty), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (npx < P.RW) {
+        // image-border strip: zero the columns no bulk copy will ever write (the conv's zero padding)
+        const int nplanes = P.stages * P.KQ;
+        const int nzero = P.RW - npx;
+        for (int i = tid; i < nplanes * nzero; i += TC_NT) {
+            const int pl = i / nzero, j = i - pl * nzero;
+            const int px = j < poff ? j : j + npx;
+            *reinterpret_cast<float4*>(s_ring + ((size_t)pl * P.RW + px) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);    // warp-uniform for the compiler
 
     if (warp < TC_EPI_WARPS) {
         // ===================== epilogue: TMEM -> registers -> fused epilogue -> global =====================
-        const int x = x0 + warp * 32 + lane;
+        const int grp = warp >> 2, wq = warp & 3;               // row-interleaved groups; TMEM lane quarter
+        const int x = x0 + wq * 32 + lane;
         float csum[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) csum[c] = 0.f;
-        for (int ro = 0; ro < nrows; ++ro) {
+        for (int ro = grp; ro < nrows; ro += 2) {
             const int slot = ro % TC_SLOTS, use = ro / TC_SLOTS;
             mbar_wait(smem_u32(&bars->acc_full[slot]), use & 1);
             tc_fence_after();
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + slot * 32, v);
+            tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32, v);
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->acc_empty[slot]));
             if (x < g.W) {
@@ -199,7 +224,8 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         }
         if (e.chan_partials) {
             // deterministic per-CTA channel sums: shuffle tree, then fixed-order cross-warp sum via smem
-            float* red = reinterpret_cast<float*>(s_ring);          // ring is idle once the last accumulator is done
+            float* red = reinterpret_cast<float*>(s_ring);          // the ring is idle once the last accumulator is done
+            asm volatile("bar.sync 1, 256;" ::: "memory");            // both groups have drained their last rows
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
                 float t = csum[c];
@@ -207,112 +233,128 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                 for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
                 if (lane == 0) red[warp * 32 + c] = t;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             if (tid < 32) {
-                const float t = red[tid] + red[32 + tid] + red[64 + tid] + red[96 + tid];
+                float t = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < TC_EPI_WARPS; ++w8) t += red[w8 * 32 + tid];
                 const int tile = blockIdx.y * gridDim.x + blockIdx.x;
                 e.chan_partials[((size_t)b * g.tiles_alloc + tile) * 32 + tid] = t;
             }
         }
-    } else if (warp == TC_EPI_WARPS) {
-        // ===================== MMA issuer (one elected thread) =====================
-        if (lane == 0) {
+    } else if (warp == TC_MMA_WARP) {
+        // ===================== MMA issuer (whole warp runs the uniform loop; one elected lane issues) =====================
+        {
             const uint32_t plane_bytes = P.RW * 16;
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
-            int u = 0;                                           // global unit counter (ring position)
+            const uint64_t a_desc0 = make_desc(0, plane_bytes, 128);
+            const uint64_t b_desc0 = make_desc(0, 512, 128);
+            const int nk8 = P.KQ / 2;
+            uint32_t fresh = 0;                                  // slots whose next MMA must overwrite (not accumulate)
+            int u = 0;                                           // ring position (valid units only)
             for (int pass = 0; pass < P.npass; ++pass) {
                 mbar_wait(smem_u32(&bars->wfull), pass & 1);
                 tc_fence_after();
-                for (int ri = 0; ri < nin; ++ri) {               // input row r0 - pad + ri
-                    for (int gl = 0; gl < P.gpp; ++gl, ++u) {
-                        const int stage = u % P.stages;
-                        mbar_wait(smem_u32(&bars->full[stage]), (u / P.stages) & 1);
-                        tc_fence_after();
-                        const uint32_t a_base = ring_base + stage * P.unit_bytes;
-                        const bool first_group = (pass == 0 && gl == 0);
-                        for (int dy = 0; dy < k; ++dy) {
-                            const int ro = ri - dy * dil;        // output row (chunk-relative) fed by this tap row
-                            if (ro < 0 || ro >= nrows) continue;
-                            const int slot = ro % TC_SLOTS, use = ro / TC_SLOTS;
-                            if (first_group && dy == 0 && use > 0) {
+                for (int ri = 0; ri < nin; ++ri) {               // input row y = r0 - pad + ri
+                    const int y = r0 - pad + ri;
+                    const bool yok = (y >= 0 && y < g.H);
+                    for (int gl = 0; gl < P.gpp; ++gl) {
+                        if (pass == 0 && gl == 0 && ri < nrows) {
+                            // output row ri starts accumulating now: claim its TMEM slot
+                            const int slot = ri % TC_SLOTS, use = ri / TC_SLOTS;
+                            if (use > 0) {
                                 mbar_wait(smem_u32(&bars->acc_empty[slot]), (use - 1) & 1);
                                 tc_fence_after();
                             }
-                            const uint32_t d_tmem = tmem_base + slot * 32;
-                            for (int dx = 0; dx < k; ++dx) {
-                                const uint32_t w_tap = w_base + ((gl * taps + dy * k + dx) * (P.KQ / 2)) * 1024;
-                                for (int k8 = 0; k8 < P.KQ / 2; ++k8) {
-                                    const uint64_t ad = make_desc(a_base + (2 * k8) * plane_bytes + dx * dil * 16, plane_bytes, 128);
-                                    const uint64_t bd = make_desc(w_tap + k8 * 1024, 512, 128);
-                                    const uint32_t acc = (first_group && dy == 0 && dx == 0 && k8 == 0) ? 0u : 1u;
-                                    tc_mma_tf32(d_tmem, ad, bd, TC_IDESC, acc);
+                            fresh |= 1u << slot;
+                        }
+                        if (yok) {
+                            const int stage = u % P.stages;
+                            mbar_wait(smem_u32(&bars->full[stage]), (u / P.stages) & 1);
+                            tc_fence_after();
+                            const uint32_t a_base = ring_base + stage * P.unit_bytes;
+                            for (int dy = 0; dy < k; ++dy) {
+                                const int ro = ri - dy * dil;    // output row (chunk-relative) fed by this tap row
+                                if (ro < 0 || ro >= nrows) continue;
+                                const int slot = ro % TC_SLOTS;
+                                const uint32_t d_tmem = tmem_base + slot * 32;
+                                uint32_t acc = (fresh >> slot) & 1u ? 0u : 1u;
+                                fresh &= ~(1u << slot);
+                                // descriptors differ only in the 14-bit start-address field (units of 16 B)
+                                const uint32_t w_lo = (w_base + ((gl * taps + dy * k) * nk8) * 1024) >> 4;
+                                const uint32_t a_lo = a_base >> 4;
+                                if (elect_one()) {
+                                    uint32_t wl = w_lo;
+                                    for (int dx = 0; dx < k; ++dx) {
+                                        uint32_t al = a_lo + dx * dil;
+#pragma unroll 2
+                                        for (int k8 = 0; k8 < nk8; ++k8) {
+                                            tc_mma_tf32(d_tmem, a_desc0 | (uint64_t)al, b_desc0 | (uint64_t)wl, TC_IDESC, acc);
+                                            acc = 1u;
+                                            al += 2 * P.RW;              // two quad planes = 2 * RW * 16 B
+                                            wl += 64;                    // 1 KB per B tile
+                                        }
+                                    }
                                 }
                             }
+                            if (elect_one()) tc_commit(smem_u32(&bars->empty[stage]));   // stage reusable once these MMAs retire
+                            ++u;
                         }
-                        tc_commit(smem_u32(&bars->empty[stage]));          // ring stage reusable once these MMAs retire
                         if (pass == P.npass - 1 && gl == P.gpp - 1) {
-                            const int rdone = ri - (k - 1) * dil;           // output row whose last tap row just ran
-                            if (rdone >= 0 && rdone < nrows) tc_commit(smem_u32(&bars->acc_full[rdone % TC_SLOTS]));
+                            const int rdone = ri - (k - 1) * dil;           // output row whose last tap row just passed
+                            if (rdone >= 0 && rdone < nrows && elect_one()) tc_commit(smem_u32(&bars->acc_full[rdone % TC_SLOTS]));
                         }
                     }
                 }
-                if (pass + 1 < P.npass) tc_commit(smem_u32(&bars->wempty));  // weights of this pass no longer read
+                if (pass + 1 < P.npass && elect_one()) tc_commit(smem_u32(&bars->wempty));  // weights of this pass no longer read
             }
         }
         __syncwarp();
     } else {
-        // ===================== producers: weights slab + halo'd input rows via cp.async =====================
-        const int pt = tid - (TC_EPI_WARPS + 1) * 32;
-        const size_t plane = (size_t)g.H * g.W;
-        int u = 0;
-        for (int pass = 0; pass < P.npass; ++pass) {
-            if (pass > 0) mbar_wait(smem_u32(&bars->wempty), (pass - 1) & 1);
-            {
-                const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(g.wmma) + (size_t)pass * P.slab_bytes;
-                const uint32_t wdst = smem_u32(s_w);
-                for (int i = pt * 16; i < P.slab_bytes; i += TC_PROD_THREADS * 16) cp_async16(wdst + i, wsrc + i, 16);
-                cp_async_commit();
-                cp_async_wait<0>();
-                fence_proxy_async();
-                mbar_arrive(smem_u32(&bars->wfull));
-            }
-            int pending_stage = -1;                              // unit whose copies are in flight (1-deep software pipeline)
-            for (int ri = 0; ri < nin; ++ri) {
-                const int y = r0 - pad + ri;
-                const bool yok = (y >= 0 && y < g.H);
-                for (int gl = 0; gl < P.gpp; ++gl, ++u) {
-                    const int stage = u % P.stages;
-                    mbar_wait(smem_u32(&bars->empty[stage]), ((u / P.stages) & 1) ^ 1);
-                    const int gk = pass * P.gpp + gl;            // global K-group
-                    const int s = gk / P.gps, qoff = (gk % P.gps) * P.KQ;
-                    const float4* sp = reinterpret_cast<const float4*>(g.src[s]) + ((size_t)b * 8 + qoff) * plane;
-                    const uint32_t dst = smem_u32(s_ring) + stage * P.unit_bytes;
-                    const int n = P.KQ * P.RW;
-                    for (int i = pt; i < n; i += TC_PROD_THREADS) {
-                        const int q = i / P.RW, px = i - q * P.RW;
-                        const int x = x0 - pad + px;
-                        const bool ok = yok && x >= 0 && x < g.W;
-                        const float4* src = ok ? sp + (size_t)q * plane + (size_t)y * g.W + x : sp;
-                        cp_async16(dst + i * 16, src, ok ? 16u : 0u);
+        // ===================== producer: weight slab + halo'd input rows via cp.async.bulk =====================
+        {
+            const size_t plane = (size_t)g.H * g.W;
+            const uint32_t row_bytes = (uint32_t)npx * 16;
+            int u = 0;
+            for (int pass = 0; pass < P.npass; ++pass) {
+                if (pass > 0) mbar_wait(smem_u32(&bars->wempty), (pass - 1) & 1);
+                {
+                    const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(g.wmma) + (size_t)pass * P.slab_bytes;
+                    const uint32_t wdst = smem_u32(s_w), wbar = smem_u32(&bars->wfull);
+                    if (elect_one()) {
+                        mbar_expect_tx(wbar, (uint32_t)P.slab_bytes);
+                        for (int off = 0; off < P.slab_bytes; off += 16384) {
+                            const int n = min(16384, P.slab_bytes - off);
+                            bulk_g2s(wdst + off, wsrc + off, (uint32_t)n, wbar);
+                        }
                     }
-                    cp_async_commit();
-                    if (pending_stage >= 0) {
-                        cp_async_wait<1>();
-                        fence_proxy_async();
-                        mbar_arrive(smem_u32(&bars->full[pending_stage]));
+                }
+                for (int ri = 0; ri < nin; ++ri) {
+                    const int y = r0 - pad + ri;
+                    if (y < 0 || y >= g.H) continue;             // zero padding rows: skipped by the MMA issuer too
+                    for (int gl = 0; gl < P.gpp; ++gl, ++u) {
+                        const int stage = u % P.stages;
+                        mbar_wait(smem_u32(&bars->empty[stage]), ((u / P.stages) & 1) ^ 1);
+                        const int gk = pass * P.gpp + gl;        // global K-group
+                        const int s = gk / P.gps, qoff = (gk % P.gps) * P.KQ;
+                        const float4* sp = reinterpret_cast<const float4*>(g.src[s]) + ((size_t)b * 8 + qoff) * plane
+                                           + (size_t)y * g.W + xs;
+                        const uint32_t dst = smem_u32(s_ring) + stage * P.unit_bytes + poff * 16;
+                        const uint32_t bar = smem_u32(&bars->full[stage]);
+                        if (elect_one()) {
+                            mbar_expect_tx(bar, row_bytes * P.KQ);
+                            for (int q = 0; q < P.KQ; ++q) bulk_g2s(dst + q * P.RW * 16, sp + (size_t)q * plane, row_bytes, bar);
+                        }
                     }
-                    pending_stage = stage;
                 }
             }
-            cp_async_wait<0>();
-            fence_proxy_async();
-            if (pending_stage >= 0) mbar_arrive(smem_u32(&bars->full[pending_stage]));
         }
+        __syncwarp();
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
