@@ -55,9 +55,12 @@ int paif_stem_forward(const float* img, long long stride_b, long long stride_y, 
 
 /* GuidedFilter(4, eps)(residue, feat) for eps in {1e-3, 1e-4} — core/model_fusion_auto.py:522-535
  * + third-party guided_filter_pytorch (box filter radius 4, clipped borders).
- * Writes the two low-frequency maps; HF = feat - LF is folded into the 1x1 conv weights. */
-int paif_gf_decomp_forward(const float* feat, const float* residue, float* lf1, float* lf2,
-                           int C, int B, int H, int W, void* stream);
+ * Pass 0 computes what all 32 channels share: stats = [3][B][H][W] = mean_guide, 1/(var_guide + 1e-3),
+ * 1/(var_guide + 1e-4) (caller-owned scratch).  Pass 1 writes the two low-frequency maps;
+ * HF = feat - LF is folded into the 1x1 conv weights. */
+int paif_gf_guide_stats(const float* residue, float* stats, int B, int H, int W, void* stream);
+int paif_gf_decomp_forward(const float* feat, const float* residue, const float* stats,
+                           float* lf1, float* lf2, int C, int B, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Generic dense "same"-padded stride-1 convolution over 1..3 concatenated C4 source maps

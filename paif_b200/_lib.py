@@ -43,7 +43,8 @@ SIGNATURES = {
     "paif_abi_version": [],
     "paif_last_error_string": [],
     "paif_stem_forward": [_f, _ll, _ll, _ll, _f, _f, _f, _f, _i, _i, _i, _f],
-    "paif_gf_decomp_forward": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_gf_guide_stats": [_f, _f, _i, _i, _i, _f],
+    "paif_gf_decomp_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_conv_forward": [C.POINTER(ConvDesc), _f],
     "paif_conv_num_tiles": [_i, _i, _i],
     "paif_conv_tc_kq": [_i, _i, _i],

@@ -13,7 +13,7 @@
 //  * Weights (TF32-rounded, pre-packed as UMMA B tiles) stay resident in shared memory; when they do
 //    not fit (7x7: 196 KB) K is split into passes over <=16 rows whose accumulators stay in TMEM.
 //  * Warp roles: 0-7 epilogue in two groups that alternate output rows (TMEM -> registers -> fused
-//    epilogue -> coalesced quad stores), 8 MMA issuer (one elected thread) + TMEM allocator, 9 producer
+//    epilogue -> coalesced quad stores), 8-11 MMA issuers (one elected thread each; 8 also allocates TMEM), 12 producer
 //    (one elected thread issuing cp.async.bulk row copies that complete on the stage's mbarrier).
 //    mbarrier pipelines: full/empty per ring stage, acc_full/acc_empty per accumulator slot,
 //    wfull/wempty for the weight slab.  Zero padding: rows outside the image are skipped (no copy, no
@@ -26,8 +26,14 @@ constexpr int TC_TW = 128;            // pixels per MMA (M)
 constexpr int TC_SLOTS = 16;          // TMEM accumulator ring (16 x 32 columns = 512)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 8;                                   // two groups of 4 (TMEM lane quarters)
-constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_PROD_WARP = TC_EPI_WARPS + 1;
-constexpr int TC_NT = (TC_EPI_WARPS + 2) * 32;                    // 320
+// One tcgen05.mma of this shape (M128 N32 K8) occupies its issuing thread for ~91-98 cycles although the
+// tensor pipe needs 16 and the shared-memory operand fetch ~40 (scripts/mma_ubench.cu, measured on B200:
+// 1 issuer 209 TFLOP/s, 2 issuers 389, 4 issuers 476 = operand-fetch bound).  So four warps issue
+// concurrently; each owns the output rows (TMEM slots) with row % 4 == its index, which also keeps every
+// accumulator's MMAs and its acc_full commit in one thread's program order.
+constexpr int TC_MMA_WARPS = 4;
+constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_PROD_WARP = TC_EPI_WARPS + TC_MMA_WARPS;
+constexpr int TC_NT = (TC_EPI_WARPS + TC_MMA_WARPS + 1) * 32;     // 416
 constexpr int TC_SMEM_BUDGET = 222 * 1024;
 constexpr int TC_WSLAB_MAX = 110 * 1024;
 
@@ -156,6 +162,7 @@ struct TcBars {
     uint32_t pad_;
 };
 static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservation");
+static_assert(TC_SLOTS % TC_MMA_WARPS == 0, "slot ownership (row % TC_MMA_WARPS) must be stable across ring wraps");
 
 __global__ void __launch_bounds__(TC_NT, 1)
 conv_tc_kernel(TcGeom g, EpiParams e) {
@@ -175,10 +182,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     const int poff = xs - (x0 - pad), npx = xe - xs;
 
     if (tid == 0) {
-        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), TC_MMA_WARPS); }
         for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 128); }
         mbar_init(smem_u32(&bars->wfull), 1);
-        mbar_init(smem_u32(&bars->wempty), 1);
+        mbar_init(smem_u32(&bars->wempty), TC_MMA_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_MMA_WARP) {
@@ -242,9 +249,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                 e.chan_partials[((size_t)b * g.tiles_alloc + tile) * 32 + tid] = t;
             }
         }
-    } else if (warp == TC_MMA_WARP) {
-        // ===================== MMA issuer (whole warp runs the uniform loop; one elected lane issues) =====================
+    } else if (warp < TC_PROD_WARP) {
+        // ===================== MMA issuers (each warp runs the uniform loop; one elected lane issues) =====================
         {
+            const int mw = warp - TC_MMA_WARP;                   // owns output rows with (row % TC_MMA_WARPS) == mw
             const uint32_t plane_bytes = P.RW * 16;
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
             const uint64_t a_desc0 = make_desc(0, plane_bytes, 128);
@@ -259,7 +267,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                     const int y = r0 - pad + ri;
                     const bool yok = (y >= 0 && y < g.H);
                     for (int gl = 0; gl < P.gpp; ++gl) {
-                        if (pass == 0 && gl == 0 && ri < nrows) {
+                        if (pass == 0 && gl == 0 && ri < nrows && (ri % TC_MMA_WARPS) == mw) {
                             // output row ri starts accumulating now: claim its TMEM slot
                             const int slot = ri % TC_SLOTS, use = ri / TC_SLOTS;
                             if (use > 0) {
@@ -275,7 +283,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                             const uint32_t a_base = ring_base + stage * P.unit_bytes;
                             for (int dy = 0; dy < k; ++dy) {
                                 const int ro = ri - dy * dil;    // output row (chunk-relative) fed by this tap row
-                                if (ro < 0 || ro >= nrows) continue;
+                                if (ro < 0 || ro >= nrows || (ro % TC_MMA_WARPS) != mw) continue;
                                 const int slot = ro % TC_SLOTS;
                                 const uint32_t d_tmem = tmem_base + slot * 32;
                                 uint32_t acc = (fresh >> slot) & 1u ? 0u : 1u;
@@ -302,7 +310,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                         }
                         if (pass == P.npass - 1 && gl == P.gpp - 1) {
                             const int rdone = ri - (k - 1) * dil;           // output row whose last tap row just passed
-                            if (rdone >= 0 && rdone < nrows && elect_one()) tc_commit(smem_u32(&bars->acc_full[rdone % TC_SLOTS]));
+                            if (rdone >= 0 && rdone < nrows && (rdone % TC_MMA_WARPS) == mw && elect_one()) tc_commit(smem_u32(&bars->acc_full[rdone % TC_SLOTS]));
                         }
                     }
                 }

@@ -630,8 +630,11 @@ class Network_Fusion_Searched(nn.Module):
         branch_out, branch_recs = [], []
         for i, (chain, packs) in enumerate(((d.chain, p["chain_ir"]), (d.chain2, p["chain_vis"]))):
             lf1, lf2 = rt.new_map(), rt.new_map()
-            rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), lf1.data_ptr(),
-                    lf2.data_ptr(), C, B, H, W)
+            stats = torch.empty((3, B, H, W), device=ir.device, dtype=torch.float32)
+            rt.call("paif_gf_guide_stats", guides[i].data_ptr(), stats.data_ptr(), B, H, W)
+            rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
+                    lf1.data_ptr(), lf2.data_ptr(), C, B, H, W)
+            del stats
             x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i])[0]
             del lf1, lf2
             o, recs = chain.fwd(rt, packs, x, [feats[i]])

@@ -50,7 +50,8 @@ def test_stem_and_residue(shape):
     assert (res.cpu() - ref_res[:, 0]).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("shape,smooth", [((2, 40, 56), False), ((1, 33, 47), True), ((1, 10, 70), False)])
+@pytest.mark.parametrize("shape,smooth", [((2, 40, 56), False), ((1, 33, 47), True), ((1, 10, 70), False),
+                                          ((1, 200, 236), False), ((1, 480, 640), True), ((1, 19, 10), False)])
 def test_guided_filter_decomposition(shape, smooth):
     B, H, W = shape
     torch.manual_seed(1)
@@ -63,7 +64,9 @@ def test_guided_filter_decomposition(shape, smooth):
     zc = to_c4(z).to(DEV)
     lf1, lf2 = torch.empty_like(zc), torch.empty_like(zc)
     resd = res[:, 0].contiguous().to(DEV)
-    _lib.call("paif_gf_decomp_forward", zc.data_ptr(), resd.data_ptr(),
+    stats = torch.empty(3, B, H, W, device=DEV)
+    _lib.call("paif_gf_guide_stats", resd.data_ptr(), stats.data_ptr(), B, H, W, stream())
+    _lib.call("paif_gf_decomp_forward", zc.data_ptr(), resd.data_ptr(), stats.data_ptr(),
               lf1.data_ptr(), lf2.data_ptr(), 32, B, H, W, stream())
     got = torch.cat([from_c4(lf1), from_c4(lf2)], 1).cpu()
     e32 = (got - LF).abs().max().item()
