@@ -107,7 +107,8 @@ typedef struct PaifConvDesc {
 
 int paif_conv_forward(const PaifConvDesc* desc, void* stream);
 /* tcgen05 engine weight image (PaifConvDesc.weight_mma): fp32 values rounded to TF32 (round to nearest),
- * [K-group of KQ channel quads][tap][KQ/2][2 (16-byte chunk)][32 cout][4 cin]; KQ = paif_conv_tc_kq()
+ * [K-group of KQ channel quads][dx][KQ/2][2 (16-byte chunk)][dy][32 cout][4 cin] — the k row taps of one
+ * (dx, 8 input channels) form one UMMA B tile of N = 32*k rows; KQ = paif_conv_tc_kq()
  * (8, or 4 when the weights must be split into passes; 0 = shape not supported by the engine). */
 int paif_conv_tc_kq(int nsrc, int k, int dil);
 /* number of per-image tiles the chosen engine writes into chan_partials ([B][tiles][cout]) */

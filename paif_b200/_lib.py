@@ -81,9 +81,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or (_build.needs_build() and os.environ.get("PAIF_NO_REBUILD") != "1"):
+    path = LIB_PATH
+    if os.environ.get("PAIF_B200_PROFILE_LIB") == "1":
+        # development only: same sources compiled with -DPAIF_TC_PROFILE (role timeline counters in the conv engine)
+        path = _build.build(profile=True)
+    elif not os.path.exists(LIB_PATH) or (_build.needs_build() and os.environ.get("PAIF_NO_REBUILD") != "1"):
         _build.build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.argtypes = argtypes

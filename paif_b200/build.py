@@ -30,14 +30,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, profile=False):
+    lib = LIB.replace(".so", "_prof.so") if profile else LIB
+    if profile:
+        if os.path.exists(lib) and os.path.getmtime(lib) >= max(
+                os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)):
+            return lib
+    elif not force and not needs_build():
         return LIB
     objs, procs = [], []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        obj = os.path.join(HERE, "build", src.replace(".cu", "_prof.o" if profile else ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + (["-DPAIF_TC_PROFILE"] if profile else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -51,9 +56,9 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("paif_b200: nvcc build failed")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"])
-    return LIB
+    subprocess.check_call([_nvcc(), "-shared", "-o", lib] + objs + ["-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))

@@ -8,12 +8,16 @@
 //    (dy,dx) is just a 16*dx-byte shift of the descriptor start address: no im2col, no staging.
 //  * One CTA owns a 128-pixel-wide column strip x RCH rows.  Producer warps stream halo'd input rows
 //    (cp.async.bulk, one contiguous copy per quad plane) through a shared-memory ring; each input row is used by all
-//    k*k taps on arrival: tap row dy accumulates into the TMEM accumulator of output row (ri - dy*dil + pad).
-//    Accumulators form a 16-slot ring in TMEM (512 columns), so input is read once (+x/y halo).
+//    k*k taps on arrival.  Input row ri feeds output rows ri - dy*dil (dy = 0..k-1): their accumulators sit in
+//    CONSECUTIVE 32-column TMEM slots, so all dy taps of one (dx, 8 input channels) are ONE tcgen05.mma with
+//    N = 32*k (B tile rows = (dy, cout)).  A tcgen05.mma occupies its issuing thread for >= 91 cycles whatever its
+//    size (scripts/mma_ubench.cu), so wide N is what makes a single issuer HBM-bound instead of issue-bound.
+//    Accumulators form a 16-slot ring in TMEM (512 columns), so input is read once (+x/y halo); slots are
+//    zeroed by the epilogue after it drains them, every MMA accumulates.
 //  * Weights (TF32-rounded, pre-packed as UMMA B tiles) stay resident in shared memory; when they do
 //    not fit (7x7: 196 KB) K is split into passes over <=16 rows whose accumulators stay in TMEM.
 //  * Warp roles: 0-7 epilogue in two groups that alternate output rows (TMEM -> registers -> fused
-//    epilogue -> coalesced quad stores), 8-11 MMA issuers (one elected thread each; 8 also allocates TMEM), 12 producer
+//    epilogue -> coalesced quad stores), 8 MMA issuer (one elected thread) + TMEM allocator, 9 producer
 //    (one elected thread issuing cp.async.bulk row copies that complete on the stage's mbarrier).
 //    mbarrier pipelines: full/empty per ring stage, acc_full/acc_empty per accumulator slot,
 //    wfull/wempty for the weight slab.  Zero padding: rows outside the image are skipped (no copy, no
@@ -26,14 +30,9 @@ constexpr int TC_TW = 128;            // pixels per MMA (M)
 constexpr int TC_SLOTS = 16;          // TMEM accumulator ring (16 x 32 columns = 512)
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_EPI_WARPS = 8;                                   // two groups of 4 (TMEM lane quarters)
-// One tcgen05.mma of this shape (M128 N32 K8) occupies its issuing thread for ~91-98 cycles although the
-// tensor pipe needs 16 and the shared-memory operand fetch ~40 (scripts/mma_ubench.cu, measured on B200:
-// 1 issuer 209 TFLOP/s, 2 issuers 389, 4 issuers 476 = operand-fetch bound).  So four warps issue
-// concurrently; each owns the output rows (TMEM slots) with row % 4 == its index, which also keeps every
-// accumulator's MMAs and its acc_full commit in one thread's program order.
-constexpr int TC_MMA_WARPS = 4;
+constexpr int TC_MMA_WARPS = 1;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_PROD_WARP = TC_EPI_WARPS + TC_MMA_WARPS;
-constexpr int TC_NT = (TC_EPI_WARPS + TC_MMA_WARPS + 1) * 32;     // 416
+constexpr int TC_NT = (TC_EPI_WARPS + TC_MMA_WARPS + 1) * 32;     // 320
 constexpr int TC_SMEM_BUDGET = 222 * 1024;
 constexpr int TC_WSLAB_MAX = 110 * 1024;
 
@@ -51,6 +50,8 @@ struct TcPlan {
 };
 
 static bool tc_make_plan(int nsrc, int k, int dil, TcPlan* p) {
+    if (dil != 1 && dil != 2) return false;              // slot arithmetic uses shifts (log2 dil)
+    if ((TC_SLOTS >> (dil >> 1)) < k) return false;      // the k rows fed by one input row need distinct slots
     const int taps = k * k;
     p->pad = dil * (k - 1) / 2;
     p->RW = TC_TW + 2 * p->pad;
@@ -127,7 +128,28 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 // kind::tf32, D=f32, A/B = TF32 K-major, N=32, M=128 (cute::UMMA::InstrDescriptor bit layout)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint32_t tc_idesc(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// TMEM slot of chunk-relative output row ro: rows of one dilation residue class descend through consecutive slots,
+// so the k rows fed by one input row (ro, ro - dil, ...) occupy ascending consecutive slots.
+// dsh = log2(dil), dil in {1, 2}: shifts and masks only (a runtime integer division costs ~100 cycles on the
+// single thread that paces the tensor pipe).
+__device__ __forceinline__ int tc_slot(int ro, int dsh) {
+    const int spr = TC_SLOTS >> dsh;                 // slots per residue class ring
+    return (ro & ((1 << dsh) - 1)) * spr + (spr - 1 - ((ro >> dsh) & (spr - 1)));
+}
+
+// zero one 32-lane x 32-column accumulator slot (this warp's lane quarter)
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n\t"
+        "tcgen05.wait::st.sync.aligned;"
+        ::"r"(taddr), "r"(z) : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -145,10 +167,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+#ifdef PAIF_TC_PROFILE
+// development-only role timeline: wait / busy cycles summed over all CTAs (read with paif_debug_tc_counters)
+__device__ unsigned long long tc_prof[16];
+#define TC_PROF_DECL long long prof_wait = 0, prof_t0 = clock64()
+#define TC_WAIT(stmt) do { const long long t_ = clock64(); stmt; prof_wait += clock64() - t_; } while (0)
+#define TC_PROF_END(slot) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&tc_prof[(slot) * 2], (unsigned long long)prof_wait); \
+                                   atomicAdd(&tc_prof[(slot) * 2 + 1], (unsigned long long)(clock64() - prof_t0)); } } while (0)
+#else
+#define TC_PROF_DECL
+#define TC_WAIT(stmt) stmt
+#define TC_PROF_END(slot)
+#endif
+
 struct TcGeom {
     int B, H, W, nsrc, k, dil, RCH, tiles_alloc;
     const float* src[3];
-    const float* wmma;     // [K-group of KQ quads][tap][KQ/2 (k8)][2 (16-B chunk)][32 cout][4 cin], TF32-rounded
+    const float* wmma;     // [K-group of KQ quads][dx][KQ/2 (k8)][2 (16-B chunk)][dy][32 cout][4 cin], TF32-rounded
     TcPlan plan;
 };
 
@@ -157,25 +192,32 @@ struct TcBars {
     uint64_t empty[TC_MAX_STAGES];
     uint64_t acc_full[TC_SLOTS];
     uint64_t acc_empty[TC_SLOTS];
-    uint64_t wfull, wempty;
+    uint64_t wfull, wempty, zeroed;
     uint32_t tmem_base;
-    uint32_t pad_;
+    alignas(16) float ch_scale[32];       // epilogue per-channel affine (1 / 0 when absent), read as float4
+    alignas(16) float ch_shift[32];
 };
 static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservation");
-static_assert(TC_SLOTS % TC_MMA_WARPS == 0, "slot ownership (row % TC_MMA_WARPS) must be stable across ring wraps");
 
+// K, DIL, KQ are compile-time so that the MMA issue loop unrolls into straight-line code whose descriptors differ
+// from a per-row base by immediates: the single issuing thread then sustains the tensor pipe's own rate
+// (max(32 + N/4, N/2) cycles per MMA, scripts/mma_ubench2.cu) instead of ~150 cycles of address arithmetic per MMA.
+template <int K, int DIL, int KQ>
 __global__ void __launch_bounds__(TC_NT, 1)
 conv_tc_kernel(TcGeom g, EpiParams e) {
     extern __shared__ __align__(128) unsigned char smem[];
     const TcPlan& P = g.plan;
     unsigned char* s_w = smem;                                 // weight slab
     unsigned char* s_ring = smem + P.slab_bytes;               // input ring
-    TcBars* bars = reinterpret_cast<TcBars*>(s_ring + P.stages * P.unit_bytes);
+    TcBars* bars = reinterpret_cast<TcBars*>(s_ring + P.stages * P.unit_bytes);   // (P.unit_bytes == UNIT, set by the host)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x0 = blockIdx.x * TC_TW, r0 = blockIdx.y * g.RCH, b = blockIdx.z;
     const int nrows = min(g.RCH, g.H - r0);
-    const int k = g.k, dil = g.dil, pad = P.pad, taps = k * k;
+    constexpr int k = K, dil = DIL, pad = DIL * (K - 1) / 2;
+    constexpr int dsh = DIL >> 1;                              // log2(dil), dil in {1, 2}
+    constexpr int RW = TC_TW + 2 * pad;                        // halo'd row width in pixels
+    constexpr int UNIT = KQ * RW * 16;                         // bytes of one ring stage
     const int nin = nrows + 2 * pad;                           // input rows touched per pass
     // valid x range of the halo'd row segment: columns [poff, poff + npx) of the RW-wide smem row
     const int xs = max(0, x0 - pad), xe = min(g.W, x0 + TC_TW + pad);
@@ -186,20 +228,25 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 128); }
         mbar_init(smem_u32(&bars->wfull), 1);
         mbar_init(smem_u32(&bars->wempty), TC_MMA_WARPS);
+        mbar_init(smem_u32(&bars->zeroed), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid >= 32 && tid < 64) {
+        bars->ch_scale[tid - 32] = e.ch_scale ? e.ch_scale[tid - 32] : 1.f;
+        bars->ch_shift[tid - 32] = e.ch_shift ? e.ch_shift[tid - 32] : 0.f;
     }
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (npx < P.RW) {
+    if (npx < RW) {
         // image-border strip: zero the columns no bulk copy will ever write (the conv's zero padding)
-        const int nplanes = P.stages * P.KQ;
-        const int nzero = P.RW - npx;
+        const int nplanes = P.stages * KQ;
+        const int nzero = RW - npx;
         for (int i = tid; i < nplanes * nzero; i += TC_NT) {
             const int pl = i / nzero, j = i - pl * nzero;
             const int px = j < poff ? j : j + npx;
-            *reinterpret_cast<float4*>(s_ring + ((size_t)pl * P.RW + px) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(s_ring + ((size_t)pl * RW + px) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         fence_proxy_async();
     }
@@ -212,23 +259,90 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         // ===================== epilogue: TMEM -> registers -> fused epilogue -> global =====================
         const int grp = warp >> 2, wq = warp & 3;               // row-interleaved groups; TMEM lane quarter
         const int x = x0 + wq * 32 + lane;
+        const bool xin = x < g.W;
+        const size_t plane = (size_t)g.H * g.W;
+        const float a = e.slope ? __ldg(e.slope) : 1.f;
+        const float ma = e.mask_slope ? __ldg(e.mask_slope) : 0.f;
+        const float a2 = e.slope2 ? __ldg(e.slope2) : 1.f;
+        const bool any_post = e.post_res[0] || e.post_res[1] || e.post_res[2];
+        // The residual maps added after the activation do not depend on the accumulator: their sum for
+        // this thread's NEXT row is fetched while the current row is still being accumulated, so the
+        // global-load latency never sits between acc_full and the stores.
+        float4 pn[8];
+        auto fetch_post = [&](int ro) {
+            const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk)
+                if (e.post_res[kk]) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pn[q] = f4_add(pn[q], __ldg(reinterpret_cast<const float4*>(e.post_res[kk]) + base + q * plane));
+                }
+        };
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (any_post && xin && grp < nrows) fetch_post(grp);
+        if (grp == 0) {
+            // accumulators start from zero: every MMA accumulates (the TMEM allocation holds garbage)
+            for (int sl = 0; sl < TC_SLOTS; ++sl) tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + sl * 32);
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->zeroed));
+        }
         float csum[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) csum[c] = 0.f;
+        TC_PROF_DECL;
         for (int ro = grp; ro < nrows; ro += 2) {
-            const int slot = ro % TC_SLOTS, use = ro / TC_SLOTS;
-            mbar_wait(smem_u32(&bars->acc_full[slot]), use & 1);
+            const int slot = tc_slot(ro, dsh), use = ro / TC_SLOTS;
+            TC_WAIT(mbar_wait(smem_u32(&bars->acc_full[slot]), use & 1));
             tc_fence_after();
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32, v);
+            tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32);
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->acc_empty[slot]));
-            if (x < g.W) {
-                epilogue_pixel<32>(e, b, r0 + ro, x, v);
+            if (xin) {
+                const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;     // float4 units, quad 0
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const size_t off = base + q * plane;
+                    const float4 sc = *reinterpret_cast<const float4*>(&bars->ch_scale[q * 4]);
+                    const float4 sh = *reinterpret_cast<const float4*>(&bars->ch_shift[q * 4]);
+                    float t[4] = {fmaf(v[q * 4 + 0], sc.x, sh.x), fmaf(v[q * 4 + 1], sc.y, sh.y),
+                                  fmaf(v[q * 4 + 2], sc.z, sh.z), fmaf(v[q * 4 + 3], sc.w, sh.w)};
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+                        if (e.pre_res[kk]) {
+                            const float4 r = __ldg(reinterpret_cast<const float4*>(e.pre_res[kk]) + off);
+                            t[0] += r.x; t[1] += r.y; t[2] += r.z; t[3] += r.w;
+                        }
+                    if (e.out_pre) reinterpret_cast<float4*>(e.out_pre)[off] = make_float4(t[0], t[1], t[2], t[3]);
+                    if (e.mask_src) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(e.mask_src) + off);
+                        t[0] *= dprelu_f(m.x, ma); t[1] *= dprelu_f(m.y, ma);
+                        t[2] *= dprelu_f(m.z, ma); t[3] *= dprelu_f(m.w, ma);
+                    } else if (e.slope) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) t[j] = prelu_f(t[j], a);
+                    }
+                    v[q * 4 + 0] = fmaf(t[0], e.post_scale, pn[q].x); v[q * 4 + 1] = fmaf(t[1], e.post_scale, pn[q].y);
+                    v[q * 4 + 2] = fmaf(t[2], e.post_scale, pn[q].z); v[q * 4 + 3] = fmaf(t[3], e.post_scale, pn[q].w);
+                }
+                if (any_post && ro + 2 < nrows) fetch_post(ro + 2);       // in flight during the next row's MMAs
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const size_t off = base + q * plane;
+                    reinterpret_cast<float4*>(e.out)[off] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                    if (e.out_act2)
+                        reinterpret_cast<float4*>(e.out_act2)[off] =
+                            make_float4(prelu_f(v[q * 4 + 0], a2), prelu_f(v[q * 4 + 1], a2), prelu_f(v[q * 4 + 2], a2), prelu_f(v[q * 4 + 3], a2));
+                }
 #pragma unroll
                 for (int c = 0; c < 32; ++c) csum[c] += v[c];
             }
         }
+        TC_PROF_END(0);
         if (e.chan_partials) {
             // deterministic per-CTA channel sums: shuffle tree, then fixed-order cross-warp sum via smem
             float* red = reinterpret_cast<float*>(s_ring);          // the ring is idle once the last accumulator is done
@@ -250,72 +364,86 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             }
         }
     } else if (warp < TC_PROD_WARP) {
-        // ===================== MMA issuers (each warp runs the uniform loop; one elected lane issues) =====================
+        // ===================== MMA issuer (the warp runs the uniform loop; one elected lane issues) =====================
         {
-            const int mw = warp - TC_MMA_WARP;                   // owns output rows with (row % TC_MMA_WARPS) == mw
-            const uint32_t plane_bytes = P.RW * 16;
+            constexpr uint32_t plane_bytes = RW * 16;
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
             const uint64_t a_desc0 = make_desc(0, plane_bytes, 128);
-            const uint64_t b_desc0 = make_desc(0, 512, 128);
-            const int nk8 = P.KQ / 2;
-            uint32_t fresh = 0;                                  // slots whose next MMA must overwrite (not accumulate)
-            int u = 0;                                           // ring position (valid units only)
+            const uint64_t b_desc0 = make_desc(0, (uint32_t)k * 512, 128);       // 16-B k-chunks are k*32 rows apart
+            constexpr int nk8 = KQ / 2;
+            constexpr int spr = TC_SLOTS >> dsh;
+            TC_PROF_DECL;
+            TC_WAIT(mbar_wait(smem_u32(&bars->zeroed), 0));
+            tc_fence_after();
+            int stage = 0;                                       // ring position (valid units only) and its phase
+            uint32_t phase = 0;
             for (int pass = 0; pass < P.npass; ++pass) {
-                mbar_wait(smem_u32(&bars->wfull), pass & 1);
+                TC_WAIT(mbar_wait(smem_u32(&bars->wfull), pass & 1));
                 tc_fence_after();
                 for (int ri = 0; ri < nin; ++ri) {               // input row y = r0 - pad + ri
                     const int y = r0 - pad + ri;
                     const bool yok = (y >= 0 && y < g.H);
+                    // taps dy whose output row ro = ri - dy*dil lies in the chunk: dy_lo..dy_hi, slots ascending from s0
+                    const int dy_lo = ri > nrows - 1 ? (ri - (nrows - 1) + dil - 1) >> dsh : 0;
+                    const int dy_hi = min(k - 1, ri >> dsh);
+                    const int ndy = dy_hi - dy_lo + 1;
+                    int s0 = 0, n1 = 0, s1 = 0;
+                    if (ndy > 0) {
+                        const int ro_top = ri - dy_lo * dil;
+                        s0 = tc_slot(ro_top, dsh);
+                        s1 = (ro_top & (dil - 1)) * spr;                       // start of this residue class's slot ring
+                        n1 = min(ndy, s1 + spr - s0);                          // taps before the ring wraps
+                    }
                     for (int gl = 0; gl < P.gpp; ++gl) {
-                        if (pass == 0 && gl == 0 && ri < nrows && (ri % TC_MMA_WARPS) == mw) {
-                            // output row ri starts accumulating now: claim its TMEM slot
-                            const int slot = ri % TC_SLOTS, use = ri / TC_SLOTS;
+                        if (pass == 0 && gl == 0 && ri < nrows) {
+                            // output row ri starts accumulating now: its TMEM slot must have been drained and zeroed
+                            const int use = ri / TC_SLOTS;
                             if (use > 0) {
-                                mbar_wait(smem_u32(&bars->acc_empty[slot]), (use - 1) & 1);
+                                TC_WAIT(mbar_wait(smem_u32(&bars->acc_empty[tc_slot(ri, dsh)]), (use - 1) & 1));
                                 tc_fence_after();
                             }
-                            fresh |= 1u << slot;
                         }
                         if (yok) {
-                            const int stage = u % P.stages;
-                            mbar_wait(smem_u32(&bars->full[stage]), (u / P.stages) & 1);
+                            TC_WAIT(mbar_wait(smem_u32(&bars->full[stage]), phase));
                             tc_fence_after();
-                            const uint32_t a_base = ring_base + stage * P.unit_bytes;
-                            for (int dy = 0; dy < k; ++dy) {
-                                const int ro = ri - dy * dil;    // output row (chunk-relative) fed by this tap row
-                                if (ro < 0 || ro >= nrows || (ro % TC_MMA_WARPS) != mw) continue;
-                                const int slot = ro % TC_SLOTS;
-                                const uint32_t d_tmem = tmem_base + slot * 32;
-                                uint32_t acc = (fresh >> slot) & 1u ? 0u : 1u;
-                                fresh &= ~(1u << slot);
-                                // descriptors differ only in the 14-bit start-address field (units of 16 B)
-                                const uint32_t w_lo = (w_base + ((gl * taps + dy * k) * nk8) * 1024) >> 4;
-                                const uint32_t a_lo = a_base >> 4;
-                                if (elect_one()) {
-                                    uint32_t wl = w_lo;
-                                    for (int dx = 0; dx < k; ++dx) {
-                                        uint32_t al = a_lo + dx * dil;
-#pragma unroll 2
-                                        for (int k8 = 0; k8 < nk8; ++k8) {
-                                            tc_mma_tf32(d_tmem, a_desc0 | (uint64_t)al, b_desc0 | (uint64_t)wl, TC_IDESC, acc);
-                                            acc = 1u;
-                                            al += 2 * P.RW;              // two quad planes = 2 * RW * 16 B
-                                            wl += 64;                    // 1 KB per B tile
-                                        }
-                                    }
+                            if (ndy > 0 && elect_one()) {
+                                // descriptors differ only in the 14-bit start-address field (units of 16 B); the
+                                // per-(dx, k8) offsets below are immediates after unrolling
+                                const uint32_t a_lo = (ring_base + stage * UNIT) >> 4;
+                                const uint32_t w_lo = ((w_base + (uint32_t)gl * (k * nk8 * k * 1024)) >> 4) + dy_lo * 32;
+                                const uint32_t d0 = tmem_base + s0 * 32;
+                                const uint32_t id0 = tc_idesc(32u * n1);
+#pragma unroll
+                                for (int dx = 0; dx < k; ++dx)
+#pragma unroll
+                                    for (int k8 = 0; k8 < nk8; ++k8)
+                                        tc_mma_tf32(d0, a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW),
+                                                    b_desc0 | (uint64_t)(w_lo + (dx * nk8 + k8) * k * 64), id0, 1u);
+                                if (n1 < ndy) {                           // the slot ring wrapped: remaining taps start at s1
+                                    const uint32_t d1 = tmem_base + s1 * 32;
+                                    const uint32_t id1 = tc_idesc(32u * (ndy - n1));
+                                    const uint32_t w_l1 = w_lo + n1 * 32;
+#pragma unroll
+                                    for (int dx = 0; dx < k; ++dx)
+#pragma unroll
+                                        for (int k8 = 0; k8 < nk8; ++k8)
+                                            tc_mma_tf32(d1, a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW),
+                                                        b_desc0 | (uint64_t)(w_l1 + (dx * nk8 + k8) * k * 64), id1, 1u);
                                 }
                             }
+                            __syncwarp();
                             if (elect_one()) tc_commit(smem_u32(&bars->empty[stage]));   // stage reusable once these MMAs retire
-                            ++u;
+                            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
                         }
                         if (pass == P.npass - 1 && gl == P.gpp - 1) {
                             const int rdone = ri - (k - 1) * dil;           // output row whose last tap row just passed
-                            if (rdone >= 0 && rdone < nrows && (rdone % TC_MMA_WARPS) == mw && elect_one()) tc_commit(smem_u32(&bars->acc_full[rdone % TC_SLOTS]));
+                            if (rdone >= 0 && rdone < nrows && elect_one()) tc_commit(smem_u32(&bars->acc_full[tc_slot(rdone, dsh)]));
                         }
                     }
                 }
                 if (pass + 1 < P.npass && elect_one()) tc_commit(smem_u32(&bars->wempty));  // weights of this pass no longer read
             }
+            TC_PROF_END(1);
         }
         __syncwarp();
     } else {
@@ -323,7 +451,9 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         {
             const size_t plane = (size_t)g.H * g.W;
             const uint32_t row_bytes = (uint32_t)npx * 16;
-            int u = 0;
+            TC_PROF_DECL;
+            int stage = 0;
+            uint32_t phase = 0;
             for (int pass = 0; pass < P.npass; ++pass) {
                 if (pass > 0) mbar_wait(smem_u32(&bars->wempty), (pass - 1) & 1);
                 {
@@ -340,22 +470,24 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                 for (int ri = 0; ri < nin; ++ri) {
                     const int y = r0 - pad + ri;
                     if (y < 0 || y >= g.H) continue;             // zero padding rows: skipped by the MMA issuer too
-                    for (int gl = 0; gl < P.gpp; ++gl, ++u) {
-                        const int stage = u % P.stages;
-                        mbar_wait(smem_u32(&bars->empty[stage]), ((u / P.stages) & 1) ^ 1);
+                    for (int gl = 0; gl < P.gpp; ++gl) {
+                        TC_WAIT(mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u));
                         const int gk = pass * P.gpp + gl;        // global K-group
-                        const int s = gk / P.gps, qoff = (gk % P.gps) * P.KQ;
+                        const int s = KQ == 8 ? gk : gk >> 1, qoff = KQ == 8 ? 0 : (gk & 1) * KQ;   // 8 / KQ groups per source
                         const float4* sp = reinterpret_cast<const float4*>(g.src[s]) + ((size_t)b * 8 + qoff) * plane
                                            + (size_t)y * g.W + xs;
-                        const uint32_t dst = smem_u32(s_ring) + stage * P.unit_bytes + poff * 16;
+                        const uint32_t dst = smem_u32(s_ring) + stage * UNIT + poff * 16;
                         const uint32_t bar = smem_u32(&bars->full[stage]);
                         if (elect_one()) {
-                            mbar_expect_tx(bar, row_bytes * P.KQ);
-                            for (int q = 0; q < P.KQ; ++q) bulk_g2s(dst + q * P.RW * 16, sp + (size_t)q * plane, row_bytes, bar);
+                            mbar_expect_tx(bar, row_bytes * KQ);
+#pragma unroll
+                            for (int q = 0; q < KQ; ++q) bulk_g2s(dst + q * RW * 16, sp + (size_t)q * plane, row_bytes, bar);
                         }
+                        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
+            TC_PROF_END(2);
         }
         __syncwarp();
     }
@@ -397,21 +529,39 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     for (int i = 0; i < 3; ++i) g.src[i] = d.src[i];
     g.wmma = reinterpret_cast<const float*>(d.weight_mma);
     EpiParams e = make_epi(d);
-    static int smem_set = 0;
-    if (g.plan.smem_bytes > smem_set) {
-        cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
-        if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; }
-        smem_set = TC_SMEM_BUDGET + 1024;
-    }
     dim3 grid(cdiv(d.W, TC_TW), cdiv(d.H, g.RCH), d.B);
     if (d.chan_partials) {
         // partial-sum slots beyond this launch's tile count must read as zero
         cudaError_t err = cudaMemsetAsync(d.chan_partials, 0, (size_t)d.B * conv_tc_tiles(d.H, d.W) * 32 * sizeof(float), stream);
         if (err != cudaSuccess) { set_error("conv_tc memset: %s", cudaGetErrorString(err)); return (int)err; }
     }
-    conv_tc_kernel<<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);
-    return check_launch("paif_conv_forward(tcgen05)");
+    const int kk = d.kh == 1 ? 1 : d.kh, dd = d.kh == 1 ? 1 : d.dil;     // a 1x1 kernel has no dilation
+#define TC_CASE(K_, D_, Q_)                                                                                        \
+    if (kk == K_ && dd == D_ && g.plan.KQ == Q_) {                                                                 \
+        static bool attr_done = false;                                                                              \
+        if (!attr_done) {                                                                                           \
+            cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_>,                                      \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024); \
+            if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; } \
+            attr_done = true;                                                                                       \
+        }                                                                                                           \
+        conv_tc_kernel<K_, D_, Q_><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);                               \
+        return check_launch("paif_conv_forward(tcgen05)");                                                          \
+    }
+    TC_CASE(1, 1, 8) TC_CASE(3, 1, 8) TC_CASE(3, 2, 8) TC_CASE(5, 1, 8) TC_CASE(5, 2, 8) TC_CASE(7, 1, 4) TC_CASE(7, 2, 4)
+#undef TC_CASE
+    set_error("conv_tc: no kernel instance for k=%d dil=%d KQ=%d", d.kh, d.dil, g.plan.KQ);
+    return PAIF_ENOTSUP;
 }
+
+#ifdef PAIF_TC_PROFILE
+extern "C" int paif_debug_tc_counters(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, tc_prof, sizeof(tc_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int conv_tc_kq(int nsrc, int k, int dil) {
     TcPlan p;

@@ -58,8 +58,9 @@ class _ConvW:
         kq = _lib.load().paif_conv_tc_kq(nsrc, k, dil) if (cout == 32 and self.cps == 32) else 0
         if kq:
             G = cin_total // (kq * 4)
-            wt = _round_tf32(w.float()).reshape(cout, G, kq // 2, 2, 4, kh * kw)
-            self.mma = wt.permute(1, 5, 2, 3, 0, 4).contiguous()
+            # [K-group][dx][k8][16-B chunk][dy][cout][4 cin]: all dy taps of one (dx, k8) form one B tile of N = 32*k rows
+            wt = _round_tf32(w.float()).reshape(cout, G, kq // 2, 2, 4, kh, kw)
+            self.mma = wt.permute(1, 6, 2, 3, 5, 0, 4).contiguous()
 
 
 def _round_tf32(w):

@@ -19,6 +19,9 @@ struct Case {
     uint32_t a_step, a_wrap, b_step, b_wrap;   // bytes added to the start addresses per MMA (mod wrap)
     int iters;
     int nissue;          // warps issuing concurrently (each on its own accumulators)
+    uint32_t a_off;      // byte offset of the A start address (operand alignment experiments)
+    int commit_every;    // tcgen05.commit to a scratch mbarrier after this many MMAs (0 = only at the end)
+    int d_step;          // TMEM column step between consecutive MMAs' accumulators when nd > 1 (0 = N)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -31,11 +34,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 __global__ void __launch_bounds__(128, 1) ubench(Case c, long long* out_total, long long* out_issue) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar[4];
+    __shared__ uint64_t scratch_bar[4];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 200 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.001f * (i & 255);
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar[i])), "r"(1u) : "memory");
+        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&scratch_bar[i])), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -49,20 +54,24 @@ __global__ void __launch_bounds__(128, 1) ubench(Case c, long long* out_total, l
     const uint32_t tmem_base = tmem_base_s;
     if ((tid & 31) == 0 && warp < c.nissue) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(c.M >> 4) << 24);
-        const uint32_t a0 = smem_u32(smem) + warp * 4096, b0 = smem_u32(smem) + 100 * 1024 + warp * 2048;
+        const uint32_t a0 = smem_u32(smem) + warp * 8192 + c.a_off, b0 = smem_u32(smem) + 100 * 1024 + warp * 2048;
         uint32_t ao = 0, bo = 0;
-        int d = 0;
+        int d = 0, since_commit = 0;
         const long long t0 = clock64();
         for (int i = 0; i < c.iters; ++i) {
             const uint64_t ad = make_desc(a0 + ao, c.a_lbo, c.a_sbo, c.layout);
             const uint64_t bd = make_desc(b0 + bo, c.b_lbo, c.b_sbo, c.layout);
-            const uint32_t dt = tmem_base + (warp * c.nd + d) * c.N;
+            const uint32_t dt = tmem_base + (c.d_step ? d * c.d_step : (warp * c.nd + d) * c.N);
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                          "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                          ::"r"(dt), "l"(ad), "l"(bd), "r"(idesc), "r"(1u) : "memory");
             ao += c.a_step; if (ao >= c.a_wrap) ao = 0;
             bo += c.b_step; if (bo >= c.b_wrap) bo = 0;
             if (++d == c.nd) d = 0;
+            if (c.commit_every && ++since_commit == c.commit_every) {
+                since_commit = 0;
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&scratch_bar[warp])) : "memory");
+            }
         }
         const long long t1 = clock64();
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[warp])) : "memory");
@@ -108,6 +117,27 @@ int main() {
         {"M128 N128 w-as-M  4 issuing warps ", 128, 128, 2048, 128, 258 * 16, 128, 0, 1, 0, 1, 0, 1, IT, 4},
         {"M128 N192 w-as-M                  ", 128, 192, 2048, 128, 258 * 16, 128, 0, 1, 0, 1, 0, 1, IT, 1},
         {"M128 N160 w-as-M                  ", 128, 160, 2048, 128, 258 * 16, 128, 0, 1, 0, 1, 0, 1, IT, 1},
+        {"N32 4 issuers: pitch 2048, A aligned     ", 128, 32, 2048, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0},
+        {"N32 4 issuers: pitch 2048, A +16 B       ", 128, 32, 2048, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 16},
+        {"N32 4 issuers: pitch 2048, A +32 B       ", 128, 32, 2048, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 32},
+        {"N32 4 issuers: pitch 2048, A +64 B       ", 128, 32, 2048, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 64},
+        {"N32 4 issuers: pitch 2080, A aligned     ", 128, 32, 2080, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0},
+        {"N32 4 issuers: pitch 2112, A aligned     ", 128, 32, 2112, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0},
+        {"N32 4 issuers: pitch 2176, A aligned     ", 128, 32, 2176, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0},
+        {"N32 4 issuers: pitch 2304(+256), aligned ", 128, 32, 2304, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0},
+        {"N32 3 issuers: pitch 2048, A aligned     ", 128, 32, 2048, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 3, 0},
+        {"N32 4 issuers: walk A (+4160/MMA)        ", 128, 32, 2080, 128, 512, 128, 0, 1, 4160, 4 * 4160, 1024, 36 * 1024, IT, 4, 0},
+        {"N64 4 issuers: pitch 2048 aligned        ", 128, 64, 2048, 128, 1024, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0},
+        {"N96 conv-engine layout (1 issuer)          ", 128, 96, 2080, 128, 1536, 128, 0, 1, 0, 1, 0, 1, IT, 1, 0, 0, 0},
+        {"N96 conv layout, D slides by 32 cols        ", 128, 96, 2080, 128, 1536, 128, 0, 13, 0, 1, 0, 1, IT, 1, 0, 0, 32},
+        {"N96 conv layout, commit every 12            ", 128, 96, 2080, 128, 1536, 128, 0, 1, 0, 1, 0, 1, IT, 1, 0, 12, 0},
+        {"N96 conv layout, commit every 12, walk A/B  ", 128, 96, 2080, 128, 1536, 128, 0, 13, 4160, 4 * 4160, 3072, 36 * 1024, IT, 1, 0, 12, 32},
+        {"N32 conv layout, commit every 12 (1 issuer) ", 128, 32, 2080, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 1, 0, 12, 0},
+        {"N32 conv layout, commit every 4  (1 issuer) ", 128, 32, 2080, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 1, 0, 4, 0},
+        {"N32 conv layout, commit every 12 (4 issuers)", 128, 32, 2080, 128, 512, 128, 0, 1, 0, 1, 0, 1, IT, 4, 0, 12, 0},
+        {"N224 conv layout (k7), commit every 14      ", 128, 224, 2080, 128, 3584, 128, 0, 1, 0, 1, 0, 1, IT, 1, 0, 14, 0},
+        {"N96 2 issuers                                ", 128, 96, 2080, 128, 1536, 128, 0, 1, 0, 1, 0, 1, IT, 2, 0, 0, 0},
+        {"N64 conv layout (1 issuer)                   ", 128, 64, 2080, 128, 1024, 128, 0, 1, 0, 1, 0, 1, IT, 1, 0, 0, 0},
     };
     long long *d_tot, *d_iss;
     cudaMalloc(&d_tot, 148 * 8); cudaMalloc(&d_iss, 148 * 8);

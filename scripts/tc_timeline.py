@@ -1,0 +1,41 @@
+"""Development tool: role timeline of the tcgen05 conv engine (wait vs busy cycles per role), using the
+-DPAIF_TC_PROFILE build.  PAIF_B200_PROFILE_LIB=1 python scripts/tc_timeline.py"""
+import ctypes, os, sys
+os.environ["PAIF_B200_PROFILE_LIB"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from paif_b200 import _lib, fusion
+lib = _lib.load()
+lib.paif_debug_tc_counters.argtypes = [ctypes.c_void_p, ctypes.c_int]
+DEV = torch.device("cuda:0")
+B, H, W = 16, 480, 640
+rt = fusion._Runtime(B, H, W, 32, DEV, _lib.ENGINE_TCGEN05, False)
+buf = (ctypes.c_ulonglong * 16)()
+def counters(reset=1):
+    lib.paif_debug_tc_counters(buf, reset)
+    return list(buf)
+torch.manual_seed(0)
+maps = [torch.randn(B, 8, H, W, 4, device=DEV) for _ in range(6)]
+a = torch.tensor([0.25], device=DEV)
+cases = [("k3 cin32 prelu", 1, 3, 1, dict(slope=a)),
+         ("k3 cin96 prelu+3res", 3, 3, 1, dict(slope=a, post_scale=0.333, post_res=maps[3:6])),
+         ("k7 cin32", 1, 7, 1, dict()),
+         ("k3d2 cin32 bn prelu 3res pre", 1, 3, 2, dict(slope=a, post_res=maps[3:6], want_pre=True)),
+         ("k1 cin32 3res", 1, 1, 1, dict(post_res=maps[3:6])),
+         ("k1 cin96", 3, 1, 1, dict())]
+for name, nsrc, k, dil, kw in cases:
+    w = torch.randn(32, 32 * nsrc, k, k, device=DEV) * 0.05
+    cw = fusion._ConvW(w, nsrc, k, dil)
+    for _ in range(2):
+        rt.conv(maps[:nsrc], cw, **kw)
+    counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); rt.conv(maps[:nsrc], cw, **kw); e1.record()
+    torch.cuda.synchronize()
+    c = counters()
+    ms = e0.elapsed_time(e1)
+    ctas = 5 * B * ((H + 31) // 32 if k != 7 else (H + 15) // 16)
+    def f(i, nw):   # per warp averages
+        return c[2 * i] / max(c[2 * i + 1], 1)
+    print("%-30s %.3f ms | epilogue warps: wait %.0f%% of %.0f kcyc | mma warps: wait %.0f%% of %.0f kcyc | producer: wait %.0f%% of %.0f kcyc" % (
+        name, ms, 100 * f(0, 8), c[1] / (8 * ctas) / 1e3, 100 * f(1, 4), c[3] / (4 * ctas) / 1e3, 100 * f(2, 1), c[5] / ctas / 1e3), flush=True)

@@ -72,8 +72,10 @@ def test_guided_filter_decomposition(shape, smooth):
     e32 = (got - LF).abs().max().item()
     e64 = (got.double() - LF64).abs().max().item()
     ref_noise = (LF.double() - LF64).abs().max().item()          # the fp32 reference's own rounding error
-    assert e32 < 1e-4, e32
-    assert e64 < max(2e-5, 2 * ref_noise), (e64, ref_noise)
+    # the fp32 cumsum reference is itself 2e-5 .. 5e-4 away from the exact answer (grows with image size);
+    # the kernel must be close to the exact answer and within the reference's own noise of the reference
+    assert e64 < max(5e-5, 0.5 * ref_noise), (e64, ref_noise)
+    assert e32 < 5e-5 + 1.5 * ref_noise, (e32, ref_noise)
 
 
 @pytest.mark.parametrize("k,dil,nsrc", [(3, 1, 1), (3, 1, 3), (3, 2, 1), (7, 1, 1), (1, 1, 3), (5, 2, 2)])
