@@ -122,6 +122,14 @@ int paif_dwconv_forward(const float* x, const float* w, int relu_in,
                         const float* mask_src, const float* post_res, float* out,
                         int C, int k, int dil, int B, int H, int W, void* stream);
 
+/* Fused DilConv (operations_m.py:494-506), C = 32, BatchNorm in eval mode folded to scale/shift:
+ *   out = ch_scale * pw1x1(dw_kxk_dil(relu(x))) + ch_shift + x + r1 + r2      (r1, r2 optional residual maps:
+ * the Cell_Chain residual, core/model_fusion_auto.py:445, and Cell_Decom's "+ feature", :516).
+ * dw: [C][k*k] depthwise taps, pw: [C_out][C_in] pointwise weights. */
+int paif_dilconv_forward(const float* x, const float* dw, const float* pw, const float* ch_scale,
+                         const float* ch_shift, const float* r1, const float* r2, float* out,
+                         int C, int k, int dil, int B, int H, int W, void* stream);
+
 /* 2-arg ChannelPool — core/model_fusion_auto.py:1352-1355.
  * pooled[B][H][W][4] = (max_c ir, mean_c ir, max_c vis, mean_c vis). */
 int paif_channel_pool(const float* ir_f, const float* vis_f, float* pooled,

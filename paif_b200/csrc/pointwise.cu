@@ -58,6 +58,97 @@ dwconv_kernel(const float* __restrict__ xin, const float* __restrict__ w, int re
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused DilConv (operations_m.py:494-506) for C = 32:
+//   out = BN(pw1x1(dw_kxk_dil(relu(x)))) + x + r1 + r2          (BN eval-mode scale/shift; r1, r2 optional)
+// One thread per pixel keeps the 32 depthwise results' contribution in 32 accumulators; the 1x1
+// weights (BN scale folded in, [cin][cout]) and the depthwise taps are broadcast from shared memory.
+// HBM-bound design point: x is read once (+L1/L2 halo re-reads), no intermediate map is written.
+// ------------------------------------------------------------------------------------------
+template <int K, int DIL>
+__global__ void __launch_bounds__(256, 2)
+dilconv_fused_kernel(const float* __restrict__ xin, const float* __restrict__ dw, const float* __restrict__ pw,
+                     const float* __restrict__ ch_scale, const float* __restrict__ ch_shift,
+                     const float* __restrict__ r1, const float* __restrict__ r2, float* __restrict__ out,
+                     int H, int W) {
+    constexpr int TAPS = K * K, PAD = DIL * (K - 1) / 2;
+    __shared__ __align__(16) float s_pw[32 * 32];      // [cin][cout], scaled by BN
+    __shared__ __align__(16) float s_dw[TAPS * 32];    // [tap][channel]
+    __shared__ __align__(16) float s_sh[32];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < 1024; i += 256) {
+        const int ci = i >> 5, co = i & 31;
+        s_pw[i] = pw[co * 32 + ci] * (ch_scale ? ch_scale[co] : 1.f);
+    }
+    for (int i = tid; i < TAPS * 32; i += 256) {
+        const int t = i >> 5, c = i & 31;
+        s_dw[i] = dw[c * TAPS + t];
+    }
+    if (tid < 32) s_sh[tid] = ch_shift ? ch_shift[tid] : 0.f;
+    __syncthreads();
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float4* xp = reinterpret_cast<const float4*>(xin) + (size_t)b * 8 * plane;
+    // tap offsets (clamped into the image) and validity: the same for every channel quad
+    int toff[TAPS];
+    float tval[TAPS];
+#pragma unroll
+    for (int ty = 0; ty < K; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < K; ++tx) {
+            const int yy = y + ty * DIL - PAD, xx = x + tx * DIL - PAD;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            toff[ty * K + tx] = ok ? yy * W + xx : (int)pix;
+            tval[ty * K + tx] = ok ? 1.f : 0.f;
+        }
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = s_sh[c];
+    float4 v[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) v[t] = __ldg(xp + toff[t]);
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+            const float4 ww = *reinterpret_cast<const float4*>(&s_dw[t * 32 + q * 4]);
+            const float m = tval[t];
+            t4.x = fmaf(fmaxf(v[t].x, 0.f) * m, ww.x, t4.x); t4.y = fmaf(fmaxf(v[t].y, 0.f) * m, ww.y, t4.y);
+            t4.z = fmaf(fmaxf(v[t].z, 0.f) * m, ww.z, t4.z); t4.w = fmaf(fmaxf(v[t].w, 0.f) * m, ww.w, t4.w);
+        }
+        if (q + 1 < 8) {                                   // next quad's taps are in flight during the 1x1 below
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) v[t] = __ldg(xp + (size_t)(q + 1) * plane + toff[t]);
+        }
+        const float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(&s_pw[(q * 4 + j) * 32]);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 w4 = wr[c4];
+                acc[c4 * 4 + 0] = fmaf(tv[j], w4.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(tv[j], w4.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(tv[j], w4.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(tv[j], w4.w, acc[c4 * 4 + 3]);
+            }
+        }
+    }
+    const size_t base = (size_t)b * 8 * plane + pix;
+    float4 rx[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const size_t off = base + q * plane;
+        rx[q] = __ldg(reinterpret_cast<const float4*>(xin) + off);
+        if (r1) rx[q] = f4_add(rx[q], __ldg(reinterpret_cast<const float4*>(r1) + off));
+        if (r2) rx[q] = f4_add(rx[q], __ldg(reinterpret_cast<const float4*>(r2) + off));
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        reinterpret_cast<float4*>(out)[base + q * plane] =
+            make_float4(acc[q * 4 + 0] + rx[q].x, acc[q * 4 + 1] + rx[q].y, acc[q * 4 + 2] + rx[q].z, acc[q * 4 + 3] + rx[q].w);
+}
+
+// ------------------------------------------------------------------------------------------
 // 2-arg ChannelPool (core/model_fusion_auto.py:1352-1355)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -330,18 +421,83 @@ eca_bwd_pass2_kernel(const float* __restrict__ gw, const float* __restrict__ e, 
 constexpr int OUT_C = 32;
 __device__ __forceinline__ int border_class(int p, int n) { return p == 0 ? 0 : (p == n - 1 ? 2 : 1); }
 
+// Forward of the merged stem_out stencil.  Every feature pixel q is read ONCE: its 25 tap products
+// d_t(q) = <w_t, f(q)> (interior-class weights) go to shared memory, then each output pixel gathers
+// out(p) = sum_t d_t(p + t).  The one-pixel image border (where the second conv's zero padding
+// changes the merged weights) is recomputed directly with its class weights.
+constexpr int OF_TX = 32, OF_TY = 16;                          // output tile
+constexpr int OF_RX = OF_TX + 4, OF_RY = OF_TY + 4;            // feature region (halo 2)
+constexpr int OF_NQ = OF_RX * OF_RY;                           // 720
+constexpr int OF_SMEM = (25 * OF_NQ + 25 * OUT_C) * 4;
+
 __global__ void __launch_bounds__(256)
 out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
                    float* __restrict__ out, float* __restrict__ pre_out, int H, int W) {
-    extern __shared__ __align__(16) float swm[];   // [9][25][32]
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < 9 * 25 * OUT_C; i += 256) swm[i] = wm[i];
+    extern __shared__ __align__(16) float of_smem[];
+    float* sd = of_smem;                         // [25][OF_NQ]
+    float* sw = of_smem + 25 * OF_NQ;            // [25][32] interior class (cls 4)
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 25 * OUT_C; i += 256) sw[i] = wm[4 * 25 * OUT_C + i];
     __syncthreads();
     const int b = blockIdx.z;
-    PIX_SETUP();
-    if (x >= W || y >= H) return;
-    const int cls = border_class(y, H) * 3 + border_class(x, W);
+    const int x0 = blockIdx.x * OF_TX, y0 = blockIdx.y * OF_TY;
+    const size_t plane = (size_t)H * W;
     const float4* fp = reinterpret_cast<const float4*>(feat) + (size_t)b * (OUT_C / 4) * plane;
+    for (int q = tid; q < OF_NQ; q += 256) {
+        const int ry = q / OF_RX, rx = q - ry * OF_RX;
+        const int yy = y0 - 2 + ry, xx = x0 - 2 + rx;
+        float4 v[OUT_C / 4];
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < OUT_C / 4; ++c)
+            v[c] = in ? __ldg(fp + c * plane + (size_t)yy * W + xx) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+        for (int t = 0; t < 25; ++t) {
+            const float4* wv = reinterpret_cast<const float4*>(sw + t * OUT_C);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < OUT_C / 4; c += 2) {
+                const float4 w0 = wv[c], w1 = wv[c + 1];
+                a0 = fmaf(v[c].x, w0.x, a0); a0 = fmaf(v[c].y, w0.y, a0); a0 = fmaf(v[c].z, w0.z, a0); a0 = fmaf(v[c].w, w0.w, a0);
+                a1 = fmaf(v[c + 1].x, w1.x, a1); a1 = fmaf(v[c + 1].y, w1.y, a1); a1 = fmaf(v[c + 1].z, w1.z, a1); a1 = fmaf(v[c + 1].w, w1.w, a1);
+            }
+            sd[t * OF_NQ + q] = a0 + a1;
+        }
+    }
+    __syncthreads();
+    const float a = __ldg(slope_p);
+    for (int o = tid; o < OF_TX * OF_TY; o += 256) {
+        const int oy = o / OF_TX, ox = o - oy * OF_TX;
+        const int y = y0 + oy, x = x0 + ox;
+        if (y >= H || x >= W) continue;
+        if (border_class(y, H) != 1 || border_class(x, W) != 1) continue;     // image border: out_border_kernel
+        float acc = 0.f;
+#pragma unroll
+        for (int ty = 0; ty < 5; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 5; ++tx) acc += sd[(ty * 5 + tx) * OF_NQ + (oy + ty) * OF_RX + ox + tx];
+        const size_t pi = (size_t)b * plane + (size_t)y * W + x;
+        if (pre_out) pre_out[pi] = acc;
+        out[pi] = tanhf(prelu_f(acc, a));
+    }
+}
+
+// The one-pixel image border of the merged stem_out stencil: its weights depend on the border class
+// (which taps of the second 3x3 conv fall on its zero padding).  2(W + H) - 4 pixels per image.
+__global__ void __launch_bounds__(128)
+out_border_kernel(const float* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
+                  float* __restrict__ out, float* __restrict__ pre_out, int H, int W) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int per = 2 * W + 2 * (H - 2);
+    if (i >= per) return;
+    int x, y;
+    if (i < W) { y = 0; x = i; }
+    else if (i < 2 * W) { y = H - 1; x = i - W; }
+    else { const int j = i - 2 * W; y = 1 + (j >> 1); x = (j & 1) ? W - 1 : 0; }
+    const size_t plane = (size_t)H * W;
+    const float4* fp = reinterpret_cast<const float4*>(feat) + (size_t)b * (OUT_C / 4) * plane;
+    const int cls = border_class(y, H) * 3 + border_class(x, W);
     float acc = 0.f;
     for (int ty = 0; ty < 5; ++ty) {
         const int yy = y + ty - 2;
@@ -349,18 +505,19 @@ out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm,
         for (int tx = 0; tx < 5; ++tx) {
             const int xx = x + tx - 2;
             if (xx < 0 || xx >= W) continue;
-            const float4* wv = reinterpret_cast<const float4*>(swm + ((size_t)cls * 25 + ty * 5 + tx) * OUT_C);
+            const float4* wv = reinterpret_cast<const float4*>(wm + ((size_t)cls * 25 + ty * 5 + tx) * OUT_C);
 #pragma unroll
-            for (int q = 0; q < OUT_C / 4; ++q) {
-                const float4 v = fp[q * plane + (size_t)yy * W + xx];
-                const float4 ww = wv[q];
+            for (int c = 0; c < OUT_C / 4; ++c) {
+                const float4 v = __ldg(fp + c * plane + (size_t)yy * W + xx);
+                const float4 ww = __ldg(wv + c);
                 acc = fmaf(v.x, ww.x, acc); acc = fmaf(v.y, ww.y, acc);
                 acc = fmaf(v.z, ww.z, acc); acc = fmaf(v.w, ww.w, acc);
             }
         }
     }
-    if (pre_out) pre_out[(size_t)b * plane + pix] = acc;
-    out[(size_t)b * plane + pix] = tanhf(prelu_f(acc, *slope_p));
+    const size_t pi = (size_t)b * plane + (size_t)y * W + x;
+    if (pre_out) pre_out[pi] = acc;
+    out[pi] = tanhf(prelu_f(acc, __ldg(slope_p)));
 }
 
 __global__ void __launch_bounds__(256)
@@ -471,6 +628,25 @@ extern "C" int paif_dwconv_forward(const float* x, const float* w, int relu_in, 
     return check_launch("paif_dwconv_forward");
 }
 
+extern "C" int paif_dilconv_forward(const float* x, const float* dw, const float* pw, const float* ch_scale,
+                                    const float* ch_shift, const float* r1, const float* r2, float* out,
+                                    int C, int k, int dil, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(x && dw && pw && out, "null pointer");
+    PAIF_REQUIRE(C == 32, "C must be 32");
+    PAIF_REQUIRE(k >= 1 && k <= 7 && (k & 1) && dil >= 1, "bad kernel size / dilation");
+    PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
+    PAIF_REQUIRE((long long)H * W < (1ll << 31), "image too large");
+#define DC_CASE(K_, D_)                                                                                              \
+    if (k == K_ && dil == D_) {                                                                                      \
+        dilconv_fused_kernel<K_, D_><<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(x, dw, pw, ch_scale, ch_shift, r1, r2, out, H, W); \
+        return check_launch("paif_dilconv_forward");                                                                 \
+    }
+    DC_CASE(3, 1) DC_CASE(3, 2)
+#undef DC_CASE
+    set_error("paif_dilconv_forward: kernel %d dilation %d not instantiated (3x3, dilation 1 or 2)", k, dil);
+    return PAIF_ENOTSUP;
+}
+
 extern "C" int paif_channel_pool(const float* ir_f, const float* vis_f, float* pooled,
                                  int C, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(ir_f && vis_f && pooled, "null pointer");
@@ -550,7 +726,7 @@ static int out_smem_attr() {
     static bool done = false;
     if (done) return 0;
     const int bytes = 9 * 25 * OUT_C * sizeof(float);
-    cudaError_t e1 = cudaFuncSetAttribute(out_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e1 = cudaFuncSetAttribute(out_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("out kernel smem attr failed"); return (int)(e1 ? e1 : e2); }
     done = true;
@@ -563,7 +739,9 @@ extern "C" int paif_out_forward(const float* feat, const float* wm, const float*
     PAIF_REQUIRE(C == OUT_C, "C must be 32");
     PAIF_REQUIRE(H >= 2 && W >= 2, "H, W must be >= 2");
     if (int r = out_smem_attr()) return r;
-    out_forward_kernel<<<pix_grid(W, H, B), dim3(32, 8), 9 * 25 * OUT_C * sizeof(float), ST>>>(feat, wm, slope, out, pre_out, H, W);
+    out_forward_kernel<<<dim3(cdiv(W, OF_TX), cdiv(H, OF_TY), B), 256, OF_SMEM, ST>>>(feat, wm, slope, out, pre_out, H, W);
+    if (int r = check_launch("paif_out_forward")) return r;
+    out_border_kernel<<<dim3(cdiv(2 * W + 2 * (H - 2), 128), B), 128, 0, ST>>>(feat, wm, slope, out, pre_out, H, W);
     return check_launch("paif_out_forward");
 }
 

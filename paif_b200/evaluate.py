@@ -1,0 +1,142 @@
+"""Sharded (one process per GPU) attack-tolerant evaluation around the fusion drop-in.
+
+What the reference does in one process with ``batch_size=1`` (robust_test.py:95-212):
+``attack_both`` PGD (attack/attack.py:417-514) -> forward on the attacked pair -> arg-max ->
+``sklearn.metrics.confusion_matrix(labels=0..8)`` summed on the host -> ``compute_results``
+(util/util.py:31-55).  Here the frames are split contiguously over the ranks of a
+``torch.distributed`` group, every rank accumulates an int64 confusion matrix on its GPU
+(``paif_confusion_accumulate``) and ONE all-reduce(SUM) of 81 int64 values merges them: integer
+addition is associative, so the N-GPU matrix is bit-identical to the 1-GPU one.
+
+Sharding invariance needs three things besides the integer reduction, all handled here:
+ * the PGD start point is drawn from a generator keyed by (seed, GLOBAL frame index), not from the
+   unseeded global RNG the reference uses (attack/attack.py:434);
+ * frames are evaluated one at a time through the task wrapper, because its min-max normalisation
+   spans the whole batch it is given (core/model_fusion_auto.py:721-723; the reference only ever
+   passes batch 1);
+ * the fusion kernels are batch-position invariant and deterministic (tests/test_gpu_parity.py).
+
+The segmentation consumer is any stock-PyTorch ``nn.Module`` mapping ``[B,3,H,W] -> [B,K,h,w]``
+logits (the reference uses SegFormer MiT-B3, which stays stock PyTorch by the scope contract).
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous split of ``range(n_items)``: the first ``n_items % world_size`` ranks get one extra."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank %d outside world of %d" % (rank, world_size))
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+class ConfusionMeter:
+    """int64 confusion matrix (rows = label, cols = prediction; labels outside 0..K-1, e.g. the
+    ignore index 255, are skipped exactly as sklearn's ``labels=`` argument does, robust_test.py:210)."""
+
+    def __init__(self, num_classes=9, device="cuda"):
+        self.num_classes = num_classes
+        self.conf = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=device)
+
+    def update(self, label, pred):
+        """label, pred: integer CUDA tensors of equal numel."""
+        if not (label.is_cuda and pred.is_cuda):
+            raise RuntimeError("ConfusionMeter.update counts on the GPU: label and pred must be CUDA tensors")
+        label = label.reshape(-1).to(torch.int64).contiguous()
+        pred = pred.reshape(-1).to(torch.int64).contiguous()
+        if label.numel() != pred.numel():
+            raise ValueError("label and pred differ in size")
+        with torch.cuda.device(label.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(label.device).cuda_stream)
+            _lib.call("paif_confusion_accumulate", label.data_ptr(), pred.data_ptr(), label.numel(),
+                      self.num_classes, self.conf.data_ptr(), stream)
+        return self
+
+    def all_reduce(self, group=None):
+        """Sum the matrices of all ranks in place (NCCL over NVLink for CUDA tensors, gloo for CPU ones)."""
+        all_reduce_confusion(self.conf, group)
+        return self
+
+    def results(self):
+        return compute_results(self.conf)
+
+
+def all_reduce_confusion(conf, group=None):
+    """all-reduce(SUM) of an int64 confusion matrix; a no-op without an initialised process group."""
+    import torch.distributed as dist
+    if conf.dtype != torch.int64:
+        raise TypeError("confusion matrices are reduced as int64 so that the sum is exact")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(conf, op=dist.ReduceOp.SUM, group=group)
+    return conf
+
+
+def compute_results(conf_total):
+    """precision / recall / IoU per class with the reference's conventions (util/util.py:31-55:
+    unlabeled class included, NaN where a denominator is zero).  Returns three float64 tensors."""
+    c = conf_total.detach().to("cpu", torch.float64)
+    tp = c.diag()
+    col, row = c.sum(0), c.sum(1)
+    nan = torch.full_like(tp, float("nan"))
+    precision = torch.where(col == 0, nan, tp / col)
+    recall = torch.where(row == 0, nan, tp / row)
+    union = row + col - tp
+    iou = torch.where(union == 0, nan, tp / union)
+    return precision, recall, iou
+
+
+def seeded_delta(shape, epsilon, seed, global_index, device):
+    """U(-eps, eps) PGD start point that depends only on (seed, global frame index)."""
+    g = torch.Generator(device="cpu").manual_seed((int(seed) * 1000003 + int(global_index)) % (2 ** 63 - 1))
+    return ((torch.rand(shape, generator=g) * 2.0 - 1.0) * epsilon).to(device)
+
+
+def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255., attack_iters=10,
+                    seed=0, global_index=0, ignore_index=255):
+    """``attack_both(..., attack_loss='l_seg', attack_way='PGD')`` (attack/attack.py:417-514) for one
+    frame, with a seeded start.  ``model(ir, vis) -> (fused, seg_logits)``.  Faithful to the reference
+    including its quirk of never zeroing ``delta.grad`` (the step uses the sign of the running sum of
+    gradients, attack/attack.py:501-512).  Returns (delta_vis, delta_ir)."""
+    dev = x_vis.device
+    d_vis = seeded_delta(x_vis.shape, epsilon, seed, 2 * global_index, dev)
+    d_ir = seeded_delta(x_ir.shape, epsilon, seed, 2 * global_index + 1, dev)
+    d_vis = torch.max(torch.min(d_vis, 1 - x_vis), 0 - x_vis).requires_grad_(True)
+    d_ir = torch.max(torch.min(d_ir, 1 - x_ir), 0 - x_ir).requires_grad_(True)
+    for _ in range(attack_iters):
+        with torch.enable_grad():
+            _, seg = model(x_ir + d_ir, x_vis + d_vis)
+            seg = F.interpolate(seg, size=label.shape[1:], mode="bilinear", align_corners=False)
+            loss = F.cross_entropy(seg, label, ignore_index=ignore_index)
+        loss.backward()
+        with torch.no_grad():
+            for d, x in ((d_vis, x_vis), (d_ir, x_ir)):
+                d.data = torch.clamp(d + alpha * torch.sign(d.grad), min=-epsilon, max=epsilon)
+                d.data = torch.max(torch.min(d, 1 - x), 0 - x)
+    return d_vis.detach(), d_ir.detach()
+
+
+def robust_eval(model, frames, num_classes=9, attack_iters=10, epsilon=8 / 255., alpha=2 / 255., seed=0,
+                rank=0, world_size=1, group=None):
+    """Evaluate this rank's shard of ``frames`` (an indexable of ``(vis[3,H,W], ir[1,H,W], label[H,W])``
+    host or device tensors) under PGD and return the all-reduced :class:`ConfusionMeter`.
+    ``attack_iters=0`` gives the clean evaluation of test_original.py:98-258."""
+    dev = next(model.parameters()).device
+    meter = ConfusionMeter(num_classes, dev)
+    for gi in shard_range(len(frames), rank, world_size):
+        vis, ir, label = frames[gi]
+        vis, ir = vis.to(dev)[None].float(), ir.to(dev)[None].float()
+        label = label.to(dev)[None].long()
+        if attack_iters > 0:
+            d_vis, d_ir = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gi)
+            vis, ir = vis + d_vis, ir + d_ir
+        with torch.no_grad():
+            _, seg = model(ir, vis)
+            seg = F.interpolate(seg, size=label.shape[1:], mode="bilinear", align_corners=False)
+            meter.update(label, seg.argmax(1))
+    return meter.all_reduce(group)

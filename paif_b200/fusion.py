@@ -274,15 +274,21 @@ class DilConv(_Primitive):
         C = dw.shape[0]
         s, sh = _bn_fold(self.op[3])
         p = {"dw": dw.reshape(C, -1).contiguous().float(), "pw": _ConvW(self.op[2].weight.detach(), 1, 1, 1),
-             "s": s, "sh": sh}
+             "pw_raw": self.op[2].weight.detach().reshape(C, C).contiguous().float(), "s": s, "sh": sh}
         if need_bwd:
             p["dw_t"] = dw.flip(-1, -2).reshape(C, -1).contiguous().float()
             p["pw_d"] = _dgrad_groups(self.op[2].weight.detach(), 1, 1, scale=s)[0]
         return p
 
     def fwd(self, rt, p, x, extras):
-        t = rt.dwconv(x, p["dw"], self.k, self.d, relu_in=True)
-        out = rt.conv([t], p["pw"], ch_scale=p["s"], ch_shift=p["sh"], post_res=[x] + list(extras))[0]
+        extras = list(extras)
+        if (self.k, self.d) not in ((3, 1), (3, 2)):       # only the 3x3 shapes have a fused kernel instance
+            t = rt.dwconv(x, p["dw"], self.k, self.d, relu_in=True)
+            return rt.conv([t], p["pw"], ch_scale=p["s"], ch_shift=p["sh"], post_res=[x] + extras)[0], ()
+        out = torch.empty_like(x)
+        rt.call("paif_dilconv_forward", x.data_ptr(), p["dw"].data_ptr(), p["pw_raw"].data_ptr(), p["s"].data_ptr(),
+                p["sh"].data_ptr(), _ptr(extras[0]) if extras else None, _ptr(extras[1]) if len(extras) > 1 else None,
+                out.data_ptr(), rt.C, self.k, self.d, rt.B, rt.H, rt.W)
         return out, ()
 
     def bwd(self, rt, p, rec, g, extra_add, x=None):

@@ -1,0 +1,90 @@
+"""CPU: host logic of the sharded evaluation (paif_b200/evaluate.py) — partitioning, seeded PGD start,
+metric conventions, and the world_size-2 integer all-reduce over gloo."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fusion_oracle as fo
+from paif_b200 import evaluate as ev
+
+
+def test_shard_range_is_a_contiguous_partition():
+    for n in (0, 1, 7, 32, 33, 1000):
+        for world in (1, 2, 3, 4, 8):
+            parts = [list(ev.shard_range(n, r, world)) for r in range(world)]
+            assert sum(parts, []) == list(range(n))
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_seeded_delta_depends_only_on_seed_and_global_index():
+    a = ev.seeded_delta((1, 3, 8, 9), 8 / 255., seed=5, global_index=17, device="cpu")
+    b = ev.seeded_delta((1, 3, 8, 9), 8 / 255., seed=5, global_index=17, device="cpu")
+    c = ev.seeded_delta((1, 3, 8, 9), 8 / 255., seed=5, global_index=18, device="cpu")
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert a.abs().max().item() <= 8 / 255.
+
+
+def _reference_style_results(conf):
+    """util/util.py:31-55 restated with the reference's loop structure (consider_unlabeled=True)."""
+    n = conf.shape[0]
+    p, r, i = np.zeros(n), np.zeros(n), np.zeros(n)
+    for cid in range(n):
+        p[cid] = np.nan if conf[:, cid].sum() == 0 else float(conf[cid, cid]) / float(conf[:, cid].sum())
+        r[cid] = np.nan if conf[cid, :].sum() == 0 else float(conf[cid, cid]) / float(conf[cid, :].sum())
+        den = conf[cid, :].sum() + conf[:, cid].sum() - conf[cid, cid]
+        i[cid] = np.nan if den == 0 else float(conf[cid, cid]) / float(den)
+    return p, r, i
+
+
+def test_compute_results_follows_reference_conventions():
+    g = torch.Generator().manual_seed(3)
+    conf = torch.randint(0, 1000, (9, 9), generator=g, dtype=torch.int64)
+    conf[:, 4] = 0          # a class never predicted  -> precision NaN
+    conf[6, :] = 0          # a class never present    -> recall NaN
+    got = ev.compute_results(conf)
+    want = _reference_style_results(conf.numpy())
+    for a, b in zip(got, want):
+        np.testing.assert_allclose(a.numpy(), b, rtol=0, atol=0, equal_nan=True)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n_frames, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(11)
+    labels = torch.randint(0, 10, (n_frames, 24, 31), generator=g)      # 9 = out of range, ignored
+    labels[labels == 9] = 255
+    preds = torch.randint(0, 9, (n_frames, 24, 31), generator=g)
+    conf = torch.zeros(9, 9, dtype=torch.int64)
+    for i in ev.shard_range(n_frames, rank, world):
+        conf += fo.confusion_matrix(labels[i], preds[i], 9)
+    ev.all_reduce_confusion(conf)
+    torch.save(conf, os.path.join(out_dir, "conf_%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_all_reduce_is_bit_exact(tmp_path):
+    n_frames, world = 7, 2
+    mp.spawn(_worker, args=(world, _free_port(), n_frames, str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(11)
+    labels = torch.randint(0, 10, (n_frames, 24, 31), generator=g)
+    labels[labels == 9] = 255
+    preds = torch.randint(0, 9, (n_frames, 24, 31), generator=g)
+    full = fo.confusion_matrix(labels, preds, 9)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), "conf_%d.pt" % r))
+        assert got.dtype == torch.int64 and torch.equal(got, full)
+    assert int(full.sum()) == int((labels != 255).sum())

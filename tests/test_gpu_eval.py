@@ -1,0 +1,52 @@
+"""GPU: confusion counting kernel through ConfusionMeter, and sharding invariance of the PGD robust
+evaluation (the N-rank result equals the 1-rank result bit for bit)."""
+import pytest
+import torch
+import torch.nn as nn
+
+import paif_b200
+from oracle import fusion_oracle as fo
+from paif_b200 import evaluate as ev
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class TinyTask(nn.Module):
+    """Stand-in for Network_MM_Searched: fusion drop-in + a small stock-PyTorch segmentation head."""
+
+    def __init__(self):
+        super().__init__()
+        self.enhance_net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+        self.head = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1, stride=2), nn.ReLU(), nn.Conv2d(8, 9, 3, padding=1, stride=2))
+
+    def forward(self, ir, vis):
+        fused = self.enhance_net(ir, vis)
+        x = torch.cat([fused, vis[:, 1:3]], 1)
+        return fused, self.head(x)
+
+
+def test_confusion_meter_matches_oracle():
+    g = torch.Generator().manual_seed(0)
+    label = torch.randint(0, 10, (3, 40, 56), generator=g)
+    label[label == 9] = 255
+    pred = torch.randint(0, 9, (3, 40, 56), generator=g)
+    m = ev.ConfusionMeter(9, DEV)
+    m.update(label[:2].to(DEV), pred[:2].to(DEV)).update(label[2:].to(DEV), pred[2:].to(DEV))
+    assert torch.equal(m.conf.cpu(), fo.confusion_matrix(label, pred, 9))
+
+
+def test_pgd_robust_eval_is_sharding_invariant():
+    torch.manual_seed(0)
+    model = TinyTask().to(DEV).eval()
+    g = torch.Generator().manual_seed(1)
+    frames = [(torch.rand(3, 24, 40, generator=g), torch.rand(1, 24, 40, generator=g),
+               torch.randint(0, 9, (24, 40), generator=g)) for _ in range(5)]
+    whole = ev.robust_eval(model, frames, attack_iters=2, rank=0, world_size=1).conf.cpu()
+    parts = sum(ev.robust_eval(model, frames, attack_iters=2, rank=r, world_size=3).conf.cpu() for r in range(3))
+    assert torch.equal(whole, parts)
+    assert int(whole.sum()) == 5 * 24 * 40
+    clean = ev.robust_eval(model, frames, attack_iters=0).conf.cpu()
+    acc_clean = clean.diag().sum().item() / clean.sum().item()
+    acc_adv = whole.diag().sum().item() / whole.sum().item()
+    assert acc_adv <= acc_clean + 1e-9          # the attack maximises the loss of the same model

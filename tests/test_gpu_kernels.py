@@ -151,6 +151,30 @@ def test_dwconv_pool_spa_out():
     assert (out.cpu() - ref).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("k,dil,nres", [(3, 2, 2), (3, 1, 0), (3, 2, 1)])
+def test_dilconv_fused(k, dil, nres):
+    """DilConv (operations_m.py:494-506) + chain residuals in one kernel, against plain torch fp32 ops."""
+    B, H, W = 2, 19, 45
+    torch.manual_seed(7)
+    x = torch.randn(B, 32, H, W)
+    dw = torch.randn(32, 1, k, k) * 0.3
+    pw = torch.randn(32, 32, 1, 1) * 0.2
+    cs, sh = torch.rand(32) + 0.5, torch.randn(32) * 0.1
+    res = [torch.randn(B, 32, H, W) for _ in range(nres)]
+    pad = dil * (k - 1) // 2
+    t = F.conv2d(F.relu(x), dw, None, 1, pad, dil, groups=32)
+    ref = F.conv2d(t, pw) * cs.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1) + x + sum(res)
+    xc = to_c4(x).to(DEV)
+    out = torch.empty_like(xc)
+    dwd, pwd = dw.reshape(32, -1).contiguous().to(DEV), pw.reshape(32, 32).contiguous().to(DEV)
+    csd, shd = cs.to(DEV), sh.to(DEV)
+    rd = [to_c4(r).to(DEV) for r in res]
+    _lib.call("paif_dilconv_forward", xc.data_ptr(), dwd.data_ptr(), pwd.data_ptr(), csd.data_ptr(), shd.data_ptr(),
+              rd[0].data_ptr() if nres > 0 else None, rd[1].data_ptr() if nres > 1 else None, out.data_ptr(),
+              32, k, dil, B, H, W, stream())
+    assert (from_c4(out).cpu() - ref).abs().max().item() < 5e-5
+
+
 def test_confusion_matrix_kernel_is_exact():
     g = torch.Generator().manual_seed(5)
     label = torch.randint(0, 10, (3, 97, 131), generator=g)
