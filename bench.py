@@ -29,6 +29,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FLOP_PER_PX = 519336.0          # conv MACs x 2 per pixel of one pair
+BYTES_PER_PX = 1891 * 4.0       # layer-granular algorithmic traffic, fp32 storage (1202 ch read + 689 written)
 
 
 def parse():
@@ -44,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", action="store_true", help="print the per-launch CUDA-event table of one step to stderr")
+    ap.add_argument("--bwd-steps", type=int, default=3, help="timed forward+backward-to-input steps (0 = skip)")
     return ap.parse_args()
 
 
@@ -209,6 +211,39 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.summary() if sampler else None
 
+    # attack inner step (BASELINE configs[4]): forward + backward-to-input on resident inputs
+    fwd_bwd = None
+    if args.bwd_steps > 0:
+        gout = torch.rand(B, 1, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) - 0.5
+
+        def step_fwd_bwd():
+            a = ir_d.detach().requires_grad_(True)
+            v = vis_d.detach().requires_grad_(True)
+            net(a, v).backward(gout)
+            return a.grad, v.grad
+
+        for _ in range(2):
+            step_fwd_bwd()
+        net.profile = [] if args.table else None
+        ms_fb = timed(step_fwd_bwd, args.bwd_steps)
+        prof_fb, net.profile = net.profile, None
+        fwd_bwd = {"value": B * world * args.bwd_steps / (ms_fb * 1e-3), "unit": "pairs/s", "ms_per_step": ms_fb / args.bwd_steps,
+                   "steps": args.bwd_steps, "launches_per_step": net.last_launches,
+                   "what": "forward + backward-to-input (the PGD inner step of attack/attack.py:444-501 without the "
+                           "segmentation consumer), batch %d per GPU, inputs resident" % B}
+        if args.table and rank == 0 and prof_fb:
+            per = len(prof_fb) // args.bwd_steps
+            agg = {}
+            for (n, m, a, b) in prof_fb[-per:]:
+                key = n if not m else "%s k%d d%d cin%d" % (n, m["k"], m["dil"], m["cin"])
+                t = a.elapsed_time(b)
+                agg[key] = (agg.get(key, (0, 0.0))[0] + 1, agg.get(key, (0, 0.0))[1] + t)
+            tot = sum(t for _, t in agg.values())
+            sys.stderr.write("--- forward+backward step, launches aggregated by kind ---\n")
+            for key, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                sys.stderr.write("%-44s x%-3d %8.3f ms %5.1f%%\n" % (key, cnt, t, 100 * t / tot))
+            sys.stderr.write("sum of launches %.3f ms (fwd+bwd step %.3f ms)\n" % (tot, ms_fb / args.bwd_steps))
+
     if args.table and rank == 0:
         per = len(prof) // args.steps
         tot = sum(a.elapsed_time(b) for (_, _, a, b) in prof[-per:])
@@ -216,22 +251,30 @@ def run_ours(args):
             t = a.elapsed_time(b)
             extra = ""
             if m:
-                extra = " k%d d%d cin%d  %.1f TFLOP/s" % (m["k"], m["dil"], m["cin"], m["flops"] / (t * 1e-3) / 1e12)
+                extra = " k%d d%d cin%d  %.1f TFLOP/s  %.0f GB/s" % (m["k"], m["dil"], m["cin"], m["flops"] / (t * 1e-3) / 1e12,
+                                                                     m["bytes"] / (t * 1e-3) / 1e9)
             sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
         sys.stderr.write("sum of launches %.3f ms (step %.3f ms)\n" % (tot, ms / args.steps))
-    # dominant kernel: the dense-conv engine (all conv launches of the timed steps)
+    # dominant kernel: the dense-conv engine (all conv launches of the timed steps).  After the wide-N MMA
+    # rewrite every conv shape of the genotype except the 7x7 is HBM-bound, so the engine is judged against
+    # the HBM roofline: algorithmic bytes (each source / residual map read once, each output written once).
     conv = [(m, a.elapsed_time(b)) for (n, m, a, b) in prof if n == "paif_conv_forward"]
     other_ms = sum(a.elapsed_time(b) for (n, m, a, b) in prof if n != "paif_conv_forward")
     conv_ms = sum(t for _, t in conv)
     conv_flops = sum(m["flops"] for m, _ in conv)
+    conv_bytes = sum(m["bytes"] for m, _ in conv)
     pk = peaks()
     engine_id = conv[0][0]["engine"] if conv else 0
-    if engine_id == _lib.ENGINE_TCGEN05:
-        peak_tf, peak_note = pk["bf16_tflops_sustained"] / 2.0, "TF32 tensor = 1/2 x %s sustained bf16 cuBLAS peak" % pk["source"]
-    else:
-        peak_tf, peak_note = pk["bf16_tflops_sustained"] / 2.0, ("direct fp32 FFMA engine measured against the TF32 tensor "
-                                                                 "peak (1/2 x %s sustained bf16) it is meant to be replaced by" % pk["source"])
+    peak_tf = pk["bf16_tflops_sustained"] / 2.0
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    achieved_gbs = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")          # from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
 
     if rank != 0:
         if world > 1:
@@ -253,14 +296,19 @@ def run_ours(args):
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(ir_h.numel() * 4 + vis_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "dense-conv engine (all %d conv launches per step)" % (len(conv) // max(args.steps, 1)),
-                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": None, "peak_note": peak_note,
+        "roofline": {"bound": "hbm", "kernel": "dense-conv engine conv_tc_kernel (all %d conv launches per step)" % (len(conv) // max(args.steps, 1)),
+                     "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
+                     "traffic": traffic, "peak_note": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % pk["source"],
+                     "bytes_per_launch": conv_bytes / max(len(conv), 1), "avg_launch_ms": conv_ms / max(len(conv), 1),
                      "conv_share_of_step": conv_ms / (conv_ms + other_ms) if conv_ms + other_ms > 0 else None,
-                     "avg_launch_ms": conv_ms / max(len(conv), 1),
-                     "whole_net_frac_of_tensor_roof": (FLOP_PER_PX * H * W * B * args.steps / (ms * 1e-3) / 1e12) / peak_tf},
+                     "tensor_tflops": achieved_tf, "tensor_frac_of_tf32_peak": achieved_tf / peak_tf,
+                     "tf32_peak_note": "TF32 = 1/2 x %s sustained bf16 cuBLAS peak" % pk["source"],
+                     "whole_step_frac_of_hbm_roof": (BYTES_PER_PX * H * W * B * args.steps / (ms * 1e-3) / 1e9) / pk["hbm_gbs"],
+                     "whole_step_note": "SURVEY 8d layer-granular bytes (1891 ch x 4 B per pixel) / step time / HBM peak"},
         "clocks": clocks,
     }
+    if fwd_bwd is not None:
+        line["fwd_bwd"] = fwd_bwd
     if not args.no_cpu_baseline and world == 1:
         v, cores, times = cpu_port_pairs_per_s(args.cpu_baseline_steps, H, W)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",

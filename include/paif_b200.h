@@ -198,11 +198,14 @@ int paif_spa_blend_backward(const float* gagg, const float* ir_f, const float* v
                             float* g_ir_f, float* g_vis_f, int C, int B, int H, int W, void* stream);
 
 /* adjoint of paif_gf_decomp_forward w.r.t. feat (source) and residue (guide).
+ * stats: the same guide statistics the forward used (paif_gf_guide_stats).
  * glf1/glf2: gradients w.r.t. the two LF maps.  gfeat: C4 map (written).
- * gres_partial: [C/4][B][H][W] per-quad partial guide gradients (summed by the stem backward). */
-int paif_gf_decomp_backward(const float* feat, const float* residue,
+ * gres_partial: [C/4][B][H][W] per-quad partial guide gradients (summed by the stem backward).
+ * work: caller-owned scratch of paif_gf_backward_work_floats(C,B,H,W) floats. */
+long long paif_gf_backward_work_floats(int C, int B, int H, int W);
+int paif_gf_decomp_backward(const float* feat, const float* residue, const float* stats,
                             const float* glf1, const float* glf2,
-                            float* gfeat, float* gres_partial,
+                            float* gfeat, float* gres_partial, float* work,
                             int C, int B, int H, int W, void* stream);
 
 /* stem backward, pass 1: total = sum of up to 4 gradient maps + route(sum_q gres_partial) to the

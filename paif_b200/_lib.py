@@ -64,7 +64,8 @@ SIGNATURES = {
     "paif_eca_bwd_pass2": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_spa_blend_backward_pre": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_spa_blend_backward": [_f, _f, _f, _f, _f, _f, _i, _f, _f, _i, _i, _i, _i, _f],
-    "paif_gf_decomp_backward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_gf_backward_work_floats": [_i, _i, _i, _i],
+    "paif_gf_decomp_backward": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_stem_backward_pre": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
@@ -92,7 +93,8 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "paif_last_error_string" else _i
+        fn.restype = (C.c_char_p if name == "paif_last_error_string" else
+                      _ll if name == "paif_gf_backward_work_floats" else _i)
     if lib.paif_abi_version() != 1:
         raise PaifError("libpaif_b200.so ABI version mismatch")
     _lib = lib

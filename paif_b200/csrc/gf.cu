@@ -6,161 +6,17 @@
 //       A = cov/(var+eps); b = mz - A mx;  LF_eps,c = box(A)/N * g + box(b)/N
 //   box = 9x9 window sum clipped to the image.
 //
-// One CTA = one 32x32 output tile of one channel quad of one image.  Two box-filter levels =
-// halo 4+4: the 48x48 input region is staged in shared memory, every box filter is two separable
-// 9-tap passes through shared memory, 4 outputs per thread, written without running-sum
-// subtraction so no cancellation error is introduced (the statistics stay fp32 throughout).
+// Forward and adjoint are row-marching, register-resident warp kernels (see below); all statistics stay fp32.
 #include "common.cuh"
 
 namespace paif {
 
-constexpr int GF_T = 32;            // output tile
-constexpr int GF_R8 = GF_T + 16;    // 48: region with halo 8
-constexpr int GF_R4 = GF_T + 8;     // 40: region with halo 4
-constexpr int GF_NT = 512;
 constexpr float GF_EPS1 = 0.001f, GF_EPS2 = 0.0001f;
-
-// horizontal 9-tap sums: dst[r][c] = sum_{k<9} src(r, c+k); 4 outputs per work item.
-template <class Ld4>
-__device__ __forceinline__ void box_h(Ld4 ld, float* dst, int dp, int rows, int ocols) {
-    const int oc4 = ocols / 4;
-    for (int it = threadIdx.x; it < rows * oc4; it += GF_NT) {
-        const int r = it / oc4, c = (it - r * oc4) * 4;
-        const float4 a = ld(r, c), b = ld(r, c + 4), d = ld(r, c + 8);
-        const float m = a.w + b.x + b.y + b.z + b.w + d.x;
-        float4 o;
-        o.x = a.x + a.y + a.z + m;
-        o.y = a.y + a.z + m + d.y;
-        o.z = a.z + m + d.y + d.z;
-        o.w = m + d.y + d.z + d.w;
-        *reinterpret_cast<float4*>(dst + r * dp + c) = o;
-    }
-}
-
-// vertical 9-tap sums of src[rows][sp]: value(r,c) = sum_{k<9} src[r+k][c]; st(r, c, value).
-template <class St>
-__device__ __forceinline__ void box_v(const float* src, int sp, int orows, int cols, St st) {
-    const int or4 = orows / 4;
-    for (int it = threadIdx.x; it < or4 * cols; it += GF_NT) {
-        const int seg = it / cols, c = it - seg * cols, r = seg * 4;
-        float v[12];
-#pragma unroll
-        for (int k = 0; k < 12; ++k) v[k] = src[(r + k) * sp + c];
-        const float m = v[3] + v[4] + v[5] + v[6] + v[7] + v[8];
-        st(r + 0, c, v[0] + v[1] + v[2] + m);
-        st(r + 1, c, v[1] + v[2] + m + v[9]);
-        st(r + 2, c, v[2] + m + v[9] + v[10]);
-        st(r + 3, c, m + v[9] + v[10] + v[11]);
-    }
-}
 
 // clipped-window pixel count along one axis
 __device__ __forceinline__ float win_count(int p, int n) {
     const int lo = p - 4 < 0 ? 0 : p - 4, hi = p + 4 > n - 1 ? n - 1 : p + 4;
     return (float)(hi - lo + 1);
-}
-
-struct GfSmem {
-    float g[GF_R8 * GF_R8];
-    float z[4][GF_R8 * GF_R8];
-    float tmp[GF_R8 * GF_R4];
-    float mx[GF_R4 * GF_R4];
-    float iv1[GF_R4 * GF_R4];
-    float iv2[GF_R4 * GF_R4];
-    float mz[GF_R4 * GF_R4];
-    float ab[4][GF_R4 * GF_R4];           // A1, b1, A2, b2 of the current channel
-    float out[2][GF_T * GF_T * 4];        // LF1 / LF2, [pixel][4 channels]
-};
-
-template <class S>
-__device__ __forceinline__ void gf_load_region(S& s, const float* feat, const float* residue,
-                                               int b, int q, int Q, int H, int W, int x0, int y0) {
-    const size_t plane = (size_t)H * W;
-    const float4* zp = reinterpret_cast<const float4*>(feat) + ((size_t)b * Q + q) * plane;
-    const float* gp = residue + (size_t)b * plane;
-    for (int i = threadIdx.x; i < GF_R8 * GF_R8; i += GF_NT) {
-        const int r = i / GF_R8, c = i - r * GF_R8;
-        const int y = y0 - 8 + r, x = x0 - 8 + c;
-        float gv = 0.f;
-        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            gv = gp[(size_t)y * W + x];
-            zv = zp[(size_t)y * W + x];
-        }
-        s.g[i] = gv;
-        s.z[0][i] = zv.x; s.z[1][i] = zv.y; s.z[2][i] = zv.z; s.z[3][i] = zv.w;
-    }
-}
-
-// mean_g, 1/(var+eps) on the 40x40 region (zero outside the image).
-template <class S>
-__device__ __forceinline__ void gf_guide_stats(S& s, int H, int W, int x0, int y0) {
-    box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&s.g[r * GF_R8 + c]); },
-          s.tmp, GF_R4, GF_R8, GF_R4);
-    __syncthreads();
-    box_v(s.tmp, GF_R4, GF_R4, GF_R4, [&](int r, int c, float v) {
-        const int y = y0 - 4 + r, x = x0 - 4 + c;
-        const bool in = y >= 0 && y < H && x >= 0 && x < W;
-        s.mx[r * GF_R4 + c] = in ? __fdiv_rn(v, win_count(y, H) * win_count(x, W)) : 0.f;
-    });
-    __syncthreads();
-    box_h([&](int r, int c) {
-              float4 v = *reinterpret_cast<const float4*>(&s.g[r * GF_R8 + c]);
-              return make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-          },
-          s.tmp, GF_R4, GF_R8, GF_R4);
-    __syncthreads();
-    box_v(s.tmp, GF_R4, GF_R4, GF_R4, [&](int r, int c, float v) {
-        const int y = y0 - 4 + r, x = x0 - 4 + c;
-        const bool in = y >= 0 && y < H && x >= 0 && x < W;
-        float i1 = 0.f, i2 = 0.f;
-        if (in) {
-            const float m = s.mx[r * GF_R4 + c];
-            const float var = __fdiv_rn(v, win_count(y, H) * win_count(x, W)) - m * m;
-            i1 = __fdiv_rn(1.f, var + GF_EPS1);
-            i2 = __fdiv_rn(1.f, var + GF_EPS2);
-        }
-        s.iv1[r * GF_R4 + c] = i1;
-        s.iv2[r * GF_R4 + c] = i2;
-    });
-    __syncthreads();
-}
-
-// A1,b1,A2,b2 of channel ch on the 40x40 region -> s.ab (zero outside the image); also s.mz.
-template <class S>
-__device__ __forceinline__ void gf_channel_ab(S& s, int ch, int H, int W, int x0, int y0) {
-    const float* z = s.z[ch];
-    box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&z[r * GF_R8 + c]); },
-          s.tmp, GF_R4, GF_R8, GF_R4);
-    __syncthreads();
-    box_v(s.tmp, GF_R4, GF_R4, GF_R4, [&](int r, int c, float v) {
-        const int y = y0 - 4 + r, x = x0 - 4 + c;
-        const bool in = y >= 0 && y < H && x >= 0 && x < W;
-        s.mz[r * GF_R4 + c] = in ? __fdiv_rn(v, win_count(y, H) * win_count(x, W)) : 0.f;
-    });
-    __syncthreads();
-    box_h([&](int r, int c) {
-              const float4 a = *reinterpret_cast<const float4*>(&s.g[r * GF_R8 + c]);
-              const float4 v = *reinterpret_cast<const float4*>(&z[r * GF_R8 + c]);
-              return make_float4(a.x * v.x, a.y * v.y, a.z * v.z, a.w * v.w);
-          },
-          s.tmp, GF_R4, GF_R8, GF_R4);
-    __syncthreads();
-    box_v(s.tmp, GF_R4, GF_R4, GF_R4, [&](int r, int c, float v) {
-        const int y = y0 - 4 + r, x = x0 - 4 + c;
-        const bool in = y >= 0 && y < H && x >= 0 && x < W;
-        float A1 = 0.f, b1 = 0.f, A2 = 0.f, b2 = 0.f;
-        if (in) {
-            const int i = r * GF_R4 + c;
-            const float m = s.mx[i], mzv = s.mz[i];
-            const float cov = __fdiv_rn(v, win_count(y, H) * win_count(x, W)) - m * mzv;
-            A1 = cov * s.iv1[i]; b1 = mzv - A1 * m;
-            A2 = cov * s.iv2[i]; b2 = mzv - A2 * m;
-        }
-        const int i = r * GF_R4 + c;
-        s.ab[0][i] = A1; s.ab[1][i] = b1; s.ab[2][i] = A2; s.ab[3][i] = b2;
-    });
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -261,10 +117,14 @@ __device__ __forceinline__ void gf_ab(float mz, float cov, float mx, float i1, f
     A2 = __fmul_rn(cov, i2); b2 = __fmaf_rn(-A2, mx, mz);
 }
 
-template <bool VEC>
+// MODE 0: forward, writes LF_1e-3 / LF_1e-4.
+// MODE 1 (adjoint, "direct" guide term): lf1/lf2 are the INCOMING gradients w.r.t. the two LF maps; writes
+//         gxd[q][b][y][x] = sum_{c in quad} sum_e gLF_e,c * mean_A_e,c  (d LF / d guide at fixed mean_A, mean_b).
+template <bool VEC, int MODE>
 __global__ void __launch_bounds__(GM_WPC * 32)
 gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict__ guide,
                         const float* __restrict__ stats, float* __restrict__ lf1, float* __restrict__ lf2,
+                        float* __restrict__ gxd,
                         int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
     extern __shared__ float4 gm_ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -398,222 +258,326 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
                 float A1, b1, A2, b2, A1o, b1o, A2o, b2o;
                 gf_ab(mz[k], cov[k], mx[k], i1[k], i2[k], A1, b1, A2, b2);
                 gf_ab(mzo[k], covo[k], mxo[k], i1o[k], i2o[k], A1o, b1o, A2o, b2o);
-                SA1[k][c] += A1 - A1o; Sb1[k][c] += b1 - b1o;
-                SA2[k][c] += A2 - A2o; Sb2[k][c] += b2 - b2o;
+                SA1[k][c] += A1 - A1o; SA2[k][c] += A2 - A2o;
+                if (MODE == 0) { Sb1[k][c] += b1 - b1o; Sb2[k][c] += b2 - b2o; }
             }
         }
         slot = slot == 8 ? 0 : slot + 1;
         if (t < 16) continue;
 
         // ---- output row yo (always inside the image and the chunk)
-        float go[4], rno[4];
-        ld_cols4<VEC>(gp + (size_t)yo * W, xo, W, go);
+        float rno[4];
         {
             const float cy = win_count(yo, H);
 #pragma unroll
             for (int k = 0; k < 4; ++k) rno[k] = co[k] > 0.f ? __frcp_rn(cy * co[k]) : 0.f;
         }
-        float r1[4][4], r2[4][4];                  // [column][channel]
+        if (MODE == 0) {
+            float go[4];
+            ld_cols4<VEC>(gp + (size_t)yo * W, xo, W, go);
+            float r1[4][4], r2[4][4];                  // [column][channel]
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a[4], hA[4], hb[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = SA1[k][c];
+                hsum9(a, hA);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = Sb1[k][c];
+                hsum9(a, hb);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r1[k][c] = __fmaf_rn(hA[k] * rno[k], go[k], hb[k] * rno[k]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = SA2[k][c];
+                hsum9(a, hA);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = Sb2[k][c];
+                hsum9(a, hb);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) r2[k][c] = __fmaf_rn(hA[k] * rno[k], go[k], hb[k] * rno[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (co[k] > 0.f) {
+                    const size_t o = (size_t)yo * W + xo + k;
+                    o1[o] = make_float4(r1[k][0], r1[k][1], r1[k][2], r1[k][3]);
+                    o2[o] = make_float4(r2[k][0], r2[k][1], r2[k][2], r2[k][3]);
+                }
+            }
+        } else {
+            float4 l1[4], l2[4];
+            ld_z4(reinterpret_cast<const float4*>(o1) + (size_t)yo * W, xo, W, l1);
+            ld_z4(reinterpret_cast<const float4*>(o2) + (size_t)yo * W, xo, W, l2);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float a[4], h1[4], h2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = SA1[k][c];
+                hsum9(a, h1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = SA2[k][c];
+                hsum9(a, h2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float g1 = c == 0 ? l1[k].x : (c == 1 ? l1[k].y : (c == 2 ? l1[k].z : l1[k].w));
+                    const float g2 = c == 0 ? l2[k].x : (c == 1 ? l2[k].y : (c == 2 ? l2[k].z : l2[k].w));
+                    acc[k] = fmaf(g1, h1[k] * rno[k], fmaf(g2, h2[k] * rno[k], acc[k]));
+                }
+            }
+            float* gx = gxd + ((size_t)q * B + b) * plane + (size_t)yo * W;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (co[k] > 0.f) gx[xo + k] = acc[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// adjoint, marching formulation (same warp-per-item structure as the forward; three passes):
+//   pass A (gf_adjoint_level2_kernel): forward level-1 statistics + adjoint of the level-2 boxes
+//       gA'_e = box(gLF_e g / N), gb_e = box(gLF_e / N), then the pointwise chain rule through
+//       A_e = cov/(var+eps_e), b_e = mean_z - A_e mean_g; writes gcov/N and gmean_z/N per channel
+//       (two maps) and this quad's share of gvar/N and gmean_g/N (two planes per quad).
+//   pass B (gf_forward_march_kernel<., 1>): the direct guide term sum gLF_e mean_A_e.
+//   pass C (gf_adjoint_level1_kernel): adjoint of the level-1 boxes: g_z = box(gcov/N) g + box(gmean_z/N),
+//       g_guide(quad) = sum_c box(gcov/N) z_c + 2 g box(gvar/N) + box(gmean_g/N) + direct term.
+// Formulas: SURVEY.md 8a (checked there against autograd in fp64).
+// ------------------------------------------------------------------------------------------
+constexpr int GA_OUTW = 120;               // one horizontal pass per kernel: 128 - 8 columns per warp
+
+template <bool VEC>
+__global__ void __launch_bounds__(64)
+gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict__ guide, const float* __restrict__ stats,
+                         const float* __restrict__ glf1, const float* __restrict__ glf2,
+                         float* __restrict__ gc, float* __restrict__ gm, float* __restrict__ gvn, float* __restrict__ gmn,
+                         int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int item = blockIdx.x * 2 + warp;
+    if (item >= nitems) return;
+    const int q = item % Q; item /= Q;
+    const int strip = item % nstrips; item /= nstrips;
+    const int chunk = item % nchunks;
+    const int b = item / nchunks;
+    const int x0 = strip * GA_OUTW, y0 = chunk * RC;
+    const int rows = min(RC, H - y0);
+    const int xr = x0 - 4 + 4 * lane, xs = xr + 4;
+    const size_t plane = (size_t)H * W;
+    const size_t qoff = ((size_t)b * Q + q) * plane;
+    const float4* zp = reinterpret_cast<const float4*>(feat) + qoff;
+    const float4* l1p = reinterpret_cast<const float4*>(glf1) + qoff;
+    const float4* l2p = reinterpret_cast<const float4*>(glf2) + qoff;
+    const float* gp = guide + (size_t)b * plane;
+    const float* mxp = stats + (size_t)b * plane;
+    const float* i1p = stats + ((size_t)B + b) * plane;
+    const float* i2p = stats + ((size_t)2 * B + b) * plane;
+    float4* gcp = reinterpret_cast<float4*>(gc) + qoff;
+    float4* gmp = reinterpret_cast<float4*>(gm) + qoff;
+    float* gvp = gvn + ((size_t)q * B + b) * plane;
+    float* gnp = gmn + ((size_t)q * B + b) * plane;
+
+    float cr[4], cs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        cr[k] = (xr + k >= 0 && xr + k < W) ? win_count(xr + k, W) : 0.f;
+        cs[k] = (xs + k < W && 4 * lane + k < GA_OUTW) ? win_count(xs + k, W) : 0.f;
+    }
+    float Sz[4][4], Sgz[4][4], P1[4][4], P2[4][4], P3[4][4], P4[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Sz[k][c] = Sgz[k][c] = P1[k][c] = P2[k][c] = P3[k][c] = P4[k][c] = 0.f; }
+
+    const int nt = rows + 8;
+    for (int t = 0; t < nt; ++t) {
+        const int yr = y0 - 4 + t;                 // row entering the vertical windows
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {     // 0: entering row (+), 1: leaving row (-)
+            const int y = side == 0 ? yr : yr - 9;
+            if (y < 0 || y >= H || (side == 1 && t < 9)) continue;
+            const float sg = side == 0 ? 1.f : -1.f;
+            float4 z[4], l1[4], l2[4];
+            float g[4];
+            ld_z4(zp + (size_t)y * W, xr, W, z);
+            ld_z4(l1p + (size_t)y * W, xr, W, l1);
+            ld_z4(l2p + (size_t)y * W, xr, W, l2);
+            ld_cols4<VEC>(gp + (size_t)y * W, xr, W, g);
+            const float cy = win_count(y, H);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float rn = cr[k] > 0.f ? __frcp_rn(cy * cr[k]) : 0.f;
+                const float w1 = sg * rn, wg = sg * __fmul_rn(g[k], rn), sgk = sg * g[k];
+                const float zc[4] = {z[k].x, z[k].y, z[k].z, z[k].w};
+                const float a1[4] = {l1[k].x, l1[k].y, l1[k].z, l1[k].w};
+                const float a2[4] = {l2[k].x, l2[k].y, l2[k].z, l2[k].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    Sz[k][c] = fmaf(sg, zc[c], Sz[k][c]);
+                    Sgz[k][c] = fmaf(sgk, zc[c], Sgz[k][c]);
+                    P1[k][c] = fmaf(wg, a1[c], P1[k][c]);
+                    P2[k][c] = fmaf(w1, a1[c], P2[k][c]);
+                    P3[k][c] = fmaf(wg, a2[c], P3[k][c]);
+                    P4[k][c] = fmaf(w1, a2[c], P4[k][c]);
+                }
+            }
+        }
+        if (t < 8) continue;
+        const int ys = yr - 4;                     // level-1 row, inside the chunk and the image
+        float mx[4], i1[4], i2[4], rn[4];
+        ld_cols4<VEC>(mxp + (size_t)ys * W, xs, W, mx);
+        ld_cols4<VEC>(i1p + (size_t)ys * W, xs, W, i1);
+        ld_cols4<VEC>(i2p + (size_t)ys * W, xs, W, i2);
+        {
+            const float cy = win_count(ys, H);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rn[k] = cs[k] > 0.f ? __frcp_rn(cy * cs[k]) : 0.f;
+        }
+        float oc[4][4], om[4][4], GV[4] = {0.f, 0.f, 0.f, 0.f}, GM[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            float a[4], hA[4], hb[4];
+            float a[4], bz[4], bg[4], pa1[4], pb1[4], pa2[4], pb2[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = SA1[k][c];
-            hsum9(a, hA);
+            for (int k = 0; k < 4; ++k) a[k] = Sz[k][c];
+            hsum9(a, bz);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sb1[k][c];
-            hsum9(a, hb);
+            for (int k = 0; k < 4; ++k) a[k] = Sgz[k][c];
+            hsum9(a, bg);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) r1[k][c] = __fmaf_rn(hA[k] * rno[k], go[k], hb[k] * rno[k]);
+            for (int k = 0; k < 4; ++k) a[k] = P1[k][c];
+            hsum9(a, pa1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = SA2[k][c];
-            hsum9(a, hA);
+            for (int k = 0; k < 4; ++k) a[k] = P2[k][c];
+            hsum9(a, pb1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sb2[k][c];
-            hsum9(a, hb);
+            for (int k = 0; k < 4; ++k) a[k] = P3[k][c];
+            hsum9(a, pa2);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) r2[k][c] = __fmaf_rn(hA[k] * rno[k], go[k], hb[k] * rno[k]);
+            for (int k = 0; k < 4; ++k) a[k] = P4[k][c];
+            hsum9(a, pb2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float mz = bz[k] * rn[k];
+                const float cov = fmaf(-mx[k], mz, bg[k] * rn[k]);
+                const float A1 = cov * i1[k], A2 = cov * i2[k];
+                const float gA1 = fmaf(-pb1[k], mx[k], pa1[k]), gA2 = fmaf(-pb2[k], mx[k], pa2[k]);
+                const float gcov = gA1 * i1[k] + gA2 * i2[k];
+                const float gmz = pb1[k] + pb2[k] - gcov * mx[k];
+                GV[k] -= gA1 * A1 * i1[k] + gA2 * A2 * i2[k];
+                GM[k] -= pb1[k] * A1 + pb2[k] * A2 + gcov * mz;
+                oc[k][c] = gcov * rn[k];
+                om[k][c] = gmz * rn[k];
+            }
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (co[k] > 0.f) {
-                const size_t o = (size_t)yo * W + xo + k;
-                o1[o] = make_float4(r1[k][0], r1[k][1], r1[k][2], r1[k][3]);
-                o2[o] = make_float4(r2[k][0], r2[k][1], r2[k][2], r2[k][3]);
+            if (cs[k] > 0.f) {
+                const size_t o = (size_t)ys * W + xs + k;
+                gcp[o] = make_float4(oc[k][0], oc[k][1], oc[k][2], oc[k][3]);
+                gmp[o] = make_float4(om[k][0], om[k][1], om[k][2], om[k][3]);
+                gvp[o] = GV[k] * rn[k];
+                gnp[o] = (GM[k] - 2.f * mx[k] * GV[k]) * rn[k];
             }
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// adjoint (SURVEY.md 8a "Guided-filter adjoint"; checked there against autograd in fp64)
-// ------------------------------------------------------------------------------------------
-struct GfBwdSmem {
-    float g[GF_R8 * GF_R8];
-    float z[4][GF_R8 * GF_R8];
-    float tmp[GF_R8 * GF_R4];
-    float mx[GF_R4 * GF_R4];
-    float iv1[GF_R4 * GF_R4];
-    float iv2[GF_R4 * GF_R4];
-    float mz[GF_R4 * GF_R4];
-    float ab[4][GF_R4 * GF_R4];      // A1, b1, A2, b2 (forward recompute)
-    float gl[2][GF_R8 * GF_R8];      // incoming dL/dLF_eps of the current channel
-    float gab[4][GF_R4 * GF_R4];     // dL/dA1', dL/db1, dL/dA2', dL/db2 ; slots 0/1 reused for g_cov/N, g_my/N
-    float gvar[GF_R4 * GF_R4];
-    float gmx[GF_R4 * GF_R4];
-    float gx[GF_T * GF_T];           // guide gradient accumulated over this quad's channels
-    float gy[GF_T * GF_T * 4];
-};
-
-__device__ __forceinline__ float f4_get(const float4& v, int j) {
-    return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
-}
-
-__global__ void __launch_bounds__(GF_NT)
-gf_backward_kernel(const float* __restrict__ feat, const float* __restrict__ residue,
-                   const float* __restrict__ glf1, const float* __restrict__ glf2,
-                   float* __restrict__ gfeat, float* __restrict__ gres_partial, int Q, int B, int H, int W) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    GfBwdSmem& s = *reinterpret_cast<GfBwdSmem*>(smem_raw);
-    const int x0 = blockIdx.x * GF_T, y0 = blockIdx.y * GF_T;
-    const int q = blockIdx.z % Q, b = blockIdx.z / Q;
+template <bool VEC>
+__global__ void __launch_bounds__(64)
+gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict__ guide,
+                         const float* __restrict__ gc, const float* __restrict__ gm,
+                         const float* __restrict__ gvn, const float* __restrict__ gmn,
+                         float* __restrict__ gfeat, float* __restrict__ gres_partial,
+                         int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int item = blockIdx.x * 2 + warp;
+    if (item >= nitems) return;
+    const int q = item % Q; item /= Q;
+    const int strip = item % nstrips; item /= nstrips;
+    const int chunk = item % nchunks;
+    const int b = item / nchunks;
+    const int x0 = strip * GA_OUTW, y0 = chunk * RC;
+    const int rows = min(RC, H - y0);
+    const int xs = x0 - 4 + 4 * lane, xo = xs + 4;
     const size_t plane = (size_t)H * W;
-
-    gf_load_region(s, feat, residue, b, q, Q, H, W, x0, y0);
-    for (int i = threadIdx.x; i < GF_R4 * GF_R4; i += GF_NT) { s.gvar[i] = 0.f; s.gmx[i] = 0.f; }
-    for (int i = threadIdx.x; i < GF_T * GF_T; i += GF_NT) s.gx[i] = 0.f;
-    __syncthreads();
-    gf_guide_stats(s, H, W, x0, y0);
-
-    const float4* g1p = reinterpret_cast<const float4*>(glf1) + ((size_t)b * Q + q) * plane;
-    const float4* g2p = reinterpret_cast<const float4*>(glf2) + ((size_t)b * Q + q) * plane;
-
-    for (int ch = 0; ch < 4; ++ch) {
-        gf_channel_ab(s, ch, H, W, x0, y0);
-        for (int i = threadIdx.x; i < GF_R8 * GF_R8; i += GF_NT) {
-            const int r = i / GF_R8, c = i - r * GF_R8;
-            const int y = y0 - 8 + r, x = x0 - 8 + c;
-            float a = 0.f, d = 0.f;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                a = f4_get(g1p[(size_t)y * W + x], ch);
-                d = f4_get(g2p[(size_t)y * W + x], ch);
-            }
-            s.gl[0][i] = a; s.gl[1][i] = d;
-        }
-        __syncthreads();
-        // pointwise term sum_e gLF_e * mean_A_e on the tile
-#pragma unroll 1
-        for (int e = 0; e < 2; ++e) {
-            const float* src = s.ab[2 * e];
-            box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&src[r * GF_R4 + c]); },
-                  s.tmp, GF_T, GF_R4, GF_T);
-            __syncthreads();
-            const float* gl = s.gl[e];
-            box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) {
-                const int y = y0 + r, x = x0 + c;
-                if (y < H && x < W) {
-                    const float mA = __fdiv_rn(v, win_count(y, H) * win_count(x, W));
-                    s.gx[r * GF_T + c] += gl[(r + 8) * GF_R8 + c + 8] * mA;
-                }
-            });
-            __syncthreads();
-        }
-        // dL/dA' = box(gLF x / N), dL/db = box(gLF / N)   (N of the pixel that owns mean_A / mean_b)
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            const float* gl = s.gl[k >> 1];
-            const bool withx = (k & 1) == 0;
-            box_h([&](int r, int c) {
-                      const float4 v = *reinterpret_cast<const float4*>(&gl[r * GF_R8 + c]);
-                      const float4 xg = *reinterpret_cast<const float4*>(&s.g[r * GF_R8 + c]);
-                      const int y = y0 - 8 + r, x = x0 - 8 + c;
-                      const float ny = fmaxf(win_count(y, H), 1.f);
-                      float4 o;
-                      o.x = __fdiv_rn(withx ? v.x * xg.x : v.x, ny * fmaxf(win_count(x + 0, W), 1.f));
-                      o.y = __fdiv_rn(withx ? v.y * xg.y : v.y, ny * fmaxf(win_count(x + 1, W), 1.f));
-                      o.z = __fdiv_rn(withx ? v.z * xg.z : v.z, ny * fmaxf(win_count(x + 2, W), 1.f));
-                      o.w = __fdiv_rn(withx ? v.w * xg.w : v.w, ny * fmaxf(win_count(x + 3, W), 1.f));
-                      return o;
-                  },
-                  s.tmp, GF_R4, GF_R8, GF_R4);
-            __syncthreads();
-            float* dst = s.gab[k];
-            box_v(s.tmp, GF_R4, GF_R4, GF_R4, [&](int r, int c, float v) { dst[r * GF_R4 + c] = v; });
-            __syncthreads();
-        }
-        // pointwise chain rule on the halo-4 region
-        for (int i = threadIdx.x; i < GF_R4 * GF_R4; i += GF_NT) {
-            const int r = i / GF_R4, c = i - r * GF_R4;
-            const int y = y0 - 4 + r, x = x0 - 4 + c;
-            float t = 0.f, u = 0.f;
-            if (y >= 0 && y < H && x >= 0 && x < W) {
-                const float mxv = s.mx[i], my = s.mz[i], A1 = s.ab[0][i], A2 = s.ab[2][i];
-                const float i1 = s.iv1[i], i2 = s.iv2[i];
-                const float gb1 = s.gab[1][i], gb2 = s.gab[3][i];
-                const float gA1 = s.gab[0][i] - gb1 * mxv, gA2 = s.gab[2][i] - gb2 * mxv;
-                const float gcov = gA1 * i1 + gA2 * i2;
-                s.gvar[i] -= gA1 * A1 * i1 + gA2 * A2 * i2;
-                const float gmy = gb1 + gb2 - gcov * mxv;
-                s.gmx[i] -= gb1 * A1 + gb2 * A2 + gcov * my;
-                const float n = win_count(y, H) * win_count(x, W);
-                t = __fdiv_rn(gcov, n);
-                u = __fdiv_rn(gmy, n);
-            }
-            s.gab[0][i] = t; s.gab[1][i] = u;
-        }
-        __syncthreads();
-        {
-            const float* src = s.gab[0];
-            box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&src[r * GF_R4 + c]); },
-                  s.tmp, GF_T, GF_R4, GF_T);
-            __syncthreads();
-            const float* zc = s.z[ch];
-            box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) {
-                const int ci = (r + 8) * GF_R8 + c + 8;
-                s.gy[(r * GF_T + c) * 4 + ch] = v * s.g[ci];
-                s.gx[r * GF_T + c] += v * zc[ci];
-            });
-            __syncthreads();
-            const float* src2 = s.gab[1];
-            box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&src2[r * GF_R4 + c]); },
-                  s.tmp, GF_T, GF_R4, GF_T);
-            __syncthreads();
-            box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) { s.gy[(r * GF_T + c) * 4 + ch] += v; });
-            __syncthreads();
-        }
-    }
-    // var = box(x^2)/N - mx^2 ; mx = box(x)/N
-    for (int i = threadIdx.x; i < GF_R4 * GF_R4; i += GF_NT) {
-        const int r = i / GF_R4, c = i - r * GF_R4;
-        const int y = y0 - 4 + r, x = x0 - 4 + c;
-        float gv = 0.f, gm = 0.f;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            const float n = win_count(y, H) * win_count(x, W);
-            gm = __fdiv_rn(s.gmx[i] - 2.f * s.mx[i] * s.gvar[i], n);
-            gv = __fdiv_rn(s.gvar[i], n);
-        }
-        s.gvar[i] = gv; s.gmx[i] = gm;
-    }
-    __syncthreads();
-    box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&s.gvar[r * GF_R4 + c]); }, s.tmp, GF_T, GF_R4, GF_T);
-    __syncthreads();
-    box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) {
-        s.gx[r * GF_T + c] += 2.f * s.g[(r + 8) * GF_R8 + c + 8] * v;
-    });
-    __syncthreads();
-    box_h([&](int r, int c) { return *reinterpret_cast<const float4*>(&s.gmx[r * GF_R4 + c]); }, s.tmp, GF_T, GF_R4, GF_T);
-    __syncthreads();
-    box_v(s.tmp, GF_T, GF_T, GF_T, [&](int r, int c, float v) { s.gx[r * GF_T + c] += v; });
-    __syncthreads();
-
-    float4* gyp = reinterpret_cast<float4*>(gfeat) + ((size_t)b * Q + q) * plane;
+    const size_t qoff = ((size_t)b * Q + q) * plane;
+    const float4* zp = reinterpret_cast<const float4*>(feat) + qoff;
+    const float4* gcp = reinterpret_cast<const float4*>(gc) + qoff;
+    const float4* gmp = reinterpret_cast<const float4*>(gm) + qoff;
+    const float* gp = guide + (size_t)b * plane;
+    const float* gvp = gvn + ((size_t)q * B + b) * plane;
+    const float* gnp = gmn + ((size_t)q * B + b) * plane;
+    float4* gzp = reinterpret_cast<float4*>(gfeat) + qoff;
     float* gxp = gres_partial + ((size_t)q * B + b) * plane;
-    for (int i = threadIdx.x; i < GF_T * GF_T; i += GF_NT) {
-        const int r = i / GF_T, c = i - r * GF_T;
-        const int y = y0 + r, x = x0 + c;
-        if (y < H && x < W) {
-            gyp[(size_t)y * W + x] = *reinterpret_cast<const float4*>(&s.gy[i * 4]);
-            gxp[(size_t)y * W + x] = s.gx[i];
+
+    bool ok_o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ok_o[k] = xo + k < W && 4 * lane + k < GA_OUTW;
+    float Sc[4][4], Sm[4][4], SV[4], SM[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        SV[k] = SM[k] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Sc[k][c] = Sm[k][c] = 0.f;
+    }
+    const int nt = rows + 8;
+    for (int t = 0; t < nt; ++t) {
+        const int ys = y0 - 4 + t;                 // level-1 row entering the vertical window
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int y = side == 0 ? ys : ys - 9;
+            if (y < 0 || y >= H || (side == 1 && t < 9)) continue;
+            const float sg = side == 0 ? 1.f : -1.f;
+            float4 c4[4], m4[4];
+            float v[4], n[4];
+            ld_z4(gcp + (size_t)y * W, xs, W, c4);
+            ld_z4(gmp + (size_t)y * W, xs, W, m4);
+            ld_cols4<VEC>(gvp + (size_t)y * W, xs, W, v);
+            ld_cols4<VEC>(gnp + (size_t)y * W, xs, W, n);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                Sc[k][0] = fmaf(sg, c4[k].x, Sc[k][0]); Sc[k][1] = fmaf(sg, c4[k].y, Sc[k][1]);
+                Sc[k][2] = fmaf(sg, c4[k].z, Sc[k][2]); Sc[k][3] = fmaf(sg, c4[k].w, Sc[k][3]);
+                Sm[k][0] = fmaf(sg, m4[k].x, Sm[k][0]); Sm[k][1] = fmaf(sg, m4[k].y, Sm[k][1]);
+                Sm[k][2] = fmaf(sg, m4[k].z, Sm[k][2]); Sm[k][3] = fmaf(sg, m4[k].w, Sm[k][3]);
+                SV[k] = fmaf(sg, v[k], SV[k]);
+                SM[k] = fmaf(sg, n[k], SM[k]);
+            }
+        }
+        if (t < 8) continue;
+        const int yo = ys - 4;                     // output row, inside the chunk and the image
+        float4 z[4];
+        float g[4], gxd[4], bv[4], bm[4];
+        ld_z4(zp + (size_t)yo * W, xo, W, z);
+        ld_cols4<VEC>(gp + (size_t)yo * W, xo, W, g);
+        ld_cols4<VEC>(gxp + (size_t)yo * W, xo, W, gxd);
+        hsum9(SV, bv);
+        hsum9(SM, bm);
+        float gx[4], gz[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gx[k] = fmaf(2.f * g[k], bv[k], bm[k]) + gxd[k];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float a[4], tt[4], uu[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = Sc[k][c];
+            hsum9(a, tt);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = Sm[k][c];
+            hsum9(a, uu);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float zc = c == 0 ? z[k].x : (c == 1 ? z[k].y : (c == 2 ? z[k].z : z[k].w));
+                gz[k][c] = fmaf(tt[k], g[k], uu[k]);
+                gx[k] = fmaf(tt[k], zc, gx[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ok_o[k]) {
+                const size_t o = (size_t)yo * W + xo + k;
+                gzp[o] = make_float4(gz[k][0], gz[k][1], gz[k][2], gz[k][3]);
+                gxp[o] = gx[k];
+            }
         }
     }
 }
@@ -621,6 +585,18 @@ gf_backward_kernel(const float* __restrict__ feat, const float* __restrict__ res
 }  // namespace paif
 
 using namespace paif;
+
+static int gf_march_attr() {
+    static bool done = false;
+    if (done) return 0;
+    cudaError_t e = cudaFuncSetAttribute(gf_forward_march_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gf_forward_march_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gf_forward_march_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gf_forward_march_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
+    if (e != cudaSuccess) { set_error("gf smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    done = true;
+    return 0;
+}
 
 extern "C" int paif_gf_guide_stats(const float* residue, float* stats, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(residue && stats, "null pointer");
@@ -644,40 +620,73 @@ extern "C" int paif_gf_decomp_forward(const float* feat, const float* residue, c
     const long long nitems = (long long)B * Q * nstrips * nchunks;
     PAIF_REQUIRE(nitems < (1ll << 30), "problem too large");
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats)) % 16 == 0);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t err = cudaFuncSetAttribute(gf_forward_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
-        if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(gf_forward_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
-        if (err != cudaSuccess) { set_error("gf smem attr: %s", cudaGetErrorString(err)); return (int)err; }
-        attr_done = true;
-    }
+    if (int r = gf_march_attr()) return r;
     const int grid = (int)((nitems + GM_WPC - 1) / GM_WPC);
     if (vec)
-        gf_forward_march_kernel<true><<<grid, GM_WPC * 32, GM_SMEM, (cudaStream_t)stream>>>(
-            feat, residue, stats, lf1, lf2, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        gf_forward_march_kernel<true, 0><<<grid, GM_WPC * 32, GM_SMEM, (cudaStream_t)stream>>>(
+            feat, residue, stats, lf1, lf2, nullptr, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
     else
-        gf_forward_march_kernel<false><<<grid, GM_WPC * 32, GM_SMEM, (cudaStream_t)stream>>>(
-            feat, residue, stats, lf1, lf2, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        gf_forward_march_kernel<false, 0><<<grid, GM_WPC * 32, GM_SMEM, (cudaStream_t)stream>>>(
+            feat, residue, stats, lf1, lf2, nullptr, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
     return check_launch("paif_gf_decomp_forward");
 }
 
-extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, const float* glf1, const float* glf2,
-                                       float* gfeat, float* gres_partial, int C, int B, int H, int W, void* stream) {
-    PAIF_REQUIRE(feat && residue && glf1 && glf2 && gfeat && gres_partial, "null pointer");
+extern "C" long long paif_gf_backward_work_floats(int C, int B, int H, int W) {
+    // two C-channel maps (gcov/N, gmean_z/N) + two per-quad planes (gvar/N, gmean_g/N)
+    return (long long)B * H * W * (2LL * C + 2LL * (C / 4));
+}
+
+extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, const float* stats,
+                                       const float* glf1, const float* glf2,
+                                       float* gfeat, float* gres_partial, float* work,
+                                       int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(feat && residue && stats && glf1 && glf2 && gfeat && gres_partial && work, "null pointer");
     PAIF_REQUIRE(C > 0 && C % 4 == 0, "C must be a multiple of 4");
     PAIF_REQUIRE(H > 9 && W > 9, "guided filter needs H, W > 2r+1 = 9");
     const int Q = C / 4;
-    PAIF_REQUIRE((long long)B * Q <= 65535, "B*C/4 exceeds grid.z");
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t err = cudaFuncSetAttribute(gf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)sizeof(GfBwdSmem));
-        if (err != cudaSuccess) { set_error("gf bwd smem attr: %s", cudaGetErrorString(err)); return (int)err; }
-        attr_done = true;
+    const size_t map = (size_t)B * C * H * W, qplanes = (size_t)Q * B * H * W;
+    float* gc = work;
+    float* gm = work + map;
+    float* gvn = work + 2 * map;
+    float* gmn = gvn + qplanes;
+    const int nchunks = H <= 160 ? 1 : (H + 60) / 120;
+    const int RC = cdiv(H, nchunks);
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats) |
+                                       reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(gres_partial)) % 16 == 0) &&
+                     (qplanes % 4 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int r = gf_march_attr()) return r;
+    {   // pass A: adjoint of the level-2 boxes + pointwise chain rule
+        const int nstrips = cdiv(W, GA_OUTW);
+        const long long nitems = (long long)B * Q * nstrips * nchunks;
+        PAIF_REQUIRE(nitems < (1ll << 30), "problem too large");
+        const int grid = (int)((nitems + 1) / 2);
+        if (vec) gf_adjoint_level2_kernel<true><<<grid, 64, 0, st>>>(feat, residue, stats, glf1, glf2, gc, gm, gvn, gmn,
+                                                                    Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        else gf_adjoint_level2_kernel<false><<<grid, 64, 0, st>>>(feat, residue, stats, glf1, glf2, gc, gm, gvn, gmn,
+                                                                  Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        if (int r = check_launch("paif_gf_decomp_backward(level 2)")) return r;
     }
-    dim3 grid(cdiv(W, GF_T), cdiv(H, GF_T), B * Q);
-    gf_backward_kernel<<<grid, GF_NT, sizeof(GfBwdSmem), (cudaStream_t)stream>>>(feat, residue, glf1, glf2, gfeat,
-                                                                               gres_partial, Q, B, H, W);
+    {   // pass B: direct guide term (forward recompute of mean_A)
+        const int nstrips = cdiv(W, GM_OUTW);
+        const long long nitems = (long long)B * Q * nstrips * nchunks;
+        const int grid = (int)((nitems + GM_WPC - 1) / GM_WPC);
+        float* l1 = const_cast<float*>(glf1);
+        float* l2 = const_cast<float*>(glf2);
+        if (vec) gf_forward_march_kernel<true, 1><<<grid, GM_WPC * 32, GM_SMEM, st>>>(feat, residue, stats, l1, l2, gres_partial,
+                                                                                    Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        else gf_forward_march_kernel<false, 1><<<grid, GM_WPC * 32, GM_SMEM, st>>>(feat, residue, stats, l1, l2, gres_partial,
+                                                                                  Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        if (int r = check_launch("paif_gf_decomp_backward(direct term)")) return r;
+    }
+    {   // pass C: adjoint of the level-1 boxes, final gradients
+        const int nstrips = cdiv(W, GA_OUTW);
+        const long long nitems = (long long)B * Q * nstrips * nchunks;
+        const int grid = (int)((nitems + 1) / 2);
+        if (vec) gf_adjoint_level1_kernel<true><<<grid, 64, 0, st>>>(feat, residue, gc, gm, gvn, gmn, gfeat, gres_partial,
+                                                                    Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+        else gf_adjoint_level1_kernel<false><<<grid, 64, 0, st>>>(feat, residue, gc, gm, gvn, gmn, gfeat, gres_partial,
+                                                                  Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+    }
     return check_launch("paif_gf_decomp_backward");
 }

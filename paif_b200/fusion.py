@@ -158,8 +158,12 @@ class _Runtime:
             tiles = _lib.load().paif_conv_num_tiles(self.H, self.W, engine)
             partials = torch.empty((self.B, tiles, cw.cout), device=self.device, dtype=torch.float32)
             d.chan_partials = partials.data_ptr()
+        # algorithmic traffic: every source / residual / mask map read once, every output map written once
+        maps = (cw.nsrc * cw.cps + cw.cout * (len(pre_res) + len(post_res) + (mask_src is not None) + 1 +
+                                               bool(want_pre) + (act2_slope is not None)))
         self._meta = {"k": cw.k, "dil": cw.dil, "cin": cw.nsrc * cw.cps, "cout": cw.cout, "engine": engine,
-                      "flops": 2.0 * cw.cout * cw.nsrc * cw.cps * cw.k * cw.k * self.B * self.H * self.W}
+                      "flops": 2.0 * cw.cout * cw.nsrc * cw.cps * cw.k * cw.k * self.B * self.H * self.W,
+                      "bytes": 4.0 * maps * self.B * self.H * self.W}
         self.call("paif_conv_forward", ctypes.byref(d))
         return out, pre, act2, partials
 
@@ -626,7 +630,7 @@ class Network_Fusion_Searched(nn.Module):
         rt = _Runtime(B, H, W, self._C, ir.device, self._engine(), save)
         rt.profile = self.profile
         C = self._C
-        feats, guides = [], []
+        feats, guides, gstats = [], [], []
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
             f, g = rt.new_map(), rt.new_plane()
             rt.call("paif_stem_forward", img.data_ptr(), img.stride(0), img.stride(2), img.stride(3),
@@ -641,6 +645,7 @@ class Network_Fusion_Searched(nn.Module):
             rt.call("paif_gf_guide_stats", guides[i].data_ptr(), stats.data_ptr(), B, H, W)
             rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
                     lf1.data_ptr(), lf2.data_ptr(), C, B, H, W)
+            gstats.append(stats if save else None)
             del stats
             x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i])[0]
             del lf1, lf2
@@ -662,7 +667,7 @@ class Network_Fusion_Searched(nn.Module):
         self.last_launches = rt.launches
         saved = None
         if save:
-            saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
+            saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, gstats=gstats, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
                          scale=scale, recs3=recs3, out=out, pre_out=pre_out, packed=p)
         return out, saved
 
@@ -703,8 +708,11 @@ class Network_Fusion_Searched(nn.Module):
             gz = rt.conv([gx], wd[2])[0]
             gfeat = rt.new_map()
             gres = torch.empty((C // 4, B, H, W), device=g.device, dtype=torch.float32)
+            work = torch.empty((_lib.load().paif_gf_backward_work_floats(C, B, H, W),), device=g.device, dtype=torch.float32)
             rt.call("paif_gf_decomp_backward", saved["feats"][i].data_ptr(), saved["guides"][i].data_ptr(),
-                    glf1.data_ptr(), glf2.data_ptr(), gfeat.data_ptr(), gres.data_ptr(), C, B, H, W)
+                    saved["gstats"][i].data_ptr(), glf1.data_ptr(), glf2.data_ptr(), gfeat.data_ptr(), gres.data_ptr(),
+                    work.data_ptr(), C, B, H, W)
+            del work
             gstem = rt.new_map()
             rt.call("paif_stem_backward_pre", saved["feats"][i].data_ptr(), p["stem_a"][i].data_ptr(),
                     gb.data_ptr(), gz.data_ptr(), gfeat.data_ptr(), None, gres.data_ptr(), gstem.data_ptr(),

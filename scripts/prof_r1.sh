@@ -2,13 +2,13 @@
 # round-1 profiling pass (run under gpurun): launch list of one bench step + full captures of the top kernels
 set -x
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 --table > gpurun_out/bench_a.json 2> gpurun_out/table_a.txt
-# launch list: skip the 2*3 warm-up steps (resident+e2e each 26 launches... keep all, small)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_a.csv \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_a.log 2>&1
-# full capture: conv engine (launch index chosen to hit k3 cin32, cin64, cin96 and k7) and the GF kernel
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 16 -c 16 \
-    -o gpurun_out/prof_conv_a python bench.py --steps 1 --warmup 3 --batch 4 --no-cpu-baseline > gpurun_out/ncu_conv_a.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gf_ -s 2 -c 2 \
-    -o gpurun_out/prof_gf_a python bench.py --steps 1 --warmup 3 --batch 4 --no-cpu-baseline > gpurun_out/ncu_gf_a.log 2>&1
+python bench.py --steps 5 --warmup 3 --table > gpurun_out/bench_r1.json 2> gpurun_out/table_r1.txt
+# launch list of the same command (cold-cache, serialised: compare shares, not absolutes)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r1.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --bwd-steps 0 > gpurun_out/ncu_launch_r1.log 2>&1
+# full captures (batch 16, the bench workload): one forward's worth of conv launches, and the GF kernels
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 15 -c 15 \
+    -o gpurun_out/prof_conv_r1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --bwd-steps 0 > gpurun_out/ncu_conv_r1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gf_forward_march -s 2 -c 2 \
+    -o gpurun_out/prof_gf_r1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --bwd-steps 0 > gpurun_out/ncu_gf_r1.log 2>&1
 ls -la gpurun_out

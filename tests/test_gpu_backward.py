@@ -56,8 +56,11 @@ def test_guided_filter_adjoint(shape, smooth):
     g1c, g2c = to_c4(g1.float()).to(DEV), to_c4(g2.float()).to(DEV)
     gfeat = torch.empty_like(zc)
     gres = torch.empty(8, B, H, W, device=DEV)
-    _lib.call("paif_gf_decomp_backward", zc.data_ptr(), gc.data_ptr(), g1c.data_ptr(), g2c.data_ptr(),
-              gfeat.data_ptr(), gres.data_ptr(), 32, B, H, W, stream())
+    stats = torch.empty(3, B, H, W, device=DEV)
+    _lib.call("paif_gf_guide_stats", gc.data_ptr(), stats.data_ptr(), B, H, W, stream())
+    work = torch.empty(_lib.load().paif_gf_backward_work_floats(32, B, H, W), device=DEV)
+    _lib.call("paif_gf_decomp_backward", zc.data_ptr(), gc.data_ptr(), stats.data_ptr(), g1c.data_ptr(), g2c.data_ptr(),
+              gfeat.data_ptr(), gres.data_ptr(), work.data_ptr(), 32, B, H, W, stream())
     e_z = rel_l2(from_c4(gfeat).cpu().double(), gz)
     e_g = rel_l2(gres.sum(0).cpu().double(), gg[:, 0])
     assert e_z < 2e-3 and e_g < 2e-3, (e_z, e_g)
