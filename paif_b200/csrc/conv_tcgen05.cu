@@ -202,7 +202,7 @@ static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservati
 // K, DIL, KQ are compile-time so that the MMA issue loop unrolls into straight-line code whose descriptors differ
 // from a per-row base by immediates: the single issuing thread then sustains the tensor pipe's own rate
 // (max(32 + N/4, N/2) cycles per MMA, scripts/mma_ubench2.cu) instead of ~150 cycles of address arithmetic per MMA.
-template <int K, int DIL, int KQ>
+template <int K, int DIL, int KQ, bool PARTIALS>
 __global__ void __launch_bounds__(TC_NT, 1)
 conv_tc_kernel(TcGeom g, EpiParams e) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -265,33 +265,59 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         const float ma = e.mask_slope ? __ldg(e.mask_slope) : 0.f;
         const float a2 = e.slope2 ? __ldg(e.slope2) : 1.f;
         const bool any_post = e.post_res[0] || e.post_res[1] || e.post_res[2];
-        // The residual maps added after the activation do not depend on the accumulator: their sum for
-        // this thread's NEXT row is fetched while the current row is still being accumulated, so the
-        // global-load latency never sits between acc_full and the stores.
-        float4 pn[8];
-        auto fetch_post = [&](int ro) {
+        const bool any_pre = e.pre_res[0] || e.pre_res[1];
+        const bool any_fetch = any_post || any_pre || e.mask_src;
+        // Residual and mask maps do not depend on the accumulator: for this thread's NEXT row the sum of the
+        // post-activation residuals (pn), the sum of the pre-activation residuals (qn) and the PReLU' mask
+        // (one bit per channel) are fetched while that row is still being accumulated, so global-load latency
+        // never sits between acc_full and the stores.
+        float4 pn[8], qn[8];
+        uint32_t mbits = 0;
+        auto fetch_next = [&](int ro) {
             const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;
+            if (any_post) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int kk = 0; kk < 3; ++kk)
-                if (e.post_res[kk]) {
+                for (int kk = 0; kk < 3; ++kk)
+                    if (e.post_res[kk]) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) pn[q] = f4_add(pn[q], __ldg(reinterpret_cast<const float4*>(e.post_res[kk]) + base + q * plane));
+                        for (int q = 0; q < 8; ++q) pn[q] = f4_add(pn[q], __ldg(reinterpret_cast<const float4*>(e.post_res[kk]) + base + q * plane));
+                    }
+            }
+            if (any_pre) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) qn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)
+                    if (e.pre_res[kk]) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) qn[q] = f4_add(qn[q], __ldg(reinterpret_cast<const float4*>(e.pre_res[kk]) + base + q * plane));
+                    }
+            }
+            if (e.mask_src) {
+                uint32_t mb = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(e.mask_src) + base + q * plane);
+                    mb |= (m.x > 0.f ? 1u : 0u) << (4 * q) | (m.y > 0.f ? 2u : 0u) << (4 * q) |
+                          (m.z > 0.f ? 4u : 0u) << (4 * q) | (m.w > 0.f ? 8u : 0u) << (4 * q);
                 }
+                mbits = mb;
+            }
         };
 #pragma unroll
-        for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (any_post && xin && grp < nrows) fetch_post(grp);
+        for (int q = 0; q < 8; ++q) { pn[q] = make_float4(0.f, 0.f, 0.f, 0.f); qn[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        if (any_fetch && xin && grp < nrows) fetch_next(grp);
         if (grp == 0) {
             // accumulators start from zero: every MMA accumulates (the TMEM allocation holds garbage)
             for (int sl = 0; sl < TC_SLOTS; ++sl) tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + sl * 32);
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->zeroed));
         }
-        float csum[32];
+        float csum[PARTIALS ? 32 : 1];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) csum[c] = 0.f;
+        for (int c = 0; c < (PARTIALS ? 32 : 1); ++c) csum[c] = 0.f;
         TC_PROF_DECL;
         for (int ro = grp; ro < nrows; ro += 2) {
             const int slot = tc_slot(ro, dsh), use = ro / TC_SLOTS;
@@ -311,17 +337,12 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                     const float4 sh = *reinterpret_cast<const float4*>(&bars->ch_shift[q * 4]);
                     float t[4] = {fmaf(v[q * 4 + 0], sc.x, sh.x), fmaf(v[q * 4 + 1], sc.y, sh.y),
                                   fmaf(v[q * 4 + 2], sc.z, sh.z), fmaf(v[q * 4 + 3], sc.w, sh.w)};
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-                        if (e.pre_res[kk]) {
-                            const float4 r = __ldg(reinterpret_cast<const float4*>(e.pre_res[kk]) + off);
-                            t[0] += r.x; t[1] += r.y; t[2] += r.z; t[3] += r.w;
-                        }
+                    t[0] += qn[q].x; t[1] += qn[q].y; t[2] += qn[q].z; t[3] += qn[q].w;
                     if (e.out_pre) reinterpret_cast<float4*>(e.out_pre)[off] = make_float4(t[0], t[1], t[2], t[3]);
                     if (e.mask_src) {
-                        const float4 m = __ldg(reinterpret_cast<const float4*>(e.mask_src) + off);
-                        t[0] *= dprelu_f(m.x, ma); t[1] *= dprelu_f(m.y, ma);
-                        t[2] *= dprelu_f(m.z, ma); t[3] *= dprelu_f(m.w, ma);
+                        const uint32_t mq = mbits >> (4 * q);
+                        t[0] *= (mq & 1u) ? 1.f : ma; t[1] *= (mq & 2u) ? 1.f : ma;
+                        t[2] *= (mq & 4u) ? 1.f : ma; t[3] *= (mq & 8u) ? 1.f : ma;
                     } else if (e.slope) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) t[j] = prelu_f(t[j], a);
@@ -329,7 +350,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                     v[q * 4 + 0] = fmaf(t[0], e.post_scale, pn[q].x); v[q * 4 + 1] = fmaf(t[1], e.post_scale, pn[q].y);
                     v[q * 4 + 2] = fmaf(t[2], e.post_scale, pn[q].z); v[q * 4 + 3] = fmaf(t[3], e.post_scale, pn[q].w);
                 }
-                if (any_post && ro + 2 < nrows) fetch_post(ro + 2);       // in flight during the next row's MMAs
+                if (any_fetch && ro + 2 < nrows) fetch_next(ro + 2);      // in flight during the next row's MMAs
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const size_t off = base + q * plane;
@@ -338,12 +359,14 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                         reinterpret_cast<float4*>(e.out_act2)[off] =
                             make_float4(prelu_f(v[q * 4 + 0], a2), prelu_f(v[q * 4 + 1], a2), prelu_f(v[q * 4 + 2], a2), prelu_f(v[q * 4 + 3], a2));
                 }
+                if (PARTIALS) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) csum[c] += v[c];
+                    for (int c = 0; c < 32; ++c) csum[c] += v[c];
+                }
             }
         }
         TC_PROF_END(0);
-        if (e.chan_partials) {
+        if (PARTIALS) {
             // deterministic per-CTA channel sums: shuffle tree, then fixed-order cross-warp sum via smem
             float* red = reinterpret_cast<float*>(s_ring);          // the ring is idle once the last accumulator is done
             asm volatile("bar.sync 1, 256;" ::: "memory");            // both groups have drained their last rows
@@ -540,12 +563,16 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     if (kk == K_ && dd == D_ && g.plan.KQ == Q_) {                                                                 \
         static bool attr_done = false;                                                                              \
         if (!attr_done) {                                                                                           \
-            cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_>,                                      \
+            cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, false>,                               \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024); \
+            if (err == cudaSuccess)                                                                                 \
+                err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, true>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);     \
             if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; } \
             attr_done = true;                                                                                       \
         }                                                                                                           \
-        conv_tc_kernel<K_, D_, Q_><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);                               \
+        if (d.chan_partials) conv_tc_kernel<K_, D_, Q_, true><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);   \
+        else conv_tc_kernel<K_, D_, Q_, false><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);                  \
         return check_launch("paif_conv_forward(tcgen05)");                                                          \
     }
     TC_CASE(1, 1, 8) TC_CASE(3, 1, 8) TC_CASE(3, 2, 8) TC_CASE(5, 1, 8) TC_CASE(5, 2, 8) TC_CASE(7, 1, 4) TC_CASE(7, 2, 4)
