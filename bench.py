@@ -187,15 +187,64 @@ def run_ours(args):
             ms = t.item()
         return ms
 
+    def timed_e2e(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e2e_drain()                                          # the last D2H is part of the timed region
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
     def step_resident():
         with torch.no_grad():
             return net(ir_d, vis_d)
 
+    # end to end: host buffers in, host buffer out, through the public nn.Module call.  The H2D copies of step
+    # i+1 and the D2H copy of step i run on a copy stream while the kernels of step i run on the compute stream
+    # (two device input slots); every step's copies are issued inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [(torch.empty_like(ir_d), torch.empty_like(vis_d)) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]      # inputs of slot landed
+    freed = [torch.cuda.Event() for _ in range(2)]      # kernels that read slot finished
+    state = {"i": 0, "primed": False}
+
+    def issue_h2d(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[slot])
+            slots[slot][0].copy_(ir_h, non_blocking=True)
+            slots[slot][1].copy_(vis_h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
     def step_e2e():
+        cur = state["i"] & 1
+        if not state["primed"]:
+            freed[0].record(); freed[1].record()
+            issue_h2d(cur)
+            state["primed"] = True
+        issue_h2d(cur ^ 1)                                   # next step's inputs, overlapped with this step's kernels
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(ready[cur])
         with torch.no_grad():
-            a = ir_h.to(dev, non_blocking=True)
-            v = vis_h.to(dev, non_blocking=True)
-            out_h.copy_(net(a, v), non_blocking=True)
+            out = net(slots[cur][0], slots[cur][1])
+        freed[cur].record(main)
+        done = torch.cuda.Event()
+        done.record(main)
+        out.record_stream(copy_stream)                       # keep the allocator from recycling it under the copy
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            out_h.copy_(out, non_blocking=True)              # D2H of the fused images
+        state["i"] += 1
+
+    def e2e_drain():
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
 
     # per-step working set (> 30 fp32 maps of B*39 MB) is far larger than the 126 MB L2
     for _ in range(max(args.warmup, 3)):
@@ -208,7 +257,9 @@ def run_ours(args):
     ms = timed(step_resident, args.steps)
     prof, net.profile = net.profile, None
     launches = net.last_launches * args.steps
-    ms_e2e = timed(step_e2e, args.steps)
+    def e2e_steps():
+        step_e2e()
+    ms_e2e = timed_e2e(e2e_steps, args.steps)
     clocks = sampler.summary() if sampler else None
 
     # attack inner step (BASELINE configs[4]): forward + backward-to-input on resident inputs

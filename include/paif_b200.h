@@ -200,9 +200,11 @@ int paif_spa_blend_backward(const float* gagg, const float* ir_f, const float* v
 /* adjoint of paif_gf_decomp_forward w.r.t. feat (source) and residue (guide).
  * stats: the same guide statistics the forward used (paif_gf_guide_stats).
  * glf1/glf2: gradients w.r.t. the two LF maps.  gfeat: C4 map (written).
- * gres_partial: [C/4][B][H][W] per-quad partial guide gradients (summed by the stem backward).
+ * gres_partial: [paif_gf_guide_parts(C)][B][H][W] partial guide gradients, one plane per channel group
+ *   (summed in fixed order by the stem backward).
  * work: caller-owned scratch of paif_gf_backward_work_floats(C,B,H,W) floats. */
 long long paif_gf_backward_work_floats(int C, int B, int H, int W);
+int paif_gf_guide_parts(int C);
 int paif_gf_decomp_backward(const float* feat, const float* residue, const float* stats,
                             const float* glf1, const float* glf2,
                             float* gfeat, float* gres_partial, float* work,
@@ -212,7 +214,7 @@ int paif_gf_decomp_backward(const float* feat, const float* residue, const float
  * arg-max / arg-min channel of feat (first index on ties); gpre = total * PReLU'(feat). */
 int paif_stem_backward_pre(const float* feat, const float* slope,
                            const float* g0, const float* g1, const float* g2, const float* g3,
-                           const float* gres_partial, float* gpre,
+                           const float* gres_partial, int nparts, float* gpre,
                            int C, int B, int H, int W, void* stream);
 /* stem backward, pass 2: gimg = conv3x3^T(gpre) (32 -> 1); gimg: contiguous [B][H][W]. */
 int paif_stem_backward(const float* gpre, const float* w, float* gimg,

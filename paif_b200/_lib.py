@@ -65,8 +65,9 @@ SIGNATURES = {
     "paif_spa_blend_backward_pre": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_spa_blend_backward": [_f, _f, _f, _f, _f, _f, _i, _f, _f, _i, _i, _i, _i, _f],
     "paif_gf_backward_work_floats": [_i, _i, _i, _i],
+    "paif_gf_guide_parts": [_i],
     "paif_gf_decomp_backward": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
-    "paif_stem_backward_pre": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_stem_backward_pre": [_f, _f, _f, _f, _f, _f, _f, _i, _f, _i, _i, _i, _i, _f],
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
 }

@@ -65,19 +65,26 @@ gf_guide_stats_kernel(const float* __restrict__ guide, float* __restrict__ stats
 // ------------------------------------------------------------------------------------------
 // forward, pass 1: row-marching, register-resident guided filter.
 //
-// One WARP = one work item: (image b, channel quad q, 112-column strip, row chunk).  Lane j owns 4
-// adjacent columns x 4 channels.  Both box-filter levels are "vertical running sum in registers,
-// then horizontal 9-sum by warp shuffles": level 1 runs on the raw rows (z, g*z), level 2 on
-// A_e = cov/(var+eps_e), b_e = mean_z - A_e mean_g.  The row leaving a vertical window is
-// re-derived (level 1: re-read from global/L2; level 2: recomputed from (mean_z, cov) kept in a
-// 9-row shared-memory ring) and subtracted.  The sums restart at every row chunk (16 halo rows),
-// which bounds the running-sum rounding drift; there is no __syncthreads anywhere.
+// One WARP = one work item: (image b, channel group, 112-column strip, row chunk); a channel group
+// is GF_NCH adjacent channels (a whole C4 quad).  Lane j owns 4 adjacent columns x GF_NCH
+// channels.  Both box-filter levels are "vertical running sum in registers, then horizontal 9-sum
+// by warp shuffles": level 1 runs on the raw rows (z, g*z), level 2 on A_e = cov/(var+eps_e),
+// b_e = mean_z - A_e mean_g.  The row leaving a vertical window is re-derived (level 1: re-read
+// from global/L2; level 2: recomputed from (mean_z, cov) kept in a 9-row shared-memory ring) and
+// subtracted.  The sums restart at every row chunk (16 halo rows), which bounds the running-sum
+// rounding drift; there is no __syncthreads anywhere.
 // Each horizontal pass shifts the columns a lane owns by +4: raw columns x0-8+4j.., level-1
 // columns x0-4+4j.. (valid for 4j+k <= 119), output columns x0+4j.. (valid for 4j+k <= 111).
+// GF_NCH = 2 (half a quad per lane: half the registers and ring, twice the resident warps) was measured 30 %
+// slower (forward 1.55 vs 1.20 ms): the per-lane costs shared by all channels (guide / statistics loads, window
+// counts, addressing) double per pixel-channel and outweigh the occupancy gain.
 // ------------------------------------------------------------------------------------------
-constexpr int GM_OUTW = 112;               // output columns per warp
+constexpr int GF_NCH = 4;                  // channels per lane (2 was measured: 30 % slower)
+constexpr int GF_SUBS = 4 / GF_NCH;        // channel groups per C4 quad
+constexpr int GM_OUTW = 112;               // output columns per warp (two horizontal passes)
+constexpr int GA_OUTW = 120;               // output columns per warp (one horizontal pass)
 constexpr int GM_WPC = 2;                  // warps (work items) per CTA
-constexpr int GM_RING_F4 = 9 * 8 * 32;     // float4 per warp: 9 rows x 8 float4 per lane
+constexpr int GM_RING_F4 = 9 * 2 * GF_NCH * 32;     // float4 per warp: 9 rows x (mean_z, cov) x 4 columns x GF_NCH
 constexpr int GM_SMEM = GM_WPC * GM_RING_F4 * 16;
 
 // o[k] = sum of columns (4j+k) .. (4j+k+8) of the per-lane column quadruples a[0..3]
@@ -93,6 +100,11 @@ __device__ __forceinline__ void hsum9(const float (&a)[4], float (&o)[4]) {
     o[2] = p23 + n1 + v8a;
     o[3] = a[3] + n1 + v8b;
 }
+// same for column c of a [4][GF_NCH] array
+__device__ __forceinline__ void hsum9c(const float (&s)[4][GF_NCH], int c, float (&o)[4]) {
+    const float a[4] = {s[0][c], s[1][c], s[2][c], s[3][c]};
+    hsum9(a, o);
+}
 
 template <bool VEC>
 __device__ __forceinline__ void ld_cols4(const float* __restrict__ row, int x, int W, float (&v)[4]) {
@@ -104,11 +116,31 @@ __device__ __forceinline__ void ld_cols4(const float* __restrict__ row, int x, i
         for (int k = 0; k < 4; ++k) v[k] = (x + k >= 0 && x + k < W) ? __ldg(row + x + k) : 0.f;
     }
 }
-
-__device__ __forceinline__ void ld_z4(const float4* __restrict__ row, int x, int W, float4 (&z)[4]) {
+template <bool VEC>
+__device__ __forceinline__ void st_cols4(float* __restrict__ row, int x, const float (&v)[4], const bool (&ok)[4]) {
+    if (VEC && ok[0] && ok[3]) { *reinterpret_cast<float4*>(row + x) = make_float4(v[0], v[1], v[2], v[3]); return; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        z[k] = (x + k >= 0 && x + k < W) ? __ldg(row + x + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < 4; ++k) if (ok[k]) row[x + k] = v[k];
+}
+
+// the GF_NCH channels of this lane's group at pixels x..x+3 of one row of a C4 map; `row` points at
+// (quad plane, row y, pixel 0, first channel of the group); zero outside [0, W)
+__device__ __forceinline__ void ld_grp(const float* __restrict__ row, int x, int W, float (&z)[4][GF_NCH]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xx = x + k;
+        if (xx >= 0 && xx < W) {
+            if (GF_NCH == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(row + (size_t)xx * 4)); z[k][0] = t.x; z[k][GF_NCH - 1] = t.y; }
+            else { const float4 t = __ldg(reinterpret_cast<const float4*>(row + (size_t)xx * 4)); z[k][0] = t.x; z[k][1 % GF_NCH] = t.y; z[k][2 % GF_NCH] = t.z; z[k][3 % GF_NCH] = t.w; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < GF_NCH; ++c) z[k][c] = 0.f;
+        }
+    }
+}
+__device__ __forceinline__ void st_grp(float* __restrict__ row, int xx, const float (&v)[GF_NCH]) {
+    if (GF_NCH == 2) *reinterpret_cast<float2*>(row + (size_t)xx * 4) = make_float2(v[0], v[GF_NCH - 1]);
+    else *reinterpret_cast<float4*>(row + (size_t)xx * 4) = make_float4(v[0], v[1 % GF_NCH], v[2 % GF_NCH], v[3 % GF_NCH]);
 }
 
 __device__ __forceinline__ void gf_ab(float mz, float cov, float mx, float i1, float i2,
@@ -117,36 +149,47 @@ __device__ __forceinline__ void gf_ab(float mz, float cov, float mx, float i1, f
     A2 = __fmul_rn(cov, i2); b2 = __fmaf_rn(-A2, mx, mz);
 }
 
+// work item -> (image, channel group, strip, chunk); returns false past the end
+struct GfItem { int b, grp, x0, y0, rows; size_t qoff; int coff; };
+__device__ __forceinline__ bool gf_item(int item, int nitems, int P, int Q, int nstrips, int nchunks, int outw, int RC,
+                                        int H, int W, GfItem& it) {
+    if (item >= nitems) return false;
+    it.grp = item % P; item /= P;
+    const int strip = item % nstrips; item /= nstrips;
+    const int chunk = item % nchunks;
+    it.b = item / nchunks;
+    it.x0 = strip * outw; it.y0 = chunk * RC;
+    it.rows = min(RC, H - it.y0);
+    it.coff = (it.grp % GF_SUBS) * GF_NCH;
+    it.qoff = (((size_t)it.b * Q + it.grp / GF_SUBS) * (size_t)H * W) * 4 + it.coff;   // float offset of (b, quad, 0, 0, coff)
+    return true;
+}
+
 // MODE 0: forward, writes LF_1e-3 / LF_1e-4.
 // MODE 1 (adjoint, "direct" guide term): lf1/lf2 are the INCOMING gradients w.r.t. the two LF maps; writes
-//         gxd[q][b][y][x] = sum_{c in quad} sum_e gLF_e,c * mean_A_e,c  (d LF / d guide at fixed mean_A, mean_b).
+//         gxd[grp][b][y][x] = sum_{c in group} sum_e gLF_e,c * mean_A_e,c  (d LF / d guide at fixed mean_A, mean_b).
 template <bool VEC, int MODE>
 __global__ void __launch_bounds__(GM_WPC * 32)
 gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict__ guide,
                         const float* __restrict__ stats, float* __restrict__ lf1, float* __restrict__ lf2,
                         float* __restrict__ gxd,
-                        int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
+                        int P, int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
     extern __shared__ float4 gm_ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int item = blockIdx.x * GM_WPC + warp;
-    if (item >= nitems) return;
-    const int q = item % Q; item /= Q;
-    const int strip = item % nstrips; item /= nstrips;
-    const int chunk = item % nchunks;
-    const int b = item / nchunks;
-    float4* ring = gm_ring + warp * GM_RING_F4 + lane;          // element (slot, i) at [(slot * 8 + i) * 32]
+    GfItem it;
+    if (!gf_item(blockIdx.x * GM_WPC + warp, nitems, P, Q, nstrips, nchunks, GM_OUTW, RC, H, W, it)) return;
+    const int b = it.b, x0 = it.x0, y0 = it.y0, rows = it.rows;
+    float4* ring = gm_ring + warp * GM_RING_F4 + lane;          // element (slot, i) at [(slot * 2 * GF_NCH + i) * 32]
 
-    const int x0 = strip * GM_OUTW, y0 = chunk * RC;
-    const int rows = min(RC, H - y0);
     const int xr = x0 - 8 + 4 * lane, xs = xr + 4, xo = xr + 8;
     const size_t plane = (size_t)H * W;
-    const float4* zp = reinterpret_cast<const float4*>(feat) + ((size_t)b * Q + q) * plane;
+    const float* zp = feat + it.qoff;
     const float* gp = guide + (size_t)b * plane;
     const float* mxp = stats + (size_t)b * plane;
     const float* i1p = stats + ((size_t)B + b) * plane;
     const float* i2p = stats + ((size_t)2 * B + b) * plane;
-    float4* o1 = reinterpret_cast<float4*>(lf1) + ((size_t)b * Q + q) * plane;
-    float4* o2 = reinterpret_cast<float4*>(lf2) + ((size_t)b * Q + q) * plane;
+    float* o1 = lf1 + it.qoff;
+    float* o2 = lf2 + it.qoff;
 
     float cs[4], co[4];            // clipped window widths of the level-1 / output columns (0 = column unused)
 #pragma unroll
@@ -155,24 +198,27 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
         co[k] = (xo + k < W && 4 * lane + k < GM_OUTW) ? win_count(xo + k, W) : 0.f;
     }
 
-    float Sz[4][4], Sgz[4][4], SA1[4][4], Sb1[4][4], SA2[4][4], Sb2[4][4];     // [column k][channel c]
+    float Sz[4][GF_NCH], Sgz[4][GF_NCH], SA1[4][GF_NCH], Sb1[4][GF_NCH], SA2[4][GF_NCH], Sb2[4][GF_NCH];   // [column][channel]
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { Sz[k][c] = Sgz[k][c] = SA1[k][c] = Sb1[k][c] = SA2[k][c] = Sb2[k][c] = 0.f; }
+        for (int c = 0; c < GF_NCH; ++c) { Sz[k][c] = Sgz[k][c] = SA1[k][c] = Sb1[k][c] = SA2[k][c] = Sb2[k][c] = 0.f; }
 
     // raw rows are fetched one iteration ahead: zn/gn = entering row, zq/gq = leaving row of iteration t
-    float4 zn[4], zq[4];
-    float gn[4], gq[4];
+    float zn[4][GF_NCH], zq[4][GF_NCH], gn[4], gq[4];
     {
         const int yr = y0 - 8;
-        if (yr >= 0) { ld_z4(zp + (size_t)yr * W, xr, W, zn); ld_cols4<VEC>(gp + (size_t)yr * W, xr, W, gn); }
+        if (yr >= 0) { ld_grp(zp + (size_t)yr * W * 4, xr, W, zn); ld_cols4<VEC>(gp + (size_t)yr * W, xr, W, gn); }
         else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { zn[k] = make_float4(0.f, 0.f, 0.f, 0.f); gn[k] = 0.f; }
+            for (int k = 0; k < 4; ++k) { gn[k] = 0.f;
+#pragma unroll
+                for (int c = 0; c < GF_NCH; ++c) zn[k][c] = 0.f; }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { zq[k] = make_float4(0.f, 0.f, 0.f, 0.f); gq[k] = 0.f; }
+        for (int k = 0; k < 4; ++k) { gq[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < GF_NCH; ++c) zq[k][c] = 0.f; }
     }
 
     int slot = 0;
@@ -184,27 +230,28 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
 
         // ---- level-1 vertical running sums: + entering row, - leaving row
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float zc[4] = {zn[k].x, zn[k].y, zn[k].z, zn[k].w};
-            const float zo[4] = {zq[k].x, zq[k].y, zq[k].z, zq[k].w};
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                Sz[k][c] += zc[c] - zo[c];
-                Sgz[k][c] += __fmul_rn(gn[k], zc[c]) - __fmul_rn(gq[k], zo[c]);
+            for (int c = 0; c < GF_NCH; ++c) {
+                Sz[k][c] += zn[k][c] - zq[k][c];
+                Sgz[k][c] += __fmul_rn(gn[k], zn[k][c]) - __fmul_rn(gq[k], zq[k][c]);
             }
-        }
         // ---- prefetch the rows of iteration t+1 (entering: yr+1, leaving: yr-8)
         {
             const int yn = yr + 1, yl = yr - 8;
-            if (t + 1 < nt && yn >= 0 && yn < H) { ld_z4(zp + (size_t)yn * W, xr, W, zn); ld_cols4<VEC>(gp + (size_t)yn * W, xr, W, gn); }
+            if (t + 1 < nt && yn >= 0 && yn < H) { ld_grp(zp + (size_t)yn * W * 4, xr, W, zn); ld_cols4<VEC>(gp + (size_t)yn * W, xr, W, gn); }
             else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { zn[k] = make_float4(0.f, 0.f, 0.f, 0.f); gn[k] = 0.f; }
+                for (int k = 0; k < 4; ++k) { gn[k] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < GF_NCH; ++c) zn[k][c] = 0.f; }
             }
-            if (t + 1 >= 9 && yl >= 0 && yl < H) { ld_z4(zp + (size_t)yl * W, xr, W, zq); ld_cols4<VEC>(gp + (size_t)yl * W, xr, W, gq); }
+            if (t + 1 >= 9 && yl >= 0 && yl < H) { ld_grp(zp + (size_t)yl * W * 4, xr, W, zq); ld_cols4<VEC>(gp + (size_t)yl * W, xr, W, gq); }
             else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { zq[k] = make_float4(0.f, 0.f, 0.f, 0.f); gq[k] = 0.f; }
+                for (int k = 0; k < 4; ++k) { gq[k] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < GF_NCH; ++c) zq[k][c] = 0.f; }
             }
         }
         if (t < 8) continue;
@@ -232,16 +279,12 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
 #pragma unroll
             for (int k = 0; k < 4; ++k) { mxo[k] = i1o[k] = i2o[k] = 0.f; }
         }
-        float4* rs = ring + slot * 8 * 32;
+        float4* rs = ring + slot * 2 * GF_NCH * 32;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float a[4], bz[4], bg[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sz[k][c];
-            hsum9(a, bz);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sgz[k][c];
-            hsum9(a, bg);
+        for (int c = 0; c < GF_NCH; ++c) {
+            float bz[4], bg[4];
+            hsum9c(Sz, c, bz);
+            hsum9c(Sgz, c, bg);
             float mz[4], cov[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -275,60 +318,43 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
         if (MODE == 0) {
             float go[4];
             ld_cols4<VEC>(gp + (size_t)yo * W, xo, W, go);
-            float r1[4][4], r2[4][4];                  // [column][channel]
+            float r1[4][GF_NCH], r2[4][GF_NCH];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float a[4], hA[4], hb[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a[k] = SA1[k][c];
-                hsum9(a, hA);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a[k] = Sb1[k][c];
-                hsum9(a, hb);
+            for (int c = 0; c < GF_NCH; ++c) {
+                float hA[4], hb[4];
+                hsum9c(SA1, c, hA);
+                hsum9c(Sb1, c, hb);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) r1[k][c] = __fmaf_rn(hA[k] * rno[k], go[k], hb[k] * rno[k]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a[k] = SA2[k][c];
-                hsum9(a, hA);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a[k] = Sb2[k][c];
-                hsum9(a, hb);
+                hsum9c(SA2, c, hA);
+                hsum9c(Sb2, c, hb);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) r2[k][c] = __fmaf_rn(hA[k] * rno[k], go[k], hb[k] * rno[k]);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (co[k] > 0.f) {
-                    const size_t o = (size_t)yo * W + xo + k;
-                    o1[o] = make_float4(r1[k][0], r1[k][1], r1[k][2], r1[k][3]);
-                    o2[o] = make_float4(r2[k][0], r2[k][1], r2[k][2], r2[k][3]);
+                    st_grp(o1 + (size_t)yo * W * 4, xo + k, r1[k]);
+                    st_grp(o2 + (size_t)yo * W * 4, xo + k, r2[k]);
                 }
             }
         } else {
-            float4 l1[4], l2[4];
-            ld_z4(reinterpret_cast<const float4*>(o1) + (size_t)yo * W, xo, W, l1);
-            ld_z4(reinterpret_cast<const float4*>(o2) + (size_t)yo * W, xo, W, l2);
+            float l1[4][GF_NCH], l2[4][GF_NCH];
+            ld_grp(o1 + (size_t)yo * W * 4, xo, W, l1);
+            ld_grp(o2 + (size_t)yo * W * 4, xo, W, l2);
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float a[4], h1[4], h2[4];
+            for (int c = 0; c < GF_NCH; ++c) {
+                float h1[4], h2[4];
+                hsum9c(SA1, c, h1);
+                hsum9c(SA2, c, h2);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) a[k] = SA1[k][c];
-                hsum9(a, h1);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) a[k] = SA2[k][c];
-                hsum9(a, h2);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float g1 = c == 0 ? l1[k].x : (c == 1 ? l1[k].y : (c == 2 ? l1[k].z : l1[k].w));
-                    const float g2 = c == 0 ? l2[k].x : (c == 1 ? l2[k].y : (c == 2 ? l2[k].z : l2[k].w));
-                    acc[k] = fmaf(g1, h1[k] * rno[k], fmaf(g2, h2[k] * rno[k], acc[k]));
-                }
+                for (int k = 0; k < 4; ++k) acc[k] = fmaf(l1[k][c], h1[k] * rno[k], fmaf(l2[k][c], h2[k] * rno[k], acc[k]));
             }
-            float* gx = gxd + ((size_t)q * B + b) * plane + (size_t)yo * W;
+            bool ok[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (co[k] > 0.f) gx[xo + k] = acc[k];
+            for (int k = 0; k < 4; ++k) ok[k] = co[k] > 0.f;
+            st_cols4<VEC>(gxd + ((size_t)it.grp * B + b) * plane + (size_t)yo * W, xo, acc, ok);
         }
     }
 }
@@ -338,43 +364,35 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
 //   pass A (gf_adjoint_level2_kernel): forward level-1 statistics + adjoint of the level-2 boxes
 //       gA'_e = box(gLF_e g / N), gb_e = box(gLF_e / N), then the pointwise chain rule through
 //       A_e = cov/(var+eps_e), b_e = mean_z - A_e mean_g; writes gcov/N and gmean_z/N per channel
-//       (two maps) and this quad's share of gvar/N and gmean_g/N (two planes per quad).
+//       (two maps) and this channel group's share of gvar/N and gmean_g/N (two planes per group).
 //   pass B (gf_forward_march_kernel<., 1>): the direct guide term sum gLF_e mean_A_e.
 //   pass C (gf_adjoint_level1_kernel): adjoint of the level-1 boxes: g_z = box(gcov/N) g + box(gmean_z/N),
-//       g_guide(quad) = sum_c box(gcov/N) z_c + 2 g box(gvar/N) + box(gmean_g/N) + direct term.
+//       g_guide(group) = sum_c box(gcov/N) z_c + 2 g box(gvar/N) + box(gmean_g/N) + direct term.
 // Formulas: SURVEY.md 8a (checked there against autograd in fp64).
 // ------------------------------------------------------------------------------------------
-constexpr int GA_OUTW = 120;               // one horizontal pass per kernel: 128 - 8 columns per warp
-
 template <bool VEC>
 __global__ void __launch_bounds__(64)
 gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict__ guide, const float* __restrict__ stats,
                          const float* __restrict__ glf1, const float* __restrict__ glf2,
                          float* __restrict__ gc, float* __restrict__ gm, float* __restrict__ gvn, float* __restrict__ gmn,
-                         int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
+                         int P, int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int item = blockIdx.x * 2 + warp;
-    if (item >= nitems) return;
-    const int q = item % Q; item /= Q;
-    const int strip = item % nstrips; item /= nstrips;
-    const int chunk = item % nchunks;
-    const int b = item / nchunks;
-    const int x0 = strip * GA_OUTW, y0 = chunk * RC;
-    const int rows = min(RC, H - y0);
+    GfItem it;
+    if (!gf_item(blockIdx.x * 2 + warp, nitems, P, Q, nstrips, nchunks, GA_OUTW, RC, H, W, it)) return;
+    const int b = it.b, x0 = it.x0, y0 = it.y0, rows = it.rows;
     const int xr = x0 - 4 + 4 * lane, xs = xr + 4;
     const size_t plane = (size_t)H * W;
-    const size_t qoff = ((size_t)b * Q + q) * plane;
-    const float4* zp = reinterpret_cast<const float4*>(feat) + qoff;
-    const float4* l1p = reinterpret_cast<const float4*>(glf1) + qoff;
-    const float4* l2p = reinterpret_cast<const float4*>(glf2) + qoff;
+    const float* zp = feat + it.qoff;
+    const float* l1p = glf1 + it.qoff;
+    const float* l2p = glf2 + it.qoff;
     const float* gp = guide + (size_t)b * plane;
     const float* mxp = stats + (size_t)b * plane;
     const float* i1p = stats + ((size_t)B + b) * plane;
     const float* i2p = stats + ((size_t)2 * B + b) * plane;
-    float4* gcp = reinterpret_cast<float4*>(gc) + qoff;
-    float4* gmp = reinterpret_cast<float4*>(gm) + qoff;
-    float* gvp = gvn + ((size_t)q * B + b) * plane;
-    float* gnp = gmn + ((size_t)q * B + b) * plane;
+    float* gcp = gc + it.qoff;
+    float* gmp = gm + it.qoff;
+    float* gvp = gvn + ((size_t)it.grp * B + b) * plane;
+    float* gnp = gmn + ((size_t)it.grp * B + b) * plane;
 
     float cr[4], cs[4];
 #pragma unroll
@@ -382,11 +400,11 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
         cr[k] = (xr + k >= 0 && xr + k < W) ? win_count(xr + k, W) : 0.f;
         cs[k] = (xs + k < W && 4 * lane + k < GA_OUTW) ? win_count(xs + k, W) : 0.f;
     }
-    float Sz[4][4], Sgz[4][4], P1[4][4], P2[4][4], P3[4][4], P4[4][4];
+    float Sz[4][GF_NCH], Sgz[4][GF_NCH], P1[4][GF_NCH], P2[4][GF_NCH], P3[4][GF_NCH], P4[4][GF_NCH];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { Sz[k][c] = Sgz[k][c] = P1[k][c] = P2[k][c] = P3[k][c] = P4[k][c] = 0.f; }
+        for (int c = 0; c < GF_NCH; ++c) { Sz[k][c] = Sgz[k][c] = P1[k][c] = P2[k][c] = P3[k][c] = P4[k][c] = 0.f; }
 
     const int nt = rows + 8;
     for (int t = 0; t < nt; ++t) {
@@ -396,28 +414,24 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
             const int y = side == 0 ? yr : yr - 9;
             if (y < 0 || y >= H || (side == 1 && t < 9)) continue;
             const float sg = side == 0 ? 1.f : -1.f;
-            float4 z[4], l1[4], l2[4];
-            float g[4];
-            ld_z4(zp + (size_t)y * W, xr, W, z);
-            ld_z4(l1p + (size_t)y * W, xr, W, l1);
-            ld_z4(l2p + (size_t)y * W, xr, W, l2);
+            float z[4][GF_NCH], l1[4][GF_NCH], l2[4][GF_NCH], g[4];
+            ld_grp(zp + (size_t)y * W * 4, xr, W, z);
+            ld_grp(l1p + (size_t)y * W * 4, xr, W, l1);
+            ld_grp(l2p + (size_t)y * W * 4, xr, W, l2);
             ld_cols4<VEC>(gp + (size_t)y * W, xr, W, g);
             const float cy = win_count(y, H);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float rn = cr[k] > 0.f ? __frcp_rn(cy * cr[k]) : 0.f;
                 const float w1 = sg * rn, wg = sg * __fmul_rn(g[k], rn), sgk = sg * g[k];
-                const float zc[4] = {z[k].x, z[k].y, z[k].z, z[k].w};
-                const float a1[4] = {l1[k].x, l1[k].y, l1[k].z, l1[k].w};
-                const float a2[4] = {l2[k].x, l2[k].y, l2[k].z, l2[k].w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    Sz[k][c] = fmaf(sg, zc[c], Sz[k][c]);
-                    Sgz[k][c] = fmaf(sgk, zc[c], Sgz[k][c]);
-                    P1[k][c] = fmaf(wg, a1[c], P1[k][c]);
-                    P2[k][c] = fmaf(w1, a1[c], P2[k][c]);
-                    P3[k][c] = fmaf(wg, a2[c], P3[k][c]);
-                    P4[k][c] = fmaf(w1, a2[c], P4[k][c]);
+                for (int c = 0; c < GF_NCH; ++c) {
+                    Sz[k][c] = fmaf(sg, z[k][c], Sz[k][c]);
+                    Sgz[k][c] = fmaf(sgk, z[k][c], Sgz[k][c]);
+                    P1[k][c] = fmaf(wg, l1[k][c], P1[k][c]);
+                    P2[k][c] = fmaf(w1, l1[k][c], P2[k][c]);
+                    P3[k][c] = fmaf(wg, l2[k][c], P3[k][c]);
+                    P4[k][c] = fmaf(w1, l2[k][c], P4[k][c]);
                 }
             }
         }
@@ -432,28 +446,16 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
 #pragma unroll
             for (int k = 0; k < 4; ++k) rn[k] = cs[k] > 0.f ? __frcp_rn(cy * cs[k]) : 0.f;
         }
-        float oc[4][4], om[4][4], GV[4] = {0.f, 0.f, 0.f, 0.f}, GM[4] = {0.f, 0.f, 0.f, 0.f};
+        float oc[4][GF_NCH], om[4][GF_NCH], GV[4] = {0.f, 0.f, 0.f, 0.f}, GM[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float a[4], bz[4], bg[4], pa1[4], pb1[4], pa2[4], pb2[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sz[k][c];
-            hsum9(a, bz);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sgz[k][c];
-            hsum9(a, bg);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = P1[k][c];
-            hsum9(a, pa1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = P2[k][c];
-            hsum9(a, pb1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = P3[k][c];
-            hsum9(a, pa2);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = P4[k][c];
-            hsum9(a, pb2);
+        for (int c = 0; c < GF_NCH; ++c) {
+            float bz[4], bg[4], pa1[4], pb1[4], pa2[4], pb2[4];
+            hsum9c(Sz, c, bz);
+            hsum9c(Sgz, c, bg);
+            hsum9c(P1, c, pa1);
+            hsum9c(P2, c, pb1);
+            hsum9c(P3, c, pa2);
+            hsum9c(P4, c, pb2);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float mz = bz[k] * rn[k];
@@ -468,16 +470,20 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
                 om[k][c] = gmz * rn[k];
             }
         }
+        float ov[4], on[4];
+        bool ok[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (cs[k] > 0.f) {
-                const size_t o = (size_t)ys * W + xs + k;
-                gcp[o] = make_float4(oc[k][0], oc[k][1], oc[k][2], oc[k][3]);
-                gmp[o] = make_float4(om[k][0], om[k][1], om[k][2], om[k][3]);
-                gvp[o] = GV[k] * rn[k];
-                gnp[o] = (GM[k] - 2.f * mx[k] * GV[k]) * rn[k];
+            ok[k] = cs[k] > 0.f;
+            ov[k] = GV[k] * rn[k];
+            on[k] = (GM[k] - 2.f * mx[k] * GV[k]) * rn[k];
+            if (ok[k]) {
+                st_grp(gcp + (size_t)ys * W * 4, xs + k, oc[k]);
+                st_grp(gmp + (size_t)ys * W * 4, xs + k, om[k]);
             }
         }
+        st_cols4<VEC>(gvp + (size_t)ys * W, xs, ov, ok);
+        st_cols4<VEC>(gnp + (size_t)ys * W, xs, on, ok);
     }
 }
 
@@ -487,37 +493,31 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
                          const float* __restrict__ gc, const float* __restrict__ gm,
                          const float* __restrict__ gvn, const float* __restrict__ gmn,
                          float* __restrict__ gfeat, float* __restrict__ gres_partial,
-                         int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
+                         int P, int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int item = blockIdx.x * 2 + warp;
-    if (item >= nitems) return;
-    const int q = item % Q; item /= Q;
-    const int strip = item % nstrips; item /= nstrips;
-    const int chunk = item % nchunks;
-    const int b = item / nchunks;
-    const int x0 = strip * GA_OUTW, y0 = chunk * RC;
-    const int rows = min(RC, H - y0);
+    GfItem it;
+    if (!gf_item(blockIdx.x * 2 + warp, nitems, P, Q, nstrips, nchunks, GA_OUTW, RC, H, W, it)) return;
+    const int b = it.b, x0 = it.x0, y0 = it.y0, rows = it.rows;
     const int xs = x0 - 4 + 4 * lane, xo = xs + 4;
     const size_t plane = (size_t)H * W;
-    const size_t qoff = ((size_t)b * Q + q) * plane;
-    const float4* zp = reinterpret_cast<const float4*>(feat) + qoff;
-    const float4* gcp = reinterpret_cast<const float4*>(gc) + qoff;
-    const float4* gmp = reinterpret_cast<const float4*>(gm) + qoff;
+    const float* zp = feat + it.qoff;
+    const float* gcp = gc + it.qoff;
+    const float* gmp = gm + it.qoff;
     const float* gp = guide + (size_t)b * plane;
-    const float* gvp = gvn + ((size_t)q * B + b) * plane;
-    const float* gnp = gmn + ((size_t)q * B + b) * plane;
-    float4* gzp = reinterpret_cast<float4*>(gfeat) + qoff;
-    float* gxp = gres_partial + ((size_t)q * B + b) * plane;
+    const float* gvp = gvn + ((size_t)it.grp * B + b) * plane;
+    const float* gnp = gmn + ((size_t)it.grp * B + b) * plane;
+    float* gzp = gfeat + it.qoff;
+    float* gxp = gres_partial + ((size_t)it.grp * B + b) * plane;
 
     bool ok_o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) ok_o[k] = xo + k < W && 4 * lane + k < GA_OUTW;
-    float Sc[4][4], Sm[4][4], SV[4], SM[4];
+    float Sc[4][GF_NCH], Sm[4][GF_NCH], SV[4], SM[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         SV[k] = SM[k] = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Sc[k][c] = Sm[k][c] = 0.f;
+        for (int c = 0; c < GF_NCH; ++c) Sc[k][c] = Sm[k][c] = 0.f;
     }
     const int nt = rows + 8;
     for (int t = 0; t < nt; ++t) {
@@ -527,58 +527,48 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
             const int y = side == 0 ? ys : ys - 9;
             if (y < 0 || y >= H || (side == 1 && t < 9)) continue;
             const float sg = side == 0 ? 1.f : -1.f;
-            float4 c4[4], m4[4];
-            float v[4], n[4];
-            ld_z4(gcp + (size_t)y * W, xs, W, c4);
-            ld_z4(gmp + (size_t)y * W, xs, W, m4);
+            float c4[4][GF_NCH], m4[4][GF_NCH], v[4], n[4];
+            ld_grp(gcp + (size_t)y * W * 4, xs, W, c4);
+            ld_grp(gmp + (size_t)y * W * 4, xs, W, m4);
             ld_cols4<VEC>(gvp + (size_t)y * W, xs, W, v);
             ld_cols4<VEC>(gnp + (size_t)y * W, xs, W, n);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                Sc[k][0] = fmaf(sg, c4[k].x, Sc[k][0]); Sc[k][1] = fmaf(sg, c4[k].y, Sc[k][1]);
-                Sc[k][2] = fmaf(sg, c4[k].z, Sc[k][2]); Sc[k][3] = fmaf(sg, c4[k].w, Sc[k][3]);
-                Sm[k][0] = fmaf(sg, m4[k].x, Sm[k][0]); Sm[k][1] = fmaf(sg, m4[k].y, Sm[k][1]);
-                Sm[k][2] = fmaf(sg, m4[k].z, Sm[k][2]); Sm[k][3] = fmaf(sg, m4[k].w, Sm[k][3]);
+#pragma unroll
+                for (int c = 0; c < GF_NCH; ++c) {
+                    Sc[k][c] = fmaf(sg, c4[k][c], Sc[k][c]);
+                    Sm[k][c] = fmaf(sg, m4[k][c], Sm[k][c]);
+                }
                 SV[k] = fmaf(sg, v[k], SV[k]);
                 SM[k] = fmaf(sg, n[k], SM[k]);
             }
         }
         if (t < 8) continue;
         const int yo = ys - 4;                     // output row, inside the chunk and the image
-        float4 z[4];
-        float g[4], gxd[4], bv[4], bm[4];
-        ld_z4(zp + (size_t)yo * W, xo, W, z);
+        float z[4][GF_NCH], g[4], gxd[4], bv[4], bm[4];
+        ld_grp(zp + (size_t)yo * W * 4, xo, W, z);
         ld_cols4<VEC>(gp + (size_t)yo * W, xo, W, g);
         ld_cols4<VEC>(gxp + (size_t)yo * W, xo, W, gxd);
         hsum9(SV, bv);
         hsum9(SM, bm);
-        float gx[4], gz[4][4];
+        float gx[4], gz[4][GF_NCH];
 #pragma unroll
         for (int k = 0; k < 4; ++k) gx[k] = fmaf(2.f * g[k], bv[k], bm[k]) + gxd[k];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float a[4], tt[4], uu[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sc[k][c];
-            hsum9(a, tt);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = Sm[k][c];
-            hsum9(a, uu);
+        for (int c = 0; c < GF_NCH; ++c) {
+            float tt[4], uu[4];
+            hsum9c(Sc, c, tt);
+            hsum9c(Sm, c, uu);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float zc = c == 0 ? z[k].x : (c == 1 ? z[k].y : (c == 2 ? z[k].z : z[k].w));
                 gz[k][c] = fmaf(tt[k], g[k], uu[k]);
-                gx[k] = fmaf(tt[k], zc, gx[k]);
+                gx[k] = fmaf(tt[k], z[k][c], gx[k]);
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (ok_o[k]) {
-                const size_t o = (size_t)yo * W + xo + k;
-                gzp[o] = make_float4(gz[k][0], gz[k][1], gz[k][2], gz[k][3]);
-                gxp[o] = gx[k];
-            }
-        }
+        for (int k = 0; k < 4; ++k)
+            if (ok_o[k]) st_grp(gzp + (size_t)yo * W * 4, xo + k, gz[k]);
+        st_cols4<VEC>(gxp + (size_t)yo * W, xo, gx, ok_o);
     }
 }
 
@@ -598,6 +588,12 @@ static int gf_march_attr() {
     return 0;
 }
 
+// row chunks of ~120 rows: the running sums restart per chunk (8-16 halo rows of recompute each)
+static void gf_chunks(int H, int* nchunks, int* RC) {
+    *nchunks = H <= 160 ? 1 : (H + 60) / 120;
+    *RC = cdiv(H, *nchunks);
+}
+
 extern "C" int paif_gf_guide_stats(const float* residue, float* stats, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(residue && stats, "null pointer");
     PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
@@ -612,28 +608,29 @@ extern "C" int paif_gf_decomp_forward(const float* feat, const float* residue, c
     PAIF_REQUIRE(feat && residue && stats && lf1 && lf2, "null pointer");
     PAIF_REQUIRE(C > 0 && C % 4 == 0, "C must be a multiple of 4");
     PAIF_REQUIRE(H > 9 && W > 9, "guided filter needs H, W > 2r+1 = 9");
-    const int Q = C / 4;
+    const int Q = C / 4, P = C / GF_NCH;
     const int nstrips = cdiv(W, GM_OUTW);
-    // row chunks of ~120 rows: the running sums restart per chunk (16 halo rows of recompute each)
-    const int nchunks = H <= 160 ? 1 : (H + 60) / 120;
-    const int RC = cdiv(H, nchunks);
-    const long long nitems = (long long)B * Q * nstrips * nchunks;
+    int nchunks, RC;
+    gf_chunks(H, &nchunks, &RC);
+    const long long nitems = (long long)B * P * nstrips * nchunks;
     PAIF_REQUIRE(nitems < (1ll << 30), "problem too large");
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats)) % 16 == 0);
     if (int r = gf_march_attr()) return r;
     const int grid = (int)((nitems + GM_WPC - 1) / GM_WPC);
     if (vec)
         gf_forward_march_kernel<true, 0><<<grid, GM_WPC * 32, GM_SMEM, (cudaStream_t)stream>>>(
-            feat, residue, stats, lf1, lf2, nullptr, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+            feat, residue, stats, lf1, lf2, nullptr, P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
     else
         gf_forward_march_kernel<false, 0><<<grid, GM_WPC * 32, GM_SMEM, (cudaStream_t)stream>>>(
-            feat, residue, stats, lf1, lf2, nullptr, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+            feat, residue, stats, lf1, lf2, nullptr, P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
     return check_launch("paif_gf_decomp_forward");
 }
 
+extern "C" int paif_gf_guide_parts(int C) { return C / GF_NCH; }
+
 extern "C" long long paif_gf_backward_work_floats(int C, int B, int H, int W) {
-    // two C-channel maps (gcov/N, gmean_z/N) + two per-quad planes (gvar/N, gmean_g/N)
-    return (long long)B * H * W * (2LL * C + 2LL * (C / 4));
+    // two C-channel maps (gcov/N, gmean_z/N) + two planes per channel group (gvar/N, gmean_g/N)
+    return (long long)B * H * W * (2LL * C + 2LL * (C / GF_NCH));
 }
 
 extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, const float* stats,
@@ -643,50 +640,49 @@ extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, 
     PAIF_REQUIRE(feat && residue && stats && glf1 && glf2 && gfeat && gres_partial && work, "null pointer");
     PAIF_REQUIRE(C > 0 && C % 4 == 0, "C must be a multiple of 4");
     PAIF_REQUIRE(H > 9 && W > 9, "guided filter needs H, W > 2r+1 = 9");
-    const int Q = C / 4;
-    const size_t map = (size_t)B * C * H * W, qplanes = (size_t)Q * B * H * W;
+    const int Q = C / 4, P = C / GF_NCH;
+    const size_t map = (size_t)B * C * H * W, pplanes = (size_t)P * B * H * W;
     float* gc = work;
     float* gm = work + map;
     float* gvn = work + 2 * map;
-    float* gmn = gvn + qplanes;
-    const int nchunks = H <= 160 ? 1 : (H + 60) / 120;
-    const int RC = cdiv(H, nchunks);
+    float* gmn = gvn + pplanes;
+    int nchunks, RC;
+    gf_chunks(H, &nchunks, &RC);
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats) |
-                                       reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(gres_partial)) % 16 == 0) &&
-                     (qplanes % 4 == 0);
+                                       reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(gres_partial)) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     if (int r = gf_march_attr()) return r;
     {   // pass A: adjoint of the level-2 boxes + pointwise chain rule
         const int nstrips = cdiv(W, GA_OUTW);
-        const long long nitems = (long long)B * Q * nstrips * nchunks;
+        const long long nitems = (long long)B * P * nstrips * nchunks;
         PAIF_REQUIRE(nitems < (1ll << 30), "problem too large");
         const int grid = (int)((nitems + 1) / 2);
         if (vec) gf_adjoint_level2_kernel<true><<<grid, 64, 0, st>>>(feat, residue, stats, glf1, glf2, gc, gm, gvn, gmn,
-                                                                    Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+                                                                    P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
         else gf_adjoint_level2_kernel<false><<<grid, 64, 0, st>>>(feat, residue, stats, glf1, glf2, gc, gm, gvn, gmn,
-                                                                  Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+                                                                  P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
         if (int r = check_launch("paif_gf_decomp_backward(level 2)")) return r;
     }
     {   // pass B: direct guide term (forward recompute of mean_A)
         const int nstrips = cdiv(W, GM_OUTW);
-        const long long nitems = (long long)B * Q * nstrips * nchunks;
+        const long long nitems = (long long)B * P * nstrips * nchunks;
         const int grid = (int)((nitems + GM_WPC - 1) / GM_WPC);
         float* l1 = const_cast<float*>(glf1);
         float* l2 = const_cast<float*>(glf2);
         if (vec) gf_forward_march_kernel<true, 1><<<grid, GM_WPC * 32, GM_SMEM, st>>>(feat, residue, stats, l1, l2, gres_partial,
-                                                                                    Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+                                                                                    P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
         else gf_forward_march_kernel<false, 1><<<grid, GM_WPC * 32, GM_SMEM, st>>>(feat, residue, stats, l1, l2, gres_partial,
-                                                                                  Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+                                                                                  P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
         if (int r = check_launch("paif_gf_decomp_backward(direct term)")) return r;
     }
     {   // pass C: adjoint of the level-1 boxes, final gradients
         const int nstrips = cdiv(W, GA_OUTW);
-        const long long nitems = (long long)B * Q * nstrips * nchunks;
+        const long long nitems = (long long)B * P * nstrips * nchunks;
         const int grid = (int)((nitems + 1) / 2);
         if (vec) gf_adjoint_level1_kernel<true><<<grid, 64, 0, st>>>(feat, residue, gc, gm, gvn, gmn, gfeat, gres_partial,
-                                                                    Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+                                                                    P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
         else gf_adjoint_level1_kernel<false><<<grid, 64, 0, st>>>(feat, residue, gc, gm, gvn, gmn, gfeat, gres_partial,
-                                                                  Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
+                                                                  P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
     }
     return check_launch("paif_gf_decomp_backward");
 }

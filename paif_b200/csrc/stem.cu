@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256)
 stem_backward_pre_kernel(const float* __restrict__ feat, const float* __restrict__ slope_p,
                          const float* __restrict__ g0, const float* __restrict__ g1,
                          const float* __restrict__ g2, const float* __restrict__ g3,
-                         const float* __restrict__ gres_partial, float* __restrict__ gpre,
+                         const float* __restrict__ gres_partial, int nparts, float* __restrict__ gpre,
                          int B, int H, int W) {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
@@ -83,8 +83,7 @@ stem_backward_pre_kernel(const float* __restrict__ feat, const float* __restrict
     }
     float gres = 0.f;
     if (gres_partial) {
-#pragma unroll
-        for (int q = 0; q < STEM_C / 4; ++q) gres += gres_partial[((size_t)q * B + b) * plane + pix];
+        for (int q = 0; q < nparts; ++q) gres += gres_partial[((size_t)q * B + b) * plane + pix];   // fixed order: deterministic
     }
 #pragma unroll
     for (int q = 0; q < STEM_C / 4; ++q) {
@@ -161,13 +160,14 @@ extern "C" int paif_stem_forward(const float* img, long long sb, long long sy, l
 
 extern "C" int paif_stem_backward_pre(const float* feat, const float* slope,
                                       const float* g0, const float* g1, const float* g2, const float* g3,
-                                      const float* gres_partial, float* gpre,
+                                      const float* gres_partial, int nparts, float* gpre,
                                       int C, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(feat && slope && gpre, "null pointer");
+    PAIF_REQUIRE(!gres_partial || nparts > 0, "nparts must be positive");
     PAIF_REQUIRE(C == STEM_C, "C must be 32");
     dim3 grid(cdiv(W, 32), cdiv(H, 8), B), block(32, 8);
     stem_backward_pre_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(feat, slope, g0, g1, g2, g3,
-                                                                     gres_partial, gpre, B, H, W);
+                                                                     gres_partial, nparts, gpre, B, H, W);
     return check_launch("paif_stem_backward_pre");
 }
 

@@ -707,7 +707,8 @@ class Network_Fusion_Searched(nn.Module):
             glf2 = rt.conv([gx], wd[1])[0]
             gz = rt.conv([gx], wd[2])[0]
             gfeat = rt.new_map()
-            gres = torch.empty((C // 4, B, H, W), device=g.device, dtype=torch.float32)
+            nparts = _lib.load().paif_gf_guide_parts(C)
+            gres = torch.empty((nparts, B, H, W), device=g.device, dtype=torch.float32)
             work = torch.empty((_lib.load().paif_gf_backward_work_floats(C, B, H, W),), device=g.device, dtype=torch.float32)
             rt.call("paif_gf_decomp_backward", saved["feats"][i].data_ptr(), saved["guides"][i].data_ptr(),
                     saved["gstats"][i].data_ptr(), glf1.data_ptr(), glf2.data_ptr(), gfeat.data_ptr(), gres.data_ptr(),
@@ -715,7 +716,7 @@ class Network_Fusion_Searched(nn.Module):
             del work
             gstem = rt.new_map()
             rt.call("paif_stem_backward_pre", saved["feats"][i].data_ptr(), p["stem_a"][i].data_ptr(),
-                    gb.data_ptr(), gz.data_ptr(), gfeat.data_ptr(), None, gres.data_ptr(), gstem.data_ptr(),
+                    gb.data_ptr(), gz.data_ptr(), gfeat.data_ptr(), None, gres.data_ptr(), nparts, gstem.data_ptr(),
                     C, B, H, W)
             gimg = rt.new_plane()
             rt.call("paif_stem_backward", gstem.data_ptr(), p["stem_w"][i].data_ptr(), gimg.data_ptr(), C, B, H, W)

@@ -55,7 +55,7 @@ def test_guided_filter_adjoint(shape, smooth):
     zc, gc = to_c4(z.float()).to(DEV), guide.detach().float()[:, 0].contiguous().to(DEV)
     g1c, g2c = to_c4(g1.float()).to(DEV), to_c4(g2.float()).to(DEV)
     gfeat = torch.empty_like(zc)
-    gres = torch.empty(8, B, H, W, device=DEV)
+    gres = torch.empty(_lib.load().paif_gf_guide_parts(32), B, H, W, device=DEV)
     stats = torch.empty(3, B, H, W, device=DEV)
     _lib.call("paif_gf_guide_stats", gc.data_ptr(), stats.data_ptr(), B, H, W, stream())
     work = torch.empty(_lib.load().paif_gf_backward_work_floats(32, B, H, W), device=DEV)
