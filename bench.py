@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", action="store_true", help="print the per-launch CUDA-event table of one step to stderr")
     ap.add_argument("--bwd-steps", type=int, default=3, help="timed forward+backward-to-input steps (0 = skip)")
+    ap.add_argument("--pgd-frames", type=int, default=4,
+                    help="frames per GPU for the PGD-10 robust-eval leg (0 = skip); stock-PyTorch MiT-B3-shaped consumer")
     return ap.parse_args()
 
 
@@ -122,6 +124,62 @@ def cpu_port_pairs_per_s(steps, H, W, warmup=1):
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     return steps / sum(times), cores, times
+
+
+class SyntheticFrames:
+    """Indexable of (vis[3,H,W], ir[1,H,W], label[H,W]) generated from the GLOBAL frame index, so every rank
+    sees the same frame for the same index whatever the sharding."""
+
+    def __init__(self, n, H, W, seed=2):
+        self.n, self.H, self.W, self.seed = n, H, W, seed
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        import torch
+        g = torch.Generator().manual_seed(self.seed * 1000003 + i)
+        return (torch.rand(3, self.H, self.W, generator=g), torch.rand(1, self.H, self.W, generator=g),
+                torch.randint(0, 9, (self.H, self.W), generator=g))
+
+
+def run_pgd_leg(net, args, world, rank, dev, barrier):
+    """BASELINE's second metric: PGD-10 (eps 8/255, alpha 2/255, robust_test.py:40-41) robust-eval frames/s.
+    Every frame: 10 x (fusion + consumer forward, backward to the inputs) + 1 clean forward + confusion update;
+    frames are sharded over the ranks; ONE int64 all-reduce of the 9x9 confusion matrix at the end (inside the
+    timed region).  The consumer is the stock-PyTorch MiT-B3-shaped SegFormerLite (random init)."""
+    import torch
+    import torch.distributed as dist
+    from paif_b200.consumer import FusionSegTask, SegFormerLite
+    from paif_b200.evaluate import robust_eval
+    torch.backends.cuda.matmul.allow_tf32 = True            # the stock consumer may use TF32 matmuls (SURVEY.md 7)
+    torch.manual_seed(3)
+    seg = SegFormerLite(9, 256).to(dev).eval()
+    for p in seg.parameters():
+        p.requires_grad_(False)
+    task = FusionSegTask(net, seg).to(dev).eval()
+    H, W = args.height, args.width
+    n_total = args.pgd_frames * world
+    frames = SyntheticFrames(n_total + world, H, W)
+    robust_eval(task, [frames[n_total + rank]], attack_iters=2)             # warm-up (allocator, cuDNN autotune)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    meter = robust_eval(task, SyntheticFrames(n_total, H, W), attack_iters=10, rank=rank, world_size=world)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    conf = meter.conf.cpu()
+    return {"metric": "PGD-10 robust-eval frames/s", "value": n_total / (ms * 1e-3), "unit": "frames/s",
+            "frames": n_total, "frames_per_gpu": args.pgd_frames, "ms_per_frame_per_gpu": ms / max(args.pgd_frames, 1),
+            "attack": "PGD-10 eps 8/255 alpha 2/255, l_seg loss, seeded start per global frame index",
+            "consumer": "stock-PyTorch SegFormerLite (MiT-B3 shape, random init, TF32 matmul, params frozen)",
+            "confusion_sum": int(conf.sum()), "confusion_all_reduce": "int64 SUM over %d rank(s)" % world,
+            "confusion_trace": int(conf.diag().sum())}
 
 
 def run_reference(args):
@@ -306,6 +364,8 @@ def run_ours(args):
                                                                      m["bytes"] / (t * 1e-3) / 1e9)
             sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
         sys.stderr.write("sum of launches %.3f ms (step %.3f ms)\n" % (tot, ms / args.steps))
+    pgd = run_pgd_leg(net, args, world, rank, dev, barrier) if args.pgd_frames > 0 else None
+
     # dominant kernel: the dense-conv engine (all conv launches of the timed steps).  After the wide-N MMA
     # rewrite every conv shape of the genotype except the 7x7 is HBM-bound, so the engine is judged against
     # the HBM roofline: algorithmic bytes (each source / residual map read once, each output written once).
@@ -360,6 +420,8 @@ def run_ours(args):
     }
     if fwd_bwd is not None:
         line["fwd_bwd"] = fwd_bwd
+    if pgd is not None:
+        line["pgd10"] = pgd
     if not args.no_cpu_baseline and world == 1:
         v, cores, times = cpu_port_pairs_per_s(args.cpu_baseline_steps, H, W)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",

@@ -88,3 +88,31 @@ def test_world2_gloo_all_reduce_is_bit_exact(tmp_path):
         got = torch.load(os.path.join(str(tmp_path), "conf_%d.pt" % r))
         assert got.dtype == torch.int64 and torch.equal(got, full)
     assert int(full.sum()) == int((labels != 255).sum())
+
+
+def test_task_glue_matches_reference_colour_conventions_and_consumer_shapes():
+    """FusionSegTask restates Network_MM_CompModel.forward's glue (core/model_fusion_auto.py:69-111, 712-729);
+    checked here against a direct evaluation of the reference's formulas, with a trivial fusion stand-in."""
+    import torch.nn as nn
+    from paif_b200.consumer import FusionSegTask, SegFormerLite
+
+    class MeanFusion(nn.Module):
+        def forward(self, ir, vis):
+            return 0.5 * (ir + vis)
+
+    torch.manual_seed(0)
+    task = FusionSegTask(MeanFusion(), SegFormerLite(9, 256, depths=(1, 1, 1, 1))).eval()
+    ir, vis = torch.rand(2, 1, 64, 96), torch.rand(2, 3, 64, 96)
+    fused, seg = task(ir, vis)
+    assert fused.shape == (2, 1, 64, 96) and seg.shape == (2, 9, 16, 24)
+    # reference formulas
+    R, G, B = vis[:, 0], vis[:, 1], vis[:, 2]
+    Y = 0.299 * R + 0.587 * G + 0.114 * B
+    Cr, Cb = (R - Y) * 0.713 + 0.5, (B - Y) * 0.564 + 0.5
+    torch.testing.assert_close(fused[:, 0], 0.5 * (ir[:, 0] + Y))
+    flat = torch.stack([fused[:, 0], Cr, Cb], -1).reshape(-1, 3)
+    mat = torch.tensor([[1.0, 1.0, 1.0], [1.403, -0.714, 0.0], [0.0, -0.344, 1.773]])
+    rgb = (flat + torch.tensor([0.0, -0.5, -0.5])).mm(mat).reshape(2, 64, 96, 3).permute(0, 3, 1, 2).clamp(0, 1)
+    rgb = (rgb - rgb.min()) / (rgb.max() - rgb.min())
+    x = (rgb * 255 - task.mean) / task.std
+    torch.testing.assert_close(task.denoise_net(x), seg, rtol=1e-4, atol=1e-4)
