@@ -150,10 +150,14 @@ __device__ __forceinline__ void gf_ab(float mz, float cov, float mx, float i1, f
 }
 
 // work item -> (image, channel group, strip, chunk); returns false past the end
-struct GfItem { int b, grp, x0, y0, rows; size_t qoff; int coff; };
+struct GfItem { int b, grp, x0, y0, rows; size_t qoff; int coff; bool live; };
 __device__ __forceinline__ bool gf_item(int item, int nitems, int P, int Q, int nstrips, int nchunks, int outw, int RC,
                                         int H, int W, GfItem& it) {
-    if (item >= nitems) return false;
+    // No early return for a surplus warp: it would make the rest of the kernel "possibly divergent" for the
+    // compiler (WARPSYNC + collective brackets around every shuffle).  The surplus warp of an odd item count
+    // recomputes the last item with all of its stores masked off (it.live == false).
+    it.live = item < nitems;
+    if (!it.live) item = nitems - 1;
     it.grp = item % P; item /= P;
     const int strip = item % nstrips; item /= nstrips;
     const int chunk = item % nchunks;
@@ -177,7 +181,7 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
     extern __shared__ float4 gm_ring[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GfItem it;
-    if (!gf_item(blockIdx.x * GM_WPC + warp, nitems, P, Q, nstrips, nchunks, GM_OUTW, RC, H, W, it)) return;
+    gf_item(blockIdx.x * GM_WPC + warp, nitems, P, Q, nstrips, nchunks, GM_OUTW, RC, H, W, it);
     const int b = it.b, x0 = it.x0, y0 = it.y0, rows = it.rows;
     float4* ring = gm_ring + warp * GM_RING_F4 + lane;          // element (slot, i) at [(slot * 2 * GF_NCH + i) * 32]
 
@@ -191,11 +195,11 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
     float* o1 = lf1 + it.qoff;
     float* o2 = lf2 + it.qoff;
 
-    float cs[4], co[4];            // clipped window widths of the level-1 / output columns (0 = column unused)
+    float cs[4], co[4];            // 1 / clipped window width of the level-1 / output columns (0 = column unused)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        cs[k] = (xs + k >= 0 && xs + k < W) ? win_count(xs + k, W) : 0.f;
-        co[k] = (xo + k < W && 4 * lane + k < GM_OUTW) ? win_count(xo + k, W) : 0.f;
+        cs[k] = (xs + k >= 0 && xs + k < W) ? __frcp_rn(win_count(xs + k, W)) : 0.f;
+        co[k] = (it.live && xo + k < W && 4 * lane + k < GM_OUTW) ? __frcp_rn(win_count(xo + k, W)) : 0.f;
     }
 
     float Sz[4][GF_NCH], Sgz[4][GF_NCH], SA1[4][GF_NCH], Sb1[4][GF_NCH], SA2[4][GF_NCH], Sb2[4][GF_NCH];   // [column][channel]
@@ -234,7 +238,7 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
 #pragma unroll
             for (int c = 0; c < GF_NCH; ++c) {
                 Sz[k][c] += zn[k][c] - zq[k][c];
-                Sgz[k][c] += __fmul_rn(gn[k], zn[k][c]) - __fmul_rn(gq[k], zq[k][c]);
+                Sgz[k][c] = __fmaf_rn(-gq[k], zq[k][c], __fmaf_rn(gn[k], zn[k][c], Sgz[k][c]));   // exact products both times
             }
         // ---- prefetch the rows of iteration t+1 (entering: yr+1, leaving: yr-8)
         {
@@ -263,9 +267,9 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
             ld_cols4<VEC>(mxp + (size_t)ys * W, xs, W, mx);
             ld_cols4<VEC>(i1p + (size_t)ys * W, xs, W, i1);
             ld_cols4<VEC>(i2p + (size_t)ys * W, xs, W, i2);
-            const float cy = win_count(ys, H);
+            const float rcy = __frcp_rn(win_count(ys, H));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rn[k] = cs[k] > 0.f ? __frcp_rn(cy * cs[k]) : 0.f;
+            for (int k = 0; k < 4; ++k) rn[k] = rcy * cs[k];
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) { mx[k] = i1[k] = i2[k] = rn[k] = 0.f; }
@@ -311,9 +315,9 @@ gf_forward_march_kernel(const float* __restrict__ feat, const float* __restrict_
         // ---- output row yo (always inside the image and the chunk)
         float rno[4];
         {
-            const float cy = win_count(yo, H);
+            const float rcy = __frcp_rn(win_count(yo, H));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rno[k] = co[k] > 0.f ? __frcp_rn(cy * co[k]) : 0.f;
+            for (int k = 0; k < 4; ++k) rno[k] = rcy * co[k];
         }
         if (MODE == 0) {
             float go[4];
@@ -378,7 +382,7 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
                          int P, int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GfItem it;
-    if (!gf_item(blockIdx.x * 2 + warp, nitems, P, Q, nstrips, nchunks, GA_OUTW, RC, H, W, it)) return;
+    gf_item(blockIdx.x * 2 + warp, nitems, P, Q, nstrips, nchunks, GA_OUTW, RC, H, W, it);
     const int b = it.b, x0 = it.x0, y0 = it.y0, rows = it.rows;
     const int xr = x0 - 4 + 4 * lane, xs = xr + 4;
     const size_t plane = (size_t)H * W;
@@ -397,8 +401,8 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
     float cr[4], cs[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        cr[k] = (xr + k >= 0 && xr + k < W) ? win_count(xr + k, W) : 0.f;
-        cs[k] = (xs + k < W && 4 * lane + k < GA_OUTW) ? win_count(xs + k, W) : 0.f;
+        cr[k] = (xr + k >= 0 && xr + k < W) ? __frcp_rn(win_count(xr + k, W)) : 0.f;      // reciprocal widths, 0 = unused
+        cs[k] = (it.live && xs + k < W && 4 * lane + k < GA_OUTW) ? __frcp_rn(win_count(xs + k, W)) : 0.f;
     }
     float Sz[4][GF_NCH], Sgz[4][GF_NCH], P1[4][GF_NCH], P2[4][GF_NCH], P3[4][GF_NCH], P4[4][GF_NCH];
 #pragma unroll
@@ -419,10 +423,10 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
             ld_grp(l1p + (size_t)y * W * 4, xr, W, l1);
             ld_grp(l2p + (size_t)y * W * 4, xr, W, l2);
             ld_cols4<VEC>(gp + (size_t)y * W, xr, W, g);
-            const float cy = win_count(y, H);
+            const float rcy = __frcp_rn(win_count(y, H));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float rn = cr[k] > 0.f ? __frcp_rn(cy * cr[k]) : 0.f;
+                const float rn = rcy * cr[k];
                 const float w1 = sg * rn, wg = sg * __fmul_rn(g[k], rn), sgk = sg * g[k];
 #pragma unroll
                 for (int c = 0; c < GF_NCH; ++c) {
@@ -442,9 +446,9 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
         ld_cols4<VEC>(i1p + (size_t)ys * W, xs, W, i1);
         ld_cols4<VEC>(i2p + (size_t)ys * W, xs, W, i2);
         {
-            const float cy = win_count(ys, H);
+            const float rcy = __frcp_rn(win_count(ys, H));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rn[k] = cs[k] > 0.f ? __frcp_rn(cy * cs[k]) : 0.f;
+            for (int k = 0; k < 4; ++k) rn[k] = rcy * cs[k];
         }
         float oc[4][GF_NCH], om[4][GF_NCH], GV[4] = {0.f, 0.f, 0.f, 0.f}, GM[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -496,7 +500,7 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
                          int P, int Q, int B, int H, int W, int RC, int nstrips, int nchunks, int nitems) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GfItem it;
-    if (!gf_item(blockIdx.x * 2 + warp, nitems, P, Q, nstrips, nchunks, GA_OUTW, RC, H, W, it)) return;
+    gf_item(blockIdx.x * 2 + warp, nitems, P, Q, nstrips, nchunks, GA_OUTW, RC, H, W, it);
     const int b = it.b, x0 = it.x0, y0 = it.y0, rows = it.rows;
     const int xs = x0 - 4 + 4 * lane, xo = xs + 4;
     const size_t plane = (size_t)H * W;
@@ -511,7 +515,7 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
 
     bool ok_o[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) ok_o[k] = xo + k < W && 4 * lane + k < GA_OUTW;
+    for (int k = 0; k < 4; ++k) ok_o[k] = it.live && xo + k < W && 4 * lane + k < GA_OUTW;
     float Sc[4][GF_NCH], Sm[4][GF_NCH], SV[4], SM[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
