@@ -66,23 +66,29 @@ def test_guided_filter_adjoint(shape, smooth):
     assert e_z < 2e-3 and e_g < 2e-3, (e_z, e_g)
 
 
+# (engine, fused-image gate, gradient rel-L2 gate, sign-agreement gate): the exact-fp32 engine is held to the
+# reference's own fp32-vs-fp64 noise floor, the TF32 tensor-core engine to SURVEY.md 8d's TF32 gates
+GRAD_GATES = [("direct", 5e-5, 1e-2, 0.999), ("tcgen05", 1e-3, 5e-2, 0.995)]
+
+
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_input_gradients_match_reference_golden(case):
+@pytest.mark.parametrize("engine,out_tol,l2_tol,sign_tol", GRAD_GATES)
+def test_input_gradients_match_reference_golden(case, engine, out_tol, l2_tol, sign_tol):
     g = load_golden(case)
     net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
     net.load_state_dict(g["state_dict"], strict=True)
     net = net.to(DEV).eval()
-    net.conv_engine = "direct"
+    net.conv_engine = engine
     ir = g["ir"].to(DEV).requires_grad_(True)
     vis_full = g["vis"].to(DEV).requires_grad_(True)
     out = net(ir, strided_vis(vis_full))
-    assert (out.detach().cpu() - g["out"]).abs().max().item() < 5e-5
+    assert (out.detach().cpu() - g["out"]).abs().max().item() < out_tol
     out.backward(g["grad_out"].to(DEV))
     g_ir, g_vis = ir.grad.cpu(), vis_full.grad.cpu()
     assert g_vis[:, 1:].abs().max().item() == 0.0          # only Y gets gradient
     for got, ref in ((g_ir, g["grad_ir"]), (g_vis[:, 0:1], g["grad_vis"][:, 0:1])):
         r, s = rel_l2(got, ref), sign_agreement(got, ref)
-        assert r < 1e-2 and s > 0.999, (case, r, s)
+        assert r < l2_tol and s > sign_tol, (case, engine, r, s)
 
 
 def test_no_grad_forward_saves_nothing_and_grad_only_where_needed():
@@ -99,3 +105,32 @@ def test_no_grad_forward_saves_nothing_and_grad_only_where_needed():
         out2 = net(ir, vis)
     assert not out2.requires_grad and torch.equal(out2, out.detach())
     assert all(p.grad is None for p in net.parameters())    # weight gradients are intentionally not produced
+
+
+def test_full_size_forward_and_gradients_480x640():
+    """BASELINE shape (480x640): forward against the CPU oracle, input gradients against the oracle's autograd,
+    default ('auto' = tcgen05 TF32) engine; plus batch-position invariance with the full-size tiling (batch 17
+    makes the conv engine use 32-row chunks and TMEM slot reuse)."""
+    from oracle import fusion_oracle as fo
+    g = load_golden("seed1_random_1x48x72")
+    sd = g["state_dict"]
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    gen = torch.Generator().manual_seed(21)
+    ir, vis = torch.rand(1, 1, 480, 640, generator=gen), torch.rand(1, 3, 480, 640, generator=gen)
+    cot = torch.randn(1, 1, 480, 640, generator=gen)
+    ir_r, vis_r = ir.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+    ref = fo.fusion_forward(sd, paif_b200.fusion_at, ir_r, vis_r)
+    g_ir_ref, g_vis_ref = torch.autograd.grad(ref, [ir_r, vis_r], cot)
+    ir_d, vis_d = ir.to(DEV).requires_grad_(True), vis.to(DEV).requires_grad_(True)
+    out = net(ir_d, vis_d)
+    assert (out.detach().cpu() - ref.detach()).abs().max().item() <= 1e-3
+    out.backward(cot.to(DEV))
+    for got, want in ((ir_d.grad.cpu(), g_ir_ref), (vis_d.grad.cpu()[:, 0:1], g_vis_ref[:, 0:1])):
+        r, s = rel_l2(got, want), sign_agreement(got, want)
+        assert r < 5e-2 and s > 0.995, (r, s)
+    with torch.no_grad():
+        big = net(ir.to(DEV).expand(17, -1, -1, -1).contiguous(), vis.to(DEV).expand(17, -1, -1, -1).contiguous())
+    assert (big[0] - out.detach()[0]).abs().max().item() <= 1e-6
+    assert torch.equal(big[0], big[16])

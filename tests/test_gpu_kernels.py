@@ -215,3 +215,28 @@ def test_conv_tcgen05_matches_direct_engine(B, H, W, k, dil, nsrc):
     assert (res[_lib.ENGINE_TCGEN05][1] - pre).abs().max().item() < 2 * tf32 * scale
     assert (res[_lib.ENGINE_DIRECT][0] - ref).abs().max().item() < 1e-4 * max(1.0, scale)
     assert (res[_lib.ENGINE_TCGEN05][2] - ref.sum((2, 3))).abs().max().item() < 1e-3 * H * W
+
+
+@pytest.mark.parametrize("k,dil,nsrc", [(3, 1, 1), (3, 1, 3), (3, 2, 1), (1, 1, 3), (5, 1, 1)])
+def test_conv_tcgen05_full_size_tiling(k, dil, nsrc):
+    """Enough tiles that the engine uses 32-row chunks: exercises TMEM slot reuse, the slot-ring wrap inside one
+    wide-N MMA, ragged last chunk / last strip.  Checked against the exact-fp32 direct engine on the GPU."""
+    B, H, W = 37, 67, 507
+    torch.manual_seed(8)
+    g = torch.Generator(device=DEV).manual_seed(8)
+    xs = [torch.randn(B, 8, H, W, 4, device=DEV, generator=g) for _ in range(nsrc)]
+    r1 = torch.randn(B, 8, H, W, 4, device=DEV, generator=g)
+    m = torch.randn(B, 8, H, W, 4, device=DEV, generator=g)
+    w = torch.randn(32, 32 * nsrc, k, k, device=DEV, generator=g) * 0.1
+    a = torch.tensor([0.3], device=DEV)
+    cw = fusion._ConvW(w, nsrc, k, dil)
+    assert cw.mma is not None
+    outs = {}
+    for eng in (_lib.ENGINE_DIRECT, _lib.ENGINE_TCGEN05):
+        o1 = rt(B, H, W, eng).conv(xs, cw, slope=a, post_scale=0.5, post_res=[r1])[0]
+        o2 = rt(B, H, W, eng).conv(xs, cw, pre_res=[r1], mask_src=m, mask_slope=a)[0]
+        outs[eng] = (o1, o2)
+    scale = outs[_lib.ENGINE_DIRECT][0].abs().max().item()
+    for i in range(2):
+        err = (outs[_lib.ENGINE_TCGEN05][i] - outs[_lib.ENGINE_DIRECT][i]).abs().max().item()
+        assert err < 2.0 ** -9 * max(scale, 1.0), (i, err, scale)
