@@ -592,10 +592,22 @@ static int gf_march_attr() {
     return 0;
 }
 
-// row chunks of ~120 rows: the running sums restart per chunk (8-16 halo rows of recompute each)
-static void gf_chunks(int H, int* nchunks, int* RC) {
-    *nchunks = H <= 160 ? 1 : (H + 60) / 120;
-    *RC = cdiv(H, *nchunks);
+// Row chunks: ~120 rows when there is plenty of work (the running sums restart per chunk; 8-16 halo rows of
+// recompute each), shorter (down to 24 rows) when a small batch would otherwise leave the GPU with fewer than
+// ~6 warps per SM of these latency-bound marching kernels.
+static void gf_chunks(int H, long long items_per_chunk, int* nchunks, int* RC) {
+    int n = H <= 160 ? 1 : (H + 60) / 120;
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long want = 6LL * sms;
+    if (items_per_chunk * n < want) {
+        long long m = (want + items_per_chunk - 1) / items_per_chunk;
+        const int max_chunks = H / 24 > 1 ? H / 24 : 1;
+        n = (int)(m < max_chunks ? m : max_chunks);
+    }
+    *nchunks = n;
+    *RC = cdiv(H, n);
+    *nchunks = cdiv(H, *RC);
 }
 
 extern "C" int paif_gf_guide_stats(const float* residue, float* stats, int B, int H, int W, void* stream) {
@@ -615,7 +627,7 @@ extern "C" int paif_gf_decomp_forward(const float* feat, const float* residue, c
     const int Q = C / 4, P = C / GF_NCH;
     const int nstrips = cdiv(W, GM_OUTW);
     int nchunks, RC;
-    gf_chunks(H, &nchunks, &RC);
+    gf_chunks(H, (long long)B * P * nstrips, &nchunks, &RC);
     const long long nitems = (long long)B * P * nstrips * nchunks;
     PAIF_REQUIRE(nitems < (1ll << 30), "problem too large");
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats)) % 16 == 0);
@@ -651,7 +663,7 @@ extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, 
     float* gvn = work + 2 * map;
     float* gmn = gvn + pplanes;
     int nchunks, RC;
-    gf_chunks(H, &nchunks, &RC);
+    gf_chunks(H, (long long)B * P * cdiv(W, GA_OUTW), &nchunks, &RC);
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats) |
                                        reinterpret_cast<uintptr_t>(work) | reinterpret_cast<uintptr_t>(gres_partial)) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;

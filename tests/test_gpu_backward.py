@@ -132,5 +132,6 @@ def test_full_size_forward_and_gradients_480x640():
         assert r < 5e-2 and s > 0.995, (r, s)
     with torch.no_grad():
         big = net(ir.to(DEV).expand(17, -1, -1, -1).contiguous(), vis.to(DEV).expand(17, -1, -1, -1).contiguous())
-    assert (big[0] - out.detach()[0]).abs().max().item() <= 1e-6
+    # (the guided-filter row chunking adapts to the batch size, so batch 17 vs 1 is close, not bit-identical)
+    assert (big[0] - out.detach()[0]).abs().max().item() <= 1e-4
     assert torch.equal(big[0], big[16])
