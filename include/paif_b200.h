@@ -123,12 +123,13 @@ int paif_dwconv_forward(const float* x, const float* w, int relu_in,
                         int C, int k, int dil, int B, int H, int W, void* stream);
 
 /* Fused DilConv (operations_m.py:494-506), C = 32, BatchNorm in eval mode folded to scale/shift:
- *   out = ch_scale * pw1x1(dw_kxk_dil(relu(x))) + ch_shift + x + r1 + r2      (r1, r2 optional residual maps:
+ *   out = ch_scale * pw1x1(dw_kxk_dil(relu(x))) + ch_shift + (add_x ? x : 0) + r1 + r2
+ * (add_x = 0 gives one half of SepConv, operations_m.py:509-526; r1, r2 optional residual maps:
  * the Cell_Chain residual, core/model_fusion_auto.py:445, and Cell_Decom's "+ feature", :516).
  * dw: [C][k*k] depthwise taps, pw: [C_out][C_in] pointwise weights. */
 int paif_dilconv_forward(const float* x, const float* dw, const float* pw, const float* ch_scale,
                          const float* ch_shift, const float* r1, const float* r2, float* out,
-                         int C, int k, int dil, int B, int H, int W, void* stream);
+                         int add_x, int C, int k, int dil, int B, int H, int W, void* stream);
 
 /* 2-arg ChannelPool — core/model_fusion_auto.py:1352-1355.
  * pooled[B][H][W][4] = (max_c ir, mean_c ir, max_c vis, mean_c vis). */
@@ -177,6 +178,9 @@ int paif_mask_scale(const float* g, const float* mask_src, const float* mask_slo
 /* out = a + b (+ c)  elementwise over n floats (n % 4 == 0) — residual adds that could not be
  * fused into a producer's epilogue (Cell_Chain.forward, core/model_fusion_auto.py:445). */
 int paif_add_maps(const float* a, const float* b, const float* c, float* out, long long n, void* stream);
+/* out = PReLU_slope(x + y); pre_out (optional) = x + y — tail of Spatial_BasicBlock (operations_m.py:203-205). */
+int paif_add_act(const float* x, const float* y, const float* slope, float* out, float* pre_out,
+                 long long n, void* stream);
 
 /* ECA backward, pass 1: w = o*e + x; gw = gu * PReLU'(w); partial sums of gw*o per (b, tile, c). */
 int paif_eca_bwd_pass1(const float* gu, const float* o, const float* x, const float* e,

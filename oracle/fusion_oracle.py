@@ -121,6 +121,31 @@ def residual_module(sd, p, x, k, d):
     return x + t
 
 
+def sep_conv(sd, p, x, k):
+    """SepConv.forward, operations_m.py:509-526 (padding k//2, dilation 1, eval-mode BN; OPS drops the dilation)."""
+    C = x.shape[1]
+    t = F.relu(x)
+    t = F.conv2d(t, sd[p + 'op.1.weight'], None, 1, k // 2, 1, groups=C)
+    t = F.conv2d(t, sd[p + 'op.2.weight'])
+    t = _bn_eval(t, sd, p + 'op.3.')
+    t = F.relu(t)
+    t = F.conv2d(t, sd[p + 'op.5.weight'], None, 1, k // 2, 1, groups=C)
+    t = F.conv2d(t, sd[p + 'op.6.weight'])
+    return _bn_eval(t, sd, p + 'op.7.')
+
+
+def spatial_basic_block(sd, p, x, k):
+    """Spatial_BasicBlock.forward operations_m.py:193-206 (with_norm=False) + the 1-arg ChannelPool /
+    spatial_attn_layer of operations_m.py:146-163 (operations_m's own ChannelPool, not the 2-arg override)."""
+    a = sd[p + 'relu.weight']
+    x0 = F.conv2d(x, sd[p + 'conv1.weight'], None, 1, 1)
+    out = prelu(x0, a)
+    out = F.conv2d(out, sd[p + 'conv2.conv.weight'], None, 1, basicconv_padding(k, 1))
+    pool = torch.cat((out.max(1)[0].unsqueeze(1), out.mean(1).unsqueeze(1)), dim=1)
+    scale = torch.sigmoid(F.conv2d(pool, sd[p + 'se.spatial.conv.weight'], None, 1, basicconv_padding(k, 1)))
+    return prelu(out * scale + x0, a)
+
+
 def parse_primitive(primitive):
     """MixedOp name grammar, core/model_fusion_auto.py:404-410."""
     parts = primitive.split('_')
@@ -140,6 +165,10 @@ def mixed_op(sd, p, primitive, x):
         return eca_basic_block(sd, p, x, k)
     if name == 'Residualblocks':
         return residual_module(sd, p, x, k, d)
+    if name == 'SepConv':
+        return sep_conv(sd, p, x, k)
+    if name == 'SPAattention':
+        return spatial_basic_block(sd, p, x, k)
     raise NotImplementedError(primitive)
 
 

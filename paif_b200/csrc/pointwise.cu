@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256, 2)
 dilconv_fused_kernel(const float* __restrict__ xin, const float* __restrict__ dw, const float* __restrict__ pw,
                      const float* __restrict__ ch_scale, const float* __restrict__ ch_shift,
                      const float* __restrict__ r1, const float* __restrict__ r2, float* __restrict__ out,
-                     int H, int W) {
+                     int add_x, int H, int W) {
     constexpr int TAPS = K * K, PAD = DIL * (K - 1) / 2;
     __shared__ __align__(16) float s_pw[32 * 32];      // [cin][cout], scaled by BN
     __shared__ __align__(16) float s_dw[TAPS * 32];    // [tap][channel]
@@ -138,7 +138,7 @@ dilconv_fused_kernel(const float* __restrict__ xin, const float* __restrict__ dw
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const size_t off = base + q * plane;
-        rx[q] = __ldg(reinterpret_cast<const float4*>(xin) + off);
+        rx[q] = add_x ? __ldg(reinterpret_cast<const float4*>(xin) + off) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (r1) rx[q] = f4_add(rx[q], __ldg(reinterpret_cast<const float4*>(r1) + off));
         if (r2) rx[q] = f4_add(rx[q], __ldg(reinterpret_cast<const float4*>(r2) + off));
     }
@@ -630,7 +630,7 @@ extern "C" int paif_dwconv_forward(const float* x, const float* w, int relu_in, 
 
 extern "C" int paif_dilconv_forward(const float* x, const float* dw, const float* pw, const float* ch_scale,
                                     const float* ch_shift, const float* r1, const float* r2, float* out,
-                                    int C, int k, int dil, int B, int H, int W, void* stream) {
+                                    int add_x, int C, int k, int dil, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(x && dw && pw && out, "null pointer");
     PAIF_REQUIRE(C == 32, "C must be 32");
     PAIF_REQUIRE(k >= 1 && k <= 7 && (k & 1) && dil >= 1, "bad kernel size / dilation");
@@ -638,7 +638,7 @@ extern "C" int paif_dilconv_forward(const float* x, const float* dw, const float
     PAIF_REQUIRE((long long)H * W < (1ll << 31), "image too large");
 #define DC_CASE(K_, D_)                                                                                              \
     if (k == K_ && dil == D_) {                                                                                      \
-        dilconv_fused_kernel<K_, D_><<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(x, dw, pw, ch_scale, ch_shift, r1, r2, out, H, W); \
+        dilconv_fused_kernel<K_, D_><<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(x, dw, pw, ch_scale, ch_shift, r1, r2, out, add_x, H, W); \
         return check_launch("paif_dilconv_forward");                                                                 \
     }
     DC_CASE(3, 1) DC_CASE(3, 2)
@@ -764,6 +764,28 @@ extern "C" int paif_mask_scale(const float* g, const float* mask_src, const floa
     const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
     mask_scale_kernel<<<blocks, 256, 0, ST>>>(g, mask_src, mask_slope, scale, out, n4);
     return check_launch("paif_mask_scale");
+}
+
+__global__ void __launch_bounds__(256)
+add_act_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ slope_p,
+               float* __restrict__ out, float* __restrict__ pre_out, size_t n4) {
+    const float a = *slope_p;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 t = f4_add(reinterpret_cast<const float4*>(x)[i], reinterpret_cast<const float4*>(y)[i]);
+        if (pre_out) reinterpret_cast<float4*>(pre_out)[i] = t;
+        reinterpret_cast<float4*>(out)[i] = make_float4(prelu_f(t.x, a), prelu_f(t.y, a), prelu_f(t.z, a), prelu_f(t.w, a));
+    }
+}
+
+extern "C" int paif_add_act(const float* x, const float* y, const float* slope, float* out, float* pre_out,
+                            long long n, void* stream) {
+    PAIF_REQUIRE(x && y && slope && out, "null pointer");
+    PAIF_REQUIRE(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+    if (n == 0) return 0;
+    const size_t n4 = (size_t)n / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    add_act_kernel<<<blocks, 256, 0, ST>>>(x, y, slope, out, pre_out, n4);
+    return check_launch("paif_add_act");
 }
 
 extern "C" int paif_add_maps(const float* a, const float* b, const float* c, float* out, long long n, void* stream) {

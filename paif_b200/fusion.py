@@ -292,7 +292,7 @@ class DilConv(_Primitive):
         out = torch.empty_like(x)
         rt.call("paif_dilconv_forward", x.data_ptr(), p["dw"].data_ptr(), p["pw_raw"].data_ptr(), p["s"].data_ptr(),
                 p["sh"].data_ptr(), _ptr(extras[0]) if extras else None, _ptr(extras[1]) if len(extras) > 1 else None,
-                out.data_ptr(), rt.C, self.k, self.d, rt.B, rt.H, rt.W)
+                out.data_ptr(), 1, rt.C, self.k, self.d, rt.B, rt.H, rt.W)
         return out, ()
 
     def bwd(self, rt, p, rec, g, extra_add, x=None):
@@ -406,6 +406,129 @@ class ResidualModule(_Primitive):
         return rt.conv([gt1], p["w0_d"], post_res=[g] + list(extra_add))[0]
 
 
+class SepConv(_Primitive):
+    """operations_m.py:509-526: two (ReLU -> depthwise k x k -> 1x1 -> BN) halves, no residual of its own.
+    OPS passes padding k//2 and drops the dilation (operations_m.py:15)."""
+    max_extras, max_extra_add = 2, 0
+
+    def __init__(self, C_in, C_out, kernel_size, stride, padding, affine=True):
+        super().__init__()
+        if stride != 1 or padding != kernel_size // 2 or kernel_size % 2 == 0 or kernel_size > 7:
+            raise NotImplementedError("SepConv: only odd k <= 7, stride 1, 'same' padding")
+        self.k = kernel_size
+        self.op = nn.Sequential(
+            nn.ReLU(inplace=False),
+            nn.Conv2d(C_in, C_in, kernel_size=kernel_size, stride=stride, padding=padding, groups=C_in, bias=False),
+            nn.Conv2d(C_in, C_in, kernel_size=1, padding=0, bias=False),
+            nn.BatchNorm2d(C_in, affine=affine),
+            nn.ReLU(inplace=False),
+            nn.Conv2d(C_in, C_in, kernel_size=kernel_size, stride=1, padding=padding, groups=C_in, bias=False),
+            nn.Conv2d(C_in, C_out, kernel_size=1, padding=0, bias=False),
+            nn.BatchNorm2d(C_out, affine=affine),
+        )
+
+    def pack(self, need_bwd):
+        halves = []
+        for dw_m, pw_m, bn_m in ((self.op[1], self.op[2], self.op[3]), (self.op[5], self.op[6], self.op[7])):
+            dw = dw_m.weight.detach()
+            C = dw.shape[0]
+            s, sh = _bn_fold(bn_m)
+            h = {"dw": dw.reshape(C, -1).contiguous().float(), "pw": _ConvW(pw_m.weight.detach(), 1, 1, 1),
+                 "pw_raw": pw_m.weight.detach().reshape(C, C).contiguous().float(), "s": s, "sh": sh}
+            if need_bwd:
+                h["dw_t"] = dw.flip(-1, -2).reshape(C, -1).contiguous().float()
+                h["pw_d"] = _dgrad_groups(pw_m.weight.detach(), 1, 1, scale=s)[0]
+            halves.append(h)
+        return {"halves": halves}
+
+    def _half(self, rt, h, x, extras):
+        extras = list(extras)
+        if self.k != 3:                                     # only 3x3 has a fused kernel instance
+            t = rt.dwconv(x, h["dw"], self.k, 1, relu_in=True)
+            return rt.conv([t], h["pw"], ch_scale=h["s"], ch_shift=h["sh"], post_res=extras)[0]
+        out = torch.empty_like(x)
+        rt.call("paif_dilconv_forward", x.data_ptr(), h["dw"].data_ptr(), h["pw_raw"].data_ptr(), h["s"].data_ptr(),
+                h["sh"].data_ptr(), _ptr(extras[0]) if extras else None, _ptr(extras[1]) if len(extras) > 1 else None,
+                out.data_ptr(), 0, rt.C, self.k, 1, rt.B, rt.H, rt.W)
+        return out
+
+    def fwd(self, rt, p, x, extras):
+        y1 = self._half(rt, p["halves"][0], x, [])
+        return self._half(rt, p["halves"][1], y1, extras), (y1,)
+
+    def bwd(self, rt, p, rec, g, extra_add, x=None):
+        (y1,) = rec
+        h1, h2 = p["halves"]
+        u = rt.conv([g], h2["pw_d"])[0]
+        gy1 = rt.dwconv(u, h2["dw_t"], self.k, 1, relu_in=False, mask_src=y1)
+        u = rt.conv([gy1], h1["pw_d"])[0]
+        return rt.dwconv(u, h1["dw_t"], self.k, 1, relu_in=False, mask_src=x)
+
+
+class spatial_attn_layer(nn.Module):
+    """operations_m.py:152-163 (1-arg ChannelPool + BasicConv(2, 1, k) + sigmoid); parameter container."""
+
+    def __init__(self, kernel_size=5):
+        super().__init__()
+        self.compress = nn.Module()
+        self.spatial = BasicConv(2, 1, kernel_size, relu=False)
+
+
+class Spatial_BasicBlock(_Primitive):
+    """operations_m.py:179-206 (with_norm=False).  The 1-arg spatial attention out * sigma(conv([max_c, mean_c]))
+    runs on the 2-map blend kernels with an all-zero second map and zero weights for its pooled channels."""
+    max_extras, max_extra_add = 0, 3
+
+    def __init__(self, inplanes, planes, kernel=3, dilation=1, stride=1, reduction=64, with_norm=False):
+        super().__init__()
+        _check_same_padding(kernel, 1, "SPAattention")
+        self.k = kernel
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.conv2 = BasicConv(inplanes, inplanes, kernel, relu=False)
+        self.se = spatial_attn_layer(kernel)
+        self.relu = nn.PReLU()
+
+    def pack(self, need_bwd):
+        w = self.se.spatial.conv.weight.detach()
+        w4 = torch.cat([w.reshape(2, -1), torch.zeros_like(w.reshape(2, -1))], 0).contiguous().float()
+        p = {"w1": _ConvW(self.conv1.weight.detach(), 1, 3, 1),
+             "w2": _ConvW(self.conv2.conv.weight.detach(), 1, self.k, 1),
+             "w4": w4, "a": self.relu.weight.detach()}
+        if need_bwd:
+            p["w1_d"] = _dgrad_groups(self.conv1.weight.detach(), 3, 1)[0]
+            p["w2_d"] = _dgrad_groups(self.conv2.conv.weight.detach(), self.k, 1)[0]
+        return p
+
+    def fwd(self, rt, p, x, extras):
+        a = p["a"]
+        x0, _, px0, _ = rt.conv([x], p["w1"], act2_slope=a)
+        o = rt.conv([px0], p["w2"])[0]
+        zero = torch.zeros_like(o)
+        pooled = rt.new_plane(4)
+        rt.call("paif_channel_pool", o.data_ptr(), zero.data_ptr(), pooled.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        os_, scale = rt.new_map(), rt.new_plane()
+        rt.call("paif_spa_blend_forward", pooled.data_ptr(), p["w4"].data_ptr(), self.k, o.data_ptr(), zero.data_ptr(),
+                os_.data_ptr(), scale.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        out = rt.new_map()
+        pre = rt.new_map() if rt.save else None
+        rt.call("paif_add_act", os_.data_ptr(), x0.data_ptr(), a.data_ptr(), out.data_ptr(), _ptr(pre), out.numel())
+        return out, (x0, o, scale, pre)
+
+    def bwd(self, rt, p, rec, g, extra_add):
+        x0, o, scale, pre = rec
+        a = p["a"]
+        gpre = rt.mask_scale(g, pre, a, 1.0)
+        zero = torch.zeros_like(o)
+        gplane = rt.new_plane()
+        rt.call("paif_spa_blend_backward_pre", gpre.data_ptr(), o.data_ptr(), zero.data_ptr(), scale.data_ptr(),
+                gplane.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        g_o, g_dummy = rt.new_map(), rt.new_map()
+        rt.call("paif_spa_blend_backward", gpre.data_ptr(), o.data_ptr(), zero.data_ptr(), scale.data_ptr(),
+                gplane.data_ptr(), p["w4"].data_ptr(), self.k, g_o.data_ptr(), g_dummy.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        gx0 = rt.conv([g_o], p["w2_d"], mask_src=x0, mask_slope=a, post_res=[gpre])[0]
+        return rt.conv([gx0], p["w1_d"], post_res=list(extra_add))[0]
+
+
 def _not_on_path(name):
     def make(*a, **k):
         raise NotImplementedError(
@@ -419,9 +542,9 @@ OPS = {
     'Denseblocks': lambda C, kernel, dialtion, affine: ResidualDenseBlock(C, kernel, dialtion),
     'Residualblocks': lambda C, kernel, dialtion, affine: ResidualModule(C, kernel, dialtion),
     'ECAattention': lambda C, kernel, dialtion, affine: ECABasicBlock(C, C, kernel, dialtion),
-    'SPAattention': _not_on_path('SPAattention'),
+    'SPAattention': lambda C, kernel, dialtion, affine: Spatial_BasicBlock(C, C, kernel, dialtion),
     'DilConv': lambda C, kernel, dialtion, affine: DilConv(C, C, kernel, dialtion),
-    'SepConv': _not_on_path('SepConv'),
+    'SepConv': lambda C, kernel, dialtion, affine: SepConv(C, C, kernel, 1, kernel // 2),
     'SelAttention': _not_on_path('SelAttention'),
 }
 
@@ -482,7 +605,7 @@ class Cell_Chain(nn.Module):
             inp, rec = recs[i]
             want = [g] if i == 0 else []
             fused, rest = want[:op.max_extra_add], want[op.max_extra_add:]
-            if isinstance(op, DilConv):
+            if isinstance(op, (DilConv, SepConv)):
                 gs = op.bwd(rt, packs[i], rec, gs, fused, x=inp)
             else:
                 gs = op.bwd(rt, packs[i], rec, gs, fused)
@@ -738,7 +861,7 @@ class Network_Fusion_Searched(nn.Module):
             fused, rest = want[:op.max_extra_add], want[op.max_extra_add:]
             if i == n - 1:
                 gs = op.bwd(rt, packs[i], rec, gs, fused, g_masked=gmasked)
-            elif isinstance(op, DilConv):
+            elif isinstance(op, (DilConv, SepConv)):
                 gs = op.bwd(rt, packs[i], rec, gs, fused, x=inp)
             else:
                 gs = op.bwd(rt, packs[i], rec, gs, fused)

@@ -10,7 +10,7 @@ import torch
 import paif_b200
 from oracle import fusion_oracle as fo
 from paif_b200 import _lib
-from paif_testutil import GOLDEN_CASES, load_golden, strided_vis
+from paif_testutil import GOLDEN_CASES, golden_genotype, load_golden, strided_vis
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -75,7 +75,7 @@ GRAD_GATES = [("direct", 5e-5, 1e-2, 0.999), ("tcgen05", 1e-3, 5e-2, 0.995)]
 @pytest.mark.parametrize("engine,out_tol,l2_tol,sign_tol", GRAD_GATES)
 def test_input_gradients_match_reference_golden(case, engine, out_tol, l2_tol, sign_tol):
     g = load_golden(case)
-    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+    net = paif_b200.Network_Fusion_Searched(32, None, golden_genotype(g))
     net.load_state_dict(g["state_dict"], strict=True)
     net = net.to(DEV).eval()
     net.conv_engine = engine

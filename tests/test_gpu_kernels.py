@@ -171,8 +171,11 @@ def test_dilconv_fused(k, dil, nres):
     rd = [to_c4(r).to(DEV) for r in res]
     _lib.call("paif_dilconv_forward", xc.data_ptr(), dwd.data_ptr(), pwd.data_ptr(), csd.data_ptr(), shd.data_ptr(),
               rd[0].data_ptr() if nres > 0 else None, rd[1].data_ptr() if nres > 1 else None, out.data_ptr(),
-              32, k, dil, B, H, W, stream())
+              1, 32, k, dil, B, H, W, stream())
     assert (from_c4(out).cpu() - ref).abs().max().item() < 5e-5
+    _lib.call("paif_dilconv_forward", xc.data_ptr(), dwd.data_ptr(), pwd.data_ptr(), csd.data_ptr(), shd.data_ptr(),
+              None, None, out.data_ptr(), 0, 32, k, dil, B, H, W, stream())       # add_x = 0: one half of SepConv
+    assert (from_c4(out).cpu() - (ref - x - sum(res))).abs().max().item() < 5e-5
 
 
 def test_confusion_matrix_kernel_is_exact():

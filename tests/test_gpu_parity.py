@@ -6,15 +6,15 @@ import torch
 
 import paif_b200
 from oracle import fusion_oracle as fo
-from paif_testutil import GOLDEN_CASES, load_golden, strided_vis
+from paif_testutil import GOLDEN_CASES, golden_genotype, load_golden, strided_vis
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 ENGINES = [("direct", 5e-5), ("tcgen05", 1e-3)]      # (conv engine, max-abs gate on the fused image)
 
 
-def build(sd, engine):
-    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+def build(sd, engine, genotype=paif_b200.fusion_at):
+    net = paif_b200.Network_Fusion_Searched(32, None, genotype)
     net.load_state_dict(sd, strict=True)
     net = net.to(DEV).eval()
     net.conv_engine = engine
@@ -25,7 +25,7 @@ def build(sd, engine):
 @pytest.mark.parametrize("engine,tol", ENGINES)
 def test_forward_matches_reference_golden(case, engine, tol):
     g = load_golden(case)
-    net = build(g["state_dict"], engine)
+    net = build(g["state_dict"], engine, golden_genotype(g))
     with torch.no_grad():
         out = net(g["ir"].to(DEV), strided_vis(g["vis"].to(DEV)))
     assert out.shape == g["out"].shape and out.is_contiguous()

