@@ -12,7 +12,7 @@ def from_c4(t):
     B, Q, H, W, _ = t.shape
     return t.permute(0, 1, 4, 2, 3).reshape(B, Q * 4, H, W)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-for (B, H, W), smooth in [((2, 40, 56), False), ((1, 200, 236), False), ((1, 200, 236), True), ((1, 480, 640), False), ((1, 480, 640), True), ((1, 768, 1024), True)]:
+for (B, H, W), smooth in [((2, 40, 56), False), ((1, 200, 236), False), ((1, 200, 236), True), ((1, 480, 640), False), ((1, 480, 640), True), ((1, 768, 1024), True), ((12, 480, 640), False)]:
     torch.manual_seed(1)
     z = torch.rand(B, 32, H, W)
     if smooth:
