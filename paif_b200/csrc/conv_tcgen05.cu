@@ -537,19 +537,39 @@ bool conv_tc_supported(const PaifConvDesc& d) {
     return tc_make_plan(d.nsrc, d.kh, d.dil, &p);
 }
 
+static int tc_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
 static int tc_rows_per_cta(const PaifConvDesc& d, const TcPlan& p) {
-    // multi-pass plans keep every output row of the chunk in TMEM (<= 16 slots)
-    if (p.npass > 1) return TC_SLOTS;
-    const int strips = cdiv(d.W, TC_TW);
-    int rch = 32;
-    // aim for >= 2 waves of 148 CTAs when the problem allows it
-    while (rch > 8 && (long long)strips * cdiv(d.H, rch) * d.B < 2 * 148) rch >>= 1;
-    return rch;
+    // One CTA per SM at a time.  Pick the chunk height that minimises  waves x (rows + halo + prologue):
+    // the prologue / drain of a CTA (barriers, TMEM, weight slab, pipeline fill) costs about as much as 8 rows,
+    // and a last wave with a handful of CTAs costs a full wave (e.g. one 480x640 frame: 29 chunks of 17 rows =
+    // 145 CTAs = one wave, where 8-row chunks would take three).  Multi-pass plans keep every output row of the
+    // chunk in TMEM (<= 16 slots).
+    const int strips = cdiv(d.W, TC_TW), sms = tc_num_sms();
+    const int max_rch = p.npass > 1 ? TC_SLOTS : 32;
+    const int halo = 2 * p.pad;
+    long long best_cost = -1;
+    int best = max_rch;
+    for (int rch = max_rch; rch >= 4; --rch) {
+        const long long ctas = (long long)strips * cdiv(d.H, rch) * d.B;
+        const long long waves = (ctas + sms - 1) / sms;
+        const long long cost = waves * (rch + halo + 8);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = rch; }
+    }
+    return best;
 }
 
 int conv_tc_tiles(int H, int W) {
-    // upper bound independent of the per-launch row chunk: the smallest chunk is 8 rows
-    return cdiv(W, TC_TW) * cdiv(H, 8);
+    // upper bound independent of the per-launch row chunk: the smallest chunk is 4 rows
+    return cdiv(W, TC_TW) * cdiv(H, 4);
 }
 
 int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
