@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", action="store_true", help="print the per-launch CUDA-event table of one step to stderr")
     ap.add_argument("--bwd-steps", type=int, default=3, help="timed forward+backward-to-input steps (0 = skip)")
+    ap.add_argument("--pgd-consumer-bf16", action="store_true", help="run the stock consumer under bf16 autocast")
+    ap.add_argument("--pgd-eager", action="store_true", help="PGD leg without CUDA-graph replay of the PGD iteration")
     ap.add_argument("--pgd-frames", type=int, default=4,
                     help="frames per GPU for the PGD-10 robust-eval leg (0 = skip); stock-PyTorch MiT-B3-shaped consumer")
     return ap.parse_args()
@@ -157,15 +159,17 @@ def run_pgd_leg(net, args, world, rank, dev, barrier):
     seg = SegFormerLite(9, 256).to(dev).eval()
     for p in seg.parameters():
         p.requires_grad_(False)
-    task = FusionSegTask(net, seg).to(dev).eval()
+    task = FusionSegTask(net, seg, consumer_autocast=torch.bfloat16 if args.pgd_consumer_bf16 else None).to(dev).eval()
     H, W = args.height, args.width
     n_total = args.pgd_frames * world
     frames = SyntheticFrames(n_total + world, H, W)
-    robust_eval(task, [frames[n_total + rank]], attack_iters=2)             # warm-up (allocator, cuDNN autotune)
+    graphed = not args.pgd_eager
+    robust_eval(task, [frames[n_total + rank]], attack_iters=2, use_cuda_graph=graphed)   # warm-up (allocator, autotune, capture)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    meter = robust_eval(task, SyntheticFrames(n_total, H, W), attack_iters=10, rank=rank, world_size=world)
+    meter = robust_eval(task, SyntheticFrames(n_total, H, W), attack_iters=10, rank=rank, world_size=world,
+                        use_cuda_graph=graphed)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -177,7 +181,9 @@ def run_pgd_leg(net, args, world, rank, dev, barrier):
     return {"metric": "PGD-10 robust-eval frames/s", "value": n_total / (ms * 1e-3), "unit": "frames/s",
             "frames": n_total, "frames_per_gpu": args.pgd_frames, "ms_per_frame_per_gpu": ms / max(args.pgd_frames, 1),
             "attack": "PGD-10 eps 8/255 alpha 2/255, l_seg loss, seeded start per global frame index",
-            "consumer": "stock-PyTorch SegFormerLite (MiT-B3 shape, random init, TF32 matmul, params frozen)",
+            "consumer": "stock-PyTorch SegFormerLite (MiT-B3 shape, random init, %s, params frozen)"
+                        % ("bf16 autocast" if args.pgd_consumer_bf16 else "fp32 with TF32 matmul"),
+            "cuda_graph": graphed,
             "confusion_sum": int(conf.sum()), "confusion_all_reduce": "int64 SUM over %d rank(s)" % world,
             "confusion_trace": int(conf.diag().sum())}
 

@@ -118,10 +118,13 @@ class FusionSegTask(nn.Module):
     """``Network_MM_CompModel``-style task model (core/model_fusion_auto.py:698-729) around any fusion
     module with ``forward(ir, vis) -> [B,1,H,W]`` and any consumer ``[B,3,H,W] -> logits``."""
 
-    def __init__(self, fusion, consumer):
+    def __init__(self, fusion, consumer, consumer_autocast=None):
         super().__init__()
         self.enhance_net = fusion
         self.denoise_net = consumer
+        #: optional torch dtype (e.g. torch.bfloat16): run the stock consumer under torch.autocast — one of the
+        #: mitigations SURVEY.md 7 allows for the consumer; the fusion path is unaffected (it takes and returns fp32)
+        self.consumer_autocast = consumer_autocast
         self.register_buffer("mean", torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1))
         self.register_buffer("std", torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1))
 
@@ -146,4 +149,8 @@ class FusionSegTask(nn.Module):
         lo, hi = rgb.min(), rgb.max()                      # spans the batch, as the reference does (:721-723)
         rgb = (rgb - lo) / (hi - lo).clamp_min(1e-12)
         x = (rgb * 255.0 - self.mean) / self.std
+        if self.consumer_autocast is not None:
+            with torch.autocast(device_type=x.device.type, dtype=self.consumer_autocast):
+                seg = self.denoise_net(x)
+            return fused, seg.float()
         return fused, self.denoise_net(x)

@@ -121,19 +121,79 @@ def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255.,
     return d_vis.detach(), d_ir.detach()
 
 
+class GraphedPGD:
+    """One PGD iteration of :func:`pgd_attack_both` (forward, loss, backward to the inputs, delta update)
+    captured once in a CUDA graph and replayed ``attack_iters`` times per frame.  Same arithmetic, same
+    kernels; what disappears is the host time of launching ~1500 small stock-PyTorch kernels per iteration of
+    the segmentation consumer (and ~75 of ours), which dominates a batch-1 PGD loop.  The fusion kernels take
+    every buffer from the caller and never synchronise, so they are capturable as they are."""
+
+    def __init__(self, model, vis_shape, ir_shape, label_shape, device, epsilon, alpha, ignore_index=255):
+        self.eps, self.alpha = float(epsilon), float(alpha)
+        self.x_vis = torch.zeros(vis_shape, device=device)
+        self.x_ir = torch.zeros(ir_shape, device=device)
+        self.label = torch.zeros(label_shape, device=device, dtype=torch.long)
+        self.d_vis = torch.zeros(vis_shape, device=device, requires_grad=True)
+        self.d_ir = torch.zeros(ir_shape, device=device, requires_grad=True)
+        self.model, self.ignore_index = model, ignore_index
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up: workspaces, packed weights, .grad buffers
+                self._iteration()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+
+    def _iteration(self):
+        with torch.enable_grad():
+            _, seg = self.model(self.x_ir + self.d_ir, self.x_vis + self.d_vis)
+            seg = F.interpolate(seg, size=self.label.shape[1:], mode="bilinear", align_corners=False)
+            loss = F.cross_entropy(seg, self.label, ignore_index=self.ignore_index)
+        loss.backward()
+        with torch.no_grad():
+            for d, x in ((self.d_vis, self.x_vis), (self.d_ir, self.x_ir)):
+                step = torch.clamp(d + self.alpha * torch.sign(d.grad), min=-self.eps, max=self.eps)
+                d.copy_(torch.max(torch.min(step, 1 - x), 0 - x))
+
+    def attack(self, x_vis, x_ir, label, attack_iters, seed, global_index):
+        dev = self.x_vis.device
+        with torch.no_grad():
+            self.x_vis.copy_(x_vis)
+            self.x_ir.copy_(x_ir)
+            self.label.copy_(label)
+            for d, x, off in ((self.d_vis, self.x_vis, 0), (self.d_ir, self.x_ir, 1)):
+                init = seeded_delta(x.shape, self.eps, seed, 2 * global_index + off, dev)
+                d.copy_(torch.max(torch.min(init, 1 - x), 0 - x))
+                d.grad.zero_()                      # a fresh delta per frame, as attack/attack.py:433-441
+        for _ in range(attack_iters):
+            self.graph.replay()
+        return self.d_vis.detach().clone(), self.d_ir.detach().clone()
+
+
 def robust_eval(model, frames, num_classes=9, attack_iters=10, epsilon=8 / 255., alpha=2 / 255., seed=0,
-                rank=0, world_size=1, group=None):
+                rank=0, world_size=1, group=None, use_cuda_graph=False):
     """Evaluate this rank's shard of ``frames`` (an indexable of ``(vis[3,H,W], ir[1,H,W], label[H,W])``
     host or device tensors) under PGD and return the all-reduced :class:`ConfusionMeter`.
     ``attack_iters=0`` gives the clean evaluation of test_original.py:98-258."""
     dev = next(model.parameters()).device
     meter = ConfusionMeter(num_classes, dev)
+    runner = getattr(model, "_paif_pgd_runner", None)      # the captured graph is reused across calls
     for gi in shard_range(len(frames), rank, world_size):
         vis, ir, label = frames[gi]
         vis, ir = vis.to(dev)[None].float(), ir.to(dev)[None].float()
         label = label.to(dev)[None].long()
         if attack_iters > 0:
-            d_vis, d_ir = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gi)
+            if use_cuda_graph:
+                if (runner is None or runner.x_vis.shape != vis.shape or runner.eps != float(epsilon)
+                        or runner.alpha != float(alpha)):
+                    runner = GraphedPGD(model, vis.shape, ir.shape, label.shape, dev, epsilon, alpha)
+                    object.__setattr__(model, "_paif_pgd_runner", runner)
+                d_vis, d_ir = runner.attack(vis, ir, label, attack_iters, seed, gi)
+            else:
+                d_vis, d_ir = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gi)
             vis, ir = vis + d_vis, ir + d_ir
         with torch.no_grad():
             _, seg = model(ir, vis)
