@@ -86,7 +86,9 @@ def load():
     if _lib is not None:
         return _lib
     path = LIB_PATH
-    if os.environ.get("PAIF_B200_PROFILE_LIB") == "1":
+    if os.environ.get("PAIF_B200_LIB"):
+        path = os.environ["PAIF_B200_LIB"]             # development only: an explicitly chosen build of the library
+    elif os.environ.get("PAIF_B200_PROFILE_LIB") == "1":
         # development only: same sources compiled with -DPAIF_TC_PROFILE (role timeline counters in the conv engine)
         path = _build.build(profile=True)
     elif not os.path.exists(LIB_PATH) or (_build.needs_build() and os.environ.get("PAIF_NO_REBUILD") != "1"):
