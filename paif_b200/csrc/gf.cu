@@ -138,6 +138,29 @@ __device__ __forceinline__ void ld_grp(const float* __restrict__ row, int x, int
         }
     }
 }
+// L2 eviction policies: rows that will be re-read nine iterations later are loaded "evict last", their final
+// read "evict first" (with ~1200 resident warps the 9-row history of three maps is ~65 MB; plain LRU loses it to
+// the streaming traffic and the re-read goes to DRAM: ncu showed 3.7 GB read for 1.9 GB of input)
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_drop() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ void ld_grp_hint(const float* __restrict__ row, int x, int W, float (&z)[4][GF_NCH], uint64_t pol) {
+    static_assert(GF_NCH == 4, "float4 per column");
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xx = x + k;
+        if (xx >= 0 && xx < W) {
+            asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                         : "=f"(z[k][0]), "=f"(z[k][1]), "=f"(z[k][2]), "=f"(z[k][3])
+                         : "l"(row + (size_t)xx * 4), "l"(pol));
+        } else {
+            z[k][0] = z[k][1] = z[k][2] = z[k][3] = 0.f;
+        }
+    }
+}
 __device__ __forceinline__ void st_grp(float* __restrict__ row, int xx, const float (&v)[GF_NCH]) {
     if (GF_NCH == 2) *reinterpret_cast<float2*>(row + (size_t)xx * 4) = make_float2(v[0], v[GF_NCH - 1]);
     else *reinterpret_cast<float4*>(row + (size_t)xx * 4) = make_float4(v[0], v[1 % GF_NCH], v[2 % GF_NCH], v[3 % GF_NCH]);
@@ -404,6 +427,7 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
         cr[k] = (xr + k >= 0 && xr + k < W) ? __frcp_rn(win_count(xr + k, W)) : 0.f;      // reciprocal widths, 0 = unused
         cs[k] = (it.live && xs + k < W && 4 * lane + k < GA_OUTW) ? __frcp_rn(win_count(xs + k, W)) : 0.f;
     }
+    const uint64_t pol_keep = l2_policy_keep(), pol_drop = l2_policy_drop();
     float Sz[4][GF_NCH], Sgz[4][GF_NCH], P1[4][GF_NCH], P2[4][GF_NCH], P3[4][GF_NCH], P4[4][GF_NCH];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -419,9 +443,10 @@ gf_adjoint_level2_kernel(const float* __restrict__ feat, const float* __restrict
             if (y < 0 || y >= H || (side == 1 && t < 9)) continue;
             const float sg = side == 0 ? 1.f : -1.f;
             float z[4][GF_NCH], l1[4][GF_NCH], l2[4][GF_NCH], g[4];
-            ld_grp(zp + (size_t)y * W * 4, xr, W, z);
-            ld_grp(l1p + (size_t)y * W * 4, xr, W, l1);
-            ld_grp(l2p + (size_t)y * W * 4, xr, W, l2);
+            const uint64_t pol = side == 0 ? pol_keep : pol_drop;
+            ld_grp_hint(zp + (size_t)y * W * 4, xr, W, z, pol);
+            ld_grp_hint(l1p + (size_t)y * W * 4, xr, W, l1, pol);
+            ld_grp_hint(l2p + (size_t)y * W * 4, xr, W, l2, pol);
             ld_cols4<VEC>(gp + (size_t)y * W, xr, W, g);
             const float rcy = __frcp_rn(win_count(y, H));
 #pragma unroll
@@ -523,6 +548,10 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
 #pragma unroll
         for (int c = 0; c < GF_NCH; ++c) Sc[k][c] = Sm[k][c] = 0.f;
     }
+    // (A shared-memory ring for the leaving row of gcov/N, gmean_z/N halves this kernel's DRAM reads — 4.0 -> 2.5 GB —
+    // but caps it at 6 warps per SM and was measured slower, 1.25 vs 0.98 ms; capping the occupancy at 8 warps per SM so
+    // that the history fits L2 was slower still, 1.33 ms.  L2 eviction hints are used instead: 0.96 ms.)
+    const uint64_t pol_keep = l2_policy_keep(), pol_drop = l2_policy_drop();
     const int nt = rows + 8;
     for (int t = 0; t < nt; ++t) {
         const int ys = y0 - 4 + t;                 // level-1 row entering the vertical window
@@ -531,9 +560,10 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
             const int y = side == 0 ? ys : ys - 9;
             if (y < 0 || y >= H || (side == 1 && t < 9)) continue;
             const float sg = side == 0 ? 1.f : -1.f;
+            const uint64_t pol = side == 0 ? pol_keep : pol_drop;
             float c4[4][GF_NCH], m4[4][GF_NCH], v[4], n[4];
-            ld_grp(gcp + (size_t)y * W * 4, xs, W, c4);
-            ld_grp(gmp + (size_t)y * W * 4, xs, W, m4);
+            ld_grp_hint(gcp + (size_t)y * W * 4, xs, W, c4, pol);
+            ld_grp_hint(gmp + (size_t)y * W * 4, xs, W, m4, pol);
             ld_cols4<VEC>(gvp + (size_t)y * W, xs, W, v);
             ld_cols4<VEC>(gnp + (size_t)y * W, xs, W, n);
 #pragma unroll
