@@ -48,4 +48,14 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute is per device: `done` holds one bit per device ordinal (a process normally drives one GPU,
+// but nothing here assumes it).  Returns true when the attribute still has to be set on the current device.
+inline bool attr_needed(unsigned long long& done, int* dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev >= 64 || !((done >> dev) & 1ull);
+}
+inline void attr_mark(unsigned long long& done, int dev) { if (dev < 64) done |= 1ull << dev; }
+
 }  // namespace paif

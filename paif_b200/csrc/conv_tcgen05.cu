@@ -590,15 +590,16 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     const int kk = d.kh == 1 ? 1 : d.kh, dd = d.kh == 1 ? 1 : d.dil;     // a 1x1 kernel has no dilation
 #define TC_CASE(K_, D_, Q_)                                                                                        \
     if (kk == K_ && dd == D_ && g.plan.KQ == Q_) {                                                                 \
-        static bool attr_done = false;                                                                              \
-        if (!attr_done) {                                                                                           \
+        static unsigned long long attr_done = 0;                                                                    \
+        int dev_;                                                                                                   \
+        if (attr_needed(attr_done, &dev_)) {                                                                        \
             cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, false>,                               \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024); \
             if (err == cudaSuccess)                                                                                 \
                 err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, true>,                                        \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);     \
             if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; } \
-            attr_done = true;                                                                                       \
+            attr_mark(attr_done, dev_);                                                                             \
         }                                                                                                           \
         if (d.chan_partials) conv_tc_kernel<K_, D_, Q_, true><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);   \
         else conv_tc_kernel<K_, D_, Q_, false><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);                  \

@@ -611,14 +611,15 @@ gf_adjoint_level1_kernel(const float* __restrict__ feat, const float* __restrict
 using namespace paif;
 
 static int gf_march_attr() {
-    static bool done = false;
-    if (done) return 0;
+    static unsigned long long done = 0;
+    int dev;
+    if (!attr_needed(done, &dev)) return 0;
     cudaError_t e = cudaFuncSetAttribute(gf_forward_march_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gf_forward_march_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gf_forward_march_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gf_forward_march_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM);
     if (e != cudaSuccess) { set_error("gf smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    done = true;
+    attr_mark(done, dev);
     return 0;
 }
 

@@ -740,13 +740,14 @@ extern "C" int paif_eca_bwd_pass2(const float* gw, const float* e, const float* 
 }
 
 static int out_smem_attr() {
-    static bool done = false;
-    if (done) return 0;
+    static unsigned long long done = 0;
+    int dev;
+    if (!attr_needed(done, &dev)) return 0;
     const int bytes = 9 * 25 * OUT_C * sizeof(float);
     cudaError_t e1 = cudaFuncSetAttribute(out_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("out kernel smem attr failed"); return (int)(e1 ? e1 : e2); }
-    done = true;
+    attr_mark(done, dev);
     return 0;
 }
 
