@@ -336,7 +336,6 @@ def run_ours(args):
     def e2e_steps():
         step_e2e()
     ms_e2e = timed_e2e(e2e_steps, args.steps)
-    clocks = sampler.summary() if sampler else None
 
     # attack inner step (BASELINE configs[4]): forward + backward-to-input on resident inputs
     fwd_bwd = None
@@ -383,6 +382,7 @@ def run_ours(args):
             sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
         sys.stderr.write("sum of launches %.3f ms (step %.3f ms)\n" % (tot, ms / args.steps))
     pgd = run_pgd_leg(net, args, world, rank, dev, barrier) if args.pgd_frames > 0 else None
+    clocks = sampler.summary() if sampler else None          # sampled across every timed GPU leg above
 
     # dominant kernel: the dense-conv engine (all conv launches of the timed steps).  After the wide-N MMA
     # rewrite every conv shape of the genotype except the 7x7 is HBM-bound, so the engine is judged against

@@ -126,10 +126,12 @@ int paif_dwconv_forward(const float* x, const float* w, int relu_in,
  *   out = ch_scale * pw1x1(dw_kxk_dil(relu(x))) + ch_shift + (add_x ? x : 0) + r1 + r2
  * (add_x = 0 gives one half of SepConv, operations_m.py:509-526; r1, r2 optional residual maps:
  * the Cell_Chain residual, core/model_fusion_auto.py:445, and Cell_Decom's "+ feature", :516).
- * dw: [C][k*k] depthwise taps, pw: [C_out][C_in] pointwise weights. */
+ * dw: [C][k*k] depthwise taps, pw: [C_out][C_in] pointwise weights.
+ * engine: PAIF_ENGINE_TCGEN05 runs the 1x1 on tcgen05 (TF32 operands, fp32 accumulate; measured slower than the
+ * all-fp32 FFMA kernel that AUTO and DIRECT use). */
 int paif_dilconv_forward(const float* x, const float* dw, const float* pw, const float* ch_scale,
                          const float* ch_shift, const float* r1, const float* r2, float* out,
-                         int add_x, int C, int k, int dil, int B, int H, int W, void* stream);
+                         int add_x, int engine, int C, int k, int dil, int B, int H, int W, void* stream);
 
 /* 2-arg ChannelPool — core/model_fusion_auto.py:1352-1355.
  * pooled[B][H][W][4] = (max_c ir, mean_c ir, max_c vis, mean_c vis). */

@@ -531,6 +531,135 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused DilConv on the tensor pipe (operations_m.py:494-506):
+//   out = ch_scale * pw1x1(dw3x3_dil(relu(x))) + ch_shift + (add_x ? x : 0) + r1 + r2
+// One CTA = 128 pixels of a row strip x DC_ROWS rows, 4 warps, thread = pixel.  Per row: every thread computes
+// the 32 depthwise results of its pixel (FFMA, 9 taps) and writes them to shared memory in the quad-plane
+// layout, which IS the UMMA A operand; one thread issues 4 tcgen05.mma (M128 N32 K8, TF32) against the
+// resident BN-scaled 1x1 weights; the same threads read their pixel's 32 outputs back from TMEM, add the
+// shift and the residual maps and store.  Rows are serial inside a CTA; ~5 CTAs per SM overlap each other.
+// ---------------------------------------------------------------------------------------------
+constexpr int DC_ROWS = 16;
+
+template <int DIL>
+__global__ void __launch_bounds__(128)
+dilconv_tc_kernel(const float* __restrict__ xin, const float* __restrict__ dw, const float* __restrict__ pw,
+                  const float* __restrict__ ch_scale, const float* __restrict__ ch_shift,
+                  const float* __restrict__ r1, const float* __restrict__ r2, float* __restrict__ out,
+                  int add_x, int H, int W) {
+    __shared__ __align__(128) float4 s_a[8 * 128];          // A operand: [quad plane][pixel][4 ch]
+    __shared__ __align__(128) float s_b[4 * 2 * 32 * 4];    // B operand: [k8][16-B chunk][cout][4 cin], TF32, BN-scaled
+    __shared__ __align__(16) float s_dw[9 * 32];            // [tap][channel]
+    __shared__ __align__(16) float s_sh[32];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x = blockIdx.x * 128 + tid, r0 = blockIdx.y * DC_ROWS, b = blockIdx.z;
+    const int nrows = min(DC_ROWS, H - r0);
+    for (int i = tid; i < 1024; i += 128) {
+        const int co = i >> 5, ci = i & 31;
+        const float w = pw[co * 32 + ci] * (ch_scale ? ch_scale[co] : 1.f);
+        const uint32_t bits = (__float_as_uint(w) + 0x1000u) & 0xffffe000u;        // round to nearest TF32
+        s_b[(((ci >> 3) * 2 + ((ci >> 2) & 1)) * 32 + co) * 4 + (ci & 3)] = __uint_as_float(bits);
+    }
+    for (int i = tid; i < 288; i += 128) { const int t = i >> 5, c = i & 31; s_dw[i] = dw[c * 9 + t]; }
+    if (tid < 32) s_sh[tid] = ch_shift ? ch_shift[tid] : 0.f;
+    if (tid == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(32u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const size_t plane = (size_t)H * W;
+    const float4* xp = reinterpret_cast<const float4*>(xin) + (size_t)b * 8 * plane;
+    const bool xin_ok = x < W;
+    const uint64_t a_desc0 = make_desc(smem_u32(s_a), 128 * 16, 128);
+    const uint64_t b_desc0 = make_desc(smem_u32(s_b), 512, 128);
+    uint32_t phase = 0;
+    for (int ro = 0; ro < nrows; ++ro) {
+        const int y = r0 + ro;
+        // ---- depthwise 3x3 (dilation DIL) of relu(x): this thread's pixel, all 32 channels -> A operand
+        int toff[9];
+        float tval[9];
+#pragma unroll
+        for (int ty = 0; ty < 3; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < 3; ++tx) {
+                const int yy = y + (ty - 1) * DIL, xx = x + (tx - 1) * DIL;
+                const bool ok = xin_ok && yy >= 0 && yy < H && xx >= 0 && xx < W;
+                toff[ty * 3 + tx] = ok ? yy * W + xx : 0;
+                tval[ty * 3 + tx] = ok ? 1.f : 0.f;
+            }
+#pragma unroll 2
+        for (int q = 0; q < 8; ++q) {
+            float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 v = __ldg(xp + (size_t)q * plane + toff[t]);
+                const float4 ww = *reinterpret_cast<const float4*>(&s_dw[t * 32 + q * 4]);
+                const float m = tval[t];
+                t4.x = fmaf(fmaxf(v.x, 0.f) * m, ww.x, t4.x); t4.y = fmaf(fmaxf(v.y, 0.f) * m, ww.y, t4.y);
+                t4.z = fmaf(fmaxf(v.z, 0.f) * m, ww.z, t4.z); t4.w = fmaf(fmaxf(v.w, 0.f) * m, ww.w, t4.w);
+            }
+            s_a[q * 128 + tid] = t4;
+        }
+        // residual maps of this pixel: in flight while the MMAs run
+        const size_t base = (size_t)b * 8 * plane + (size_t)y * W + x;
+        float4 rs[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            rs[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xin_ok) {
+                const size_t off = base + q * plane;
+                if (add_x) rs[q] = __ldg(reinterpret_cast<const float4*>(xin) + off);
+                if (r1) rs[q] = f4_add(rs[q], ld_stream(reinterpret_cast<const float4*>(r1) + off));
+                if (r2) rs[q] = f4_add(rs[q], ld_stream(reinterpret_cast<const float4*>(r2) + off));
+            }
+        }
+        fence_proxy_async();                       // generic-proxy writes of s_a -> visible to the tensor core
+        tc_fence_before();
+        __syncthreads();                           // also: everyone finished reading TMEM of the previous row
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8)
+                tc_mma_tf32(tmem, a_desc0 + (uint64_t)(k8 * 2 * 128), b_desc0 + (uint64_t)(k8 * 64), tc_idesc(32u), k8 ? 1u : 0u);
+            tc_commit(smem_u32(&bar));
+        }
+        mbar_wait(smem_u32(&bar), phase);
+        phase ^= 1u;
+        tc_fence_after();
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+        tc_fence_before();
+        if (xin_ok) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(out)[base + q * plane] =
+                    make_float4(v[q * 4 + 0] + s_sh[q * 4 + 0] + rs[q].x, v[q * 4 + 1] + s_sh[q * 4 + 1] + rs[q].y,
+                                v[q * 4 + 2] + s_sh[q * 4 + 2] + rs[q].z, v[q * 4 + 3] + s_sh[q * 4 + 3] + rs[q].w);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(32u) : "memory");
+}
+
+int dilconv_tc_launch(const float* x, const float* dw, const float* pw, const float* ch_scale, const float* ch_shift,
+                      const float* r1, const float* r2, float* out, int add_x, int dil, int B, int H, int W,
+                      cudaStream_t stream) {
+    dim3 grid(cdiv(W, 128), cdiv(H, DC_ROWS), B);
+    if (dil == 1) dilconv_tc_kernel<1><<<grid, 128, 0, stream>>>(x, dw, pw, ch_scale, ch_shift, r1, r2, out, add_x, H, W);
+    else if (dil == 2) dilconv_tc_kernel<2><<<grid, 128, 0, stream>>>(x, dw, pw, ch_scale, ch_shift, r1, r2, out, add_x, H, W);
+    else { set_error("dilconv_tc: dilation %d not instantiated", dil); return PAIF_ENOTSUP; }
+    return check_launch("paif_dilconv_forward(tcgen05)");
+}
+
 bool conv_tc_supported(const PaifConvDesc& d) {
     if (d.cout != 32 || d.cin_per_src != 32 || d.kh != d.kw) return false;
     TcPlan p;

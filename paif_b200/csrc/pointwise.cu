@@ -645,14 +645,24 @@ extern "C" int paif_dwconv_forward(const float* x, const float* w, int relu_in, 
     return check_launch("paif_dwconv_forward");
 }
 
+namespace paif {
+int dilconv_tc_launch(const float* x, const float* dw, const float* pw, const float* ch_scale, const float* ch_shift,
+                      const float* r1, const float* r2, float* out, int add_x, int dil, int B, int H, int W,
+                      cudaStream_t stream);
+}
+
 extern "C" int paif_dilconv_forward(const float* x, const float* dw, const float* pw, const float* ch_scale,
                                     const float* ch_shift, const float* r1, const float* r2, float* out,
-                                    int add_x, int C, int k, int dil, int B, int H, int W, void* stream) {
+                                    int add_x, int engine, int C, int k, int dil, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(x && dw && pw && out, "null pointer");
     PAIF_REQUIRE(C == 32, "C must be 32");
     PAIF_REQUIRE(k >= 1 && k <= 7 && (k & 1) && dil >= 1, "bad kernel size / dilation");
     PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
     PAIF_REQUIRE((long long)H * W < (1ll << 31), "image too large");
+    // the tensor-core variant is correct but measured slower (1.00 vs 0.90 ms at 16x480x640: the depthwise taps'
+    // L1 traffic dominates either way), so AUTO keeps the FFMA kernel; PAIF_ENGINE_TCGEN05 selects it explicitly
+    if (engine == PAIF_ENGINE_TCGEN05 && k == 3 && (dil == 1 || dil == 2))
+        return dilconv_tc_launch(x, dw, pw, ch_scale, ch_shift, r1, r2, out, add_x, dil, B, H, W, ST);
 #define DC_CASE(K_, D_)                                                                                              \
     if (k == K_ && dil == D_) {                                                                                      \
         dilconv_fused_kernel<K_, D_><<<pix_grid(W, H, B), dim3(32, 8), 0, ST>>>(x, dw, pw, ch_scale, ch_shift, r1, r2, out, add_x, H, W); \

@@ -292,7 +292,7 @@ class DilConv(_Primitive):
         out = torch.empty_like(x)
         rt.call("paif_dilconv_forward", x.data_ptr(), p["dw"].data_ptr(), p["pw_raw"].data_ptr(), p["s"].data_ptr(),
                 p["sh"].data_ptr(), _ptr(extras[0]) if extras else None, _ptr(extras[1]) if len(extras) > 1 else None,
-                out.data_ptr(), 1, rt.C, self.k, self.d, rt.B, rt.H, rt.W)
+                out.data_ptr(), 1, _lib.ENGINE_AUTO, rt.C, self.k, self.d, rt.B, rt.H, rt.W)
         return out, ()
 
     def bwd(self, rt, p, rec, g, extra_add, x=None):
@@ -449,7 +449,7 @@ class SepConv(_Primitive):
         out = torch.empty_like(x)
         rt.call("paif_dilconv_forward", x.data_ptr(), h["dw"].data_ptr(), h["pw_raw"].data_ptr(), h["s"].data_ptr(),
                 h["sh"].data_ptr(), _ptr(extras[0]) if extras else None, _ptr(extras[1]) if len(extras) > 1 else None,
-                out.data_ptr(), 0, rt.C, self.k, 1, rt.B, rt.H, rt.W)
+                out.data_ptr(), 0, _lib.ENGINE_AUTO, rt.C, self.k, 1, rt.B, rt.H, rt.W)
         return out
 
     def fwd(self, rt, p, x, extras):

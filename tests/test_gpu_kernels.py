@@ -171,11 +171,16 @@ def test_dilconv_fused(k, dil, nres):
     rd = [to_c4(r).to(DEV) for r in res]
     _lib.call("paif_dilconv_forward", xc.data_ptr(), dwd.data_ptr(), pwd.data_ptr(), csd.data_ptr(), shd.data_ptr(),
               rd[0].data_ptr() if nres > 0 else None, rd[1].data_ptr() if nres > 1 else None, out.data_ptr(),
-              1, 32, k, dil, B, H, W, stream())
+              1, _lib.ENGINE_DIRECT, 32, k, dil, B, H, W, stream())
     assert (from_c4(out).cpu() - ref).abs().max().item() < 5e-5
     _lib.call("paif_dilconv_forward", xc.data_ptr(), dwd.data_ptr(), pwd.data_ptr(), csd.data_ptr(), shd.data_ptr(),
-              None, None, out.data_ptr(), 0, 32, k, dil, B, H, W, stream())       # add_x = 0: one half of SepConv
+              None, None, out.data_ptr(), 0, _lib.ENGINE_DIRECT, 32, k, dil, B, H, W, stream())   # add_x = 0: half a SepConv
     assert (from_c4(out).cpu() - (ref - x - sum(res))).abs().max().item() < 5e-5
+    # tensor-core engine: TF32 operands in the 1x1
+    _lib.call("paif_dilconv_forward", xc.data_ptr(), dwd.data_ptr(), pwd.data_ptr(), csd.data_ptr(), shd.data_ptr(),
+              rd[0].data_ptr() if nres > 0 else None, rd[1].data_ptr() if nres > 1 else None, out.data_ptr(),
+              1, _lib.ENGINE_TCGEN05, 32, k, dil, B, H, W, stream())
+    assert (from_c4(out).cpu() - ref).abs().max().item() < 2.0 ** -9 * t.abs().max().item() * 4
 
 
 def test_confusion_matrix_kernel_is_exact():
