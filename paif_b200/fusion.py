@@ -107,8 +107,11 @@ class _Runtime:
         shape = (self.B, self.H, self.W) if ch is None else (self.B, self.H, self.W, ch)
         return torch.empty(shape, device=self.device, dtype=torch.float32)
 
+    #: kernels behind one ABI call when it is not exactly one
+    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_gf_decomp_backward": 3}
+
     def call(self, name, *args):
-        self.launches += 1
+        self.launches += self._KERNELS_PER_CALL.get(name, 1)
         if self.profile is None:
             _lib.call(name, *args, self.stream)
             return
