@@ -144,6 +144,9 @@ int paif_channel_pool(const float* ir_f, const float* vis_f, float* pooled,
 int paif_spa_blend_forward(const float* pooled, const float* w, int k,
                            const float* ir_f, const float* vis_f,
                            float* agg, float* scale_out, int C, int B, int H, int W, void* stream);
+/* paif_channel_pool + paif_spa_blend_forward in one kernel (the pooled planes stay in shared memory). */
+int paif_spa_fused_forward(const float* w, int k, const float* ir_f, const float* vis_f, float* agg,
+                           float* scale_out, int C, int B, int H, int W, void* stream);
 
 /* eca_layer (operations_m.py:340-367): reduce per-tile channel sums (fixed order), mean,
  * Conv1d(1,1,k,pad (k-1)/2, bias=False) across channels, sigmoid.  e: [B][C]. */

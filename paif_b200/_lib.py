@@ -53,6 +53,7 @@ SIGNATURES = {
     "paif_add_act": [_f, _f, _f, _f, _f, _ll, _f],
     "paif_channel_pool": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_spa_blend_forward": [_f, _f, _i, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_spa_fused_forward": [_f, _i, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_eca_scale": [_f, _i, _f, _i, _f, _i, _i, _i, _i, _f],
     "paif_eca_apply": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_out_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],

@@ -674,6 +674,91 @@ extern "C" int paif_dilconv_forward(const float* x, const float* dw, const float
     return PAIF_ENOTSUP;
 }
 
+// ------------------------------------------------------------------------------------------
+// ChannelPool + spatial attention + blend in ONE kernel (core/model_fusion_auto.py:1352-1368, :631-632):
+// a 32 x 16 output tile computes the 4 pooled planes on its halo'd region into shared memory, then the k x k
+// conv, the sigmoid and the blend.  Both maps are read once from HBM (halo re-reads come from L2) and the
+// pooled plane never leaves the SM: 3 map transfers instead of 5.
+// ------------------------------------------------------------------------------------------
+constexpr int SF_TX = 32, SF_TY = 16;
+
+template <int QC>                                                // QC = C / 4 when known at compile time (8), else 0
+__global__ void __launch_bounds__(256)
+spa_fused_kernel(const float* __restrict__ w, int k, const float* __restrict__ a, const float* __restrict__ v,
+                 float* __restrict__ agg, float* __restrict__ scale_out, int Qrt, int H, int W) {
+    const int Q = QC ? QC : Qrt;
+    __shared__ float4 sw[49];
+    __shared__ float4 sp[(SF_TY + 6) * (SF_TX + 6)];            // pooled (max_a, mean_a, max_v, mean_v), halo <= 3
+    const int tid = threadIdx.x;
+    const int taps = k * k, pad = (k - 1) / 2;
+    if (tid < taps) sw[tid] = make_float4(w[tid], w[taps + tid], w[2 * taps + tid], w[3 * taps + tid]);
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * SF_TX, y0 = blockIdx.y * SF_TY;
+    const int RX = SF_TX + 2 * pad, RY = SF_TY + 2 * pad;
+    const size_t plane = (size_t)H * W;
+    const float4* ap = reinterpret_cast<const float4*>(a) + (size_t)b * Q * plane;
+    const float4* vp = reinterpret_cast<const float4*>(v) + (size_t)b * Q * plane;
+    const float inv = 1.f / (float)(Q * 4);
+    for (int i = tid; i < RX * RY; i += 256) {
+        const int ry = i / RX, rx = i - ry * RX;
+        const int yy = y0 - pad + ry, xx = x0 - pad + rx;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);             // zero padding of the conv input
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const size_t pix = (size_t)yy * W + xx;
+            float amax = -INFINITY, asum = 0.f, vmax = -INFINITY, vsum = 0.f;
+#pragma unroll
+            for (int q = 0; q < (QC ? QC : 1); ++q) {
+                for (int qq = q; qq < Q; qq += (QC ? Q : 1)) {          // compile-time trip count when QC != 0
+                    const float4 t = __ldg(ap + qq * plane + pix);
+                    amax = fmaxf(fmaxf(amax, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+                    asum += (t.x + t.y) + (t.z + t.w);
+                    const float4 u = __ldg(vp + qq * plane + pix);
+                    vmax = fmaxf(fmaxf(vmax, fmaxf(u.x, u.y)), fmaxf(u.z, u.w));
+                    vsum += (u.x + u.y) + (u.z + u.w);
+                }
+            }
+            p = make_float4(amax, asum * inv, vmax, vsum * inv);
+        }
+        sp[i] = p;
+    }
+    __syncthreads();
+    for (int o = tid; o < SF_TX * SF_TY; o += 256) {
+        const int oy = o / SF_TX, ox = o - oy * SF_TX;
+        const int y = y0 + oy, x = x0 + ox;
+        if (y >= H || x >= W) continue;
+        float acc = 0.f;
+        for (int ty = 0; ty < k; ++ty)
+            for (int tx = 0; tx < k; ++tx) {
+                const float4 p = sp[(oy + ty) * RX + ox + tx];
+                const float4 ww = sw[ty * k + tx];
+                acc = fmaf(p.x, ww.x, acc); acc = fmaf(p.y, ww.y, acc);
+                acc = fmaf(p.z, ww.z, acc); acc = fmaf(p.w, ww.w, acc);
+            }
+        const float s = sigmoid_f(acc), s1 = 1.f - s;
+        const size_t pix = (size_t)y * W + x;
+        if (scale_out) scale_out[(size_t)b * plane + pix] = s;
+        float4* op = reinterpret_cast<float4*>(agg) + (size_t)b * Q * plane + pix;
+#pragma unroll
+        for (int q = 0; q < (QC ? QC : 1); ++q) {
+            for (int qq = q; qq < Q; qq += (QC ? Q : 1)) {
+                const float4 t = __ldg(ap + qq * plane + pix), u = __ldg(vp + qq * plane + pix);
+                op[qq * plane] = make_float4(s * t.x + s1 * u.x, s * t.y + s1 * u.y, s * t.z + s1 * u.z, s * t.w + s1 * u.w);
+            }
+        }
+    }
+}
+
+extern "C" int paif_spa_fused_forward(const float* w, int k, const float* ir_f, const float* vis_f, float* agg,
+                                      float* scale_out, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(w && ir_f && vis_f && agg, "null pointer");
+    PAIF_REQUIRE(C % 4 == 0 && k >= 1 && k <= 7 && (k & 1), "unsupported C / kernel size");
+    PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
+    const dim3 grid(cdiv(W, SF_TX), cdiv(H, SF_TY), B);
+    if (C == 32) spa_fused_kernel<8><<<grid, 256, 0, ST>>>(w, k, ir_f, vis_f, agg, scale_out, 8, H, W);
+    else spa_fused_kernel<0><<<grid, 256, 0, ST>>>(w, k, ir_f, vis_f, agg, scale_out, C / 4, H, W);
+    return check_launch("paif_spa_fused_forward");
+}
+
 extern "C" int paif_channel_pool(const float* ir_f, const float* vis_f, float* pooled,
                                  int C, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(ir_f && vis_f && pooled, "null pointer");

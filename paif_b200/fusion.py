@@ -779,12 +779,10 @@ class Network_Fusion_Searched(nn.Module):
             branch_out.append(o)
             branch_recs.append(recs)
         a_f, v_f = branch_out
-        pooled = rt.new_plane(4)
-        rt.call("paif_channel_pool", a_f.data_ptr(), v_f.data_ptr(), pooled.data_ptr(), C, B, H, W)
         agg = rt.new_map()
         scale = rt.new_plane() if save else None
-        rt.call("paif_spa_blend_forward", pooled.data_ptr(), p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(),
-                v_f.data_ptr(), agg.data_ptr(), _ptr(scale), C, B, H, W)
+        rt.call("paif_spa_fused_forward", p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(), v_f.data_ptr(),
+                agg.data_ptr(), _ptr(scale), C, B, H, W)
         f2, recs3 = self.chain.fwd(rt, p["chain"], agg, [])
         out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
         pre_out = rt.new_plane() if save else None

@@ -140,6 +140,12 @@ def test_dwconv_pool_spa_out():
               agg.data_ptr(), sc.data_ptr(), 32, B, H, W, stream())
     assert (sc.cpu() - s[:, 0]).abs().max().item() < 1e-5
     assert (from_c4(agg).cpu() - ref).abs().max().item() < 1e-5
+    # the same in one kernel (pooled planes stay in shared memory)
+    agg2, sc2 = torch.empty_like(xc), torch.empty(B, H, W, device=DEV)
+    _lib.call("paif_spa_fused_forward", wspa.data_ptr(), 5, xc.data_ptr(), yc.data_ptr(), agg2.data_ptr(), sc2.data_ptr(),
+              32, B, H, W, stream())
+    assert (sc2.cpu() - s[:, 0]).abs().max().item() < 1e-5
+    assert (from_c4(agg2).cpu() - ref).abs().max().item() < 1e-5
     # merged stem_out + PReLU + tanh
     w1, w2, a = torch.randn(16, 32, 3, 3) * 0.1, torch.randn(1, 16, 3, 3) * 0.1, torch.tensor([0.25])
     ref = torch.tanh(F.prelu(F.conv2d(F.conv2d(x, w1, None, 1, 1), w2, None, 1, 1), a))
