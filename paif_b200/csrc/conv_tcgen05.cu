@@ -89,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
-        if (++spins > (1ull << 22)) {          // a lost arrival would otherwise hang the GPU box
+        if (++spins > (1ull << 26)) {          // (seconds) a lost arrival would otherwise hang the GPU box
             printf("paif conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n",
                    blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
             __trap();
