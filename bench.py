@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--engine", default="auto", choices=["auto", "direct", "tcgen05"])
-    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", action="store_true", help="print the per-launch CUDA-event table of one step to stderr")
     ap.add_argument("--bwd-steps", type=int, default=3, help="timed forward+backward-to-input steps (0 = skip)")
@@ -107,6 +107,24 @@ def synth_inputs(B, H, W, seed=1):
     import torch
     g = torch.Generator().manual_seed(seed)
     return torch.rand(B, 1, H, W, generator=g), torch.rand(B, 3, H, W, generator=g)
+
+
+def cpu_port_fwd_bwd_pairs_per_s(steps, H, W):
+    """Forward + backward-to-input of the CPU oracle port (autograd), one pair per step."""
+    import torch
+    import paif_b200
+    from oracle import fusion_oracle as fo
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, sd = synth_state()
+    ir, vis = synth_inputs(1, H, W)
+    gout = torch.rand(1, 1, H, W) - 0.5
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        fo.fusion_input_grads(sd, paif_b200.fusion_at, ir, vis, gout)
+        if i >= 1:
+            times.append(time.perf_counter() - t0)
+    return steps / sum(times)
 
 
 def cpu_port_pairs_per_s(steps, H, W, warmup=1):
@@ -442,9 +460,13 @@ def run_ours(args):
         line["pgd10"] = pgd
     if not args.no_cpu_baseline and world == 1:
         v, cores, times = cpu_port_pairs_per_s(args.cpu_baseline_steps, H, W)
+        st = sorted(times)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                                 "sample": "%d timed forward passes of 1 pair %dx%d on the host (oracle port, torch CPU ops) after 1 warm-up"
-                                          % (args.cpu_baseline_steps, H, W)}
+                                          % (args.cpu_baseline_steps, H, W),
+                                "min_ms": 1e3 * st[0], "median_ms": 1e3 * st[len(st) // 2],
+                                "fwd_bwd_pairs_per_s": cpu_port_fwd_bwd_pairs_per_s(2, H, W),
+                                "fwd_bwd_sample": "2 timed forward+backward-to-input passes of 1 pair (oracle autograd) after 1 warm-up"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
