@@ -23,3 +23,16 @@ net.conv_engine = "auto"
 with torch.no_grad():
     out = net(ir.cuda(), vis.cuda())
 print("77x203 engine=auto max-abs err %.3e" % (out.cpu() - ref).abs().max().item())
+# smallest legal size and a wide, short one; forward and backward
+for shp in ((1, 10, 10), (3, 11, 300), (1, 130, 10)):
+    B, H, W = shp
+    ir, vis = torch.rand(B, 1, H, W, generator=g), torch.rand(B, 3, H, W, generator=g)
+    cot = torch.randn(B, 1, H, W, generator=g)
+    ir_r, vis_r = ir.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+    ref = fo.fusion_forward(sd, paif_b200.fusion_at, ir_r, vis_r)
+    gi, gv = torch.autograd.grad(ref, [ir_r, vis_r], cot)
+    a, v = ir.cuda().requires_grad_(True), vis.cuda().requires_grad_(True)
+    out = net(a, v)
+    out.backward(cot.cuda())
+    rl = ((a.grad.cpu() - gi).norm() / gi.norm()).item()
+    print("%s engine=auto fwd err %.3e  grad rel-L2 %.3e" % (shp, (out.detach().cpu() - ref.detach()).abs().max().item(), rl))

@@ -56,3 +56,22 @@ def test_batch_position_invariance_and_determinism():
         one = net(ir[1:2], vis[1:2])
     assert torch.equal(both, again)
     assert torch.equal(both[1:2], one)
+
+
+@pytest.mark.parametrize("shape", [(1, 10, 10), (3, 11, 300), (1, 130, 10), (2, 77, 203)])
+def test_edge_sizes_forward_and_input_gradients(shape):
+    """Smallest legal image (the guided filter needs H, W > 9), wide-and-short, tall-and-narrow, and a size that is
+    a multiple of nothing: forward within 1e-3 and input gradients within the TF32 gates of the CPU oracle."""
+    B, H, W = shape
+    g = load_golden("seed1_random_1x48x72")
+    net = build(g["state_dict"], "auto")
+    gen = torch.Generator().manual_seed(31)
+    ir, vis = torch.rand(B, 1, H, W, generator=gen), torch.rand(B, 3, H, W, generator=gen)
+    cot = torch.randn(B, 1, H, W, generator=gen)
+    ref, g_ir, g_vis = fo.fusion_input_grads(g["state_dict"], paif_b200.fusion_at, ir, vis, cot)
+    a, v = ir.to(DEV).requires_grad_(True), vis.to(DEV).requires_grad_(True)
+    out = net(a, v)
+    assert (out.detach().cpu() - ref).abs().max().item() <= 1e-3
+    out.backward(cot.to(DEV))
+    for got, want in ((a.grad.cpu(), g_ir), (v.grad.cpu()[:, 0:1], g_vis[:, 0:1])):
+        assert ((got - want).norm() / want.norm()).item() < 5e-2
