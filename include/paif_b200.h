@@ -37,6 +37,14 @@ extern "C" {
 #define PAIF_ENOTSUP  (-2)   /* configuration not supported by this build     */
 
 /* conv engines */
+/* Map storage of a convolution launch (PaifConvDesc.storage).  fp32 maps use the C4 layout [B][C/4][H][W][4];
+ * bf16 maps the C8 layout [B][C/8][H][W][8] (16-byte pixel vectors either way).  The bf16 modes exist on the
+ * tcgen05 engine only and are forward-only in the module (north_star's 1e-2 tier; fp32 accumulation in TMEM,
+ * per-channel affine / PReLU / residual adds in fp32 registers, one rounding at the store). */
+#define PAIF_STORAGE_F32       0   /* fp32 sources (TF32 operands), fp32 residuals and outputs            */
+#define PAIF_STORAGE_BF16      1   /* bf16 sources (bf16 operands, kind::f16), bf16 residuals and outputs */
+#define PAIF_STORAGE_F32_BF16  2   /* fp32 sources (TF32 operands), bf16 residuals and outputs (1x1 only) */
+
 #define PAIF_ENGINE_AUTO    0
 #define PAIF_ENGINE_DIRECT  1   /* fp32 FFMA direct convolution (exact-fp32 path)          */
 #define PAIF_ENGINE_TCGEN05 2   /* tcgen05 TF32 implicit GEMM, fp32 accumulate in TMEM      */
@@ -63,6 +71,29 @@ int paif_gf_decomp_forward(const float* feat, const float* residue, const float*
                            float* lf1, float* lf2, int C, int B, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * bf16 storage mode (forward only; north_star's 1e-2 tier).  Stems, guide and guided-filter
+ * statistics stay fp32; from the 1x1 that follows the decomposition (PaifConvDesc.storage = PAIF_STORAGE_F32_BF16)
+ * every 32-channel map is a bf16 C8 map [B][4][H][W][8].  All arithmetic is fp32 in registers / TMEM; values are
+ * rounded to bf16 (nearest even) once, at the store.
+ *   paif_stem_forward_bf16copy  = paif_stem_forward that also writes feat as a bf16 C8 map (the branch residual)
+ *   paif_dilconv_forward_bf16   = paif_dilconv_forward   (FFMA kernel) on bf16 maps
+ *   paif_spa_fused_forward_bf16 = paif_spa_fused_forward on bf16 maps (no saved attention plane)
+ *   paif_eca_apply_bf16         = paif_eca_apply         on bf16 maps (e stays fp32 [B][C])
+ *   paif_out_forward_bf16       = paif_out_forward       on a bf16 feature map (fp32 image out)        */
+int paif_stem_forward_bf16copy(const float* img, long long stride_b, long long stride_y, long long stride_x,
+                               const float* w, const float* slope, float* feat, float* residue, void* feat_bf16,
+                               int B, int H, int W, void* stream);
+int paif_dilconv_forward_bf16(const void* x, const float* dw, const float* pw, const float* ch_scale,
+                              const float* ch_shift, const void* r1, const void* r2, void* out, int add_x,
+                              int C, int k, int dil, int B, int H, int W, void* stream);
+int paif_spa_fused_forward_bf16(const float* w, int k, const void* ir_f, const void* vis_f, void* agg,
+                                int C, int B, int H, int W, void* stream);
+int paif_eca_apply_bf16(const void* o, const void* x, const float* e, const float* slope, const void* post_res,
+                        void* out, int C, int B, int H, int W, void* stream);
+int paif_out_forward_bf16(const void* feat, const float* wm, const float* slope, float* out,
+                          int C, int B, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Generic dense "same"-padded stride-1 convolution over 1..3 concatenated C4 source maps
  * (torch.cat along channels is a K-loop over sources) with a fused epilogue.  Replaces
  * BasicConv / conv3x3 / nn.Conv2d call sites of ResidualDenseBlock (operations_m.py:435-449),
@@ -87,22 +118,23 @@ typedef struct PaifConvDesc {
     int cout;                 /* 32 (16 also accepted by the direct engine)        */
     int kh, kw, dil;          /* odd kernel, padding = dil*(k-1)/2                 */
     int engine;               /* PAIF_ENGINE_*                                     */
-    const float* src[3];
+    const void*  src[3];      /* maps: fp32 C4 or bf16 C8, see `storage`           */
     const float* weight;      /* direct engine: [nsrc][kh*kw][cin_per_src][cout]   */
     const void*  weight_mma;  /* tcgen05 engine: UMMA-packed image, see DESIGN.md  */
     const float* ch_scale;
     const float* ch_shift;
-    const float* pre_res[2];
-    float*       out_pre;
-    const float* mask_src;
+    const void*  pre_res[2];
+    void*        out_pre;
+    const void*  mask_src;
     const float* mask_slope;
     const float* slope;
     float        post_scale;
-    const float* post_res[3];
-    float*       out;
-    float*       out_act2;
+    const void*  post_res[3];
+    void*        out;
+    void*        out_act2;
     const float* slope2;
     float*       chan_partials;
+    int          storage;     /* PAIF_STORAGE_* (0 = fp32 everywhere, the default)  */
 } PaifConvDesc;
 
 int paif_conv_forward(const PaifConvDesc* desc, void* stream);
@@ -111,6 +143,9 @@ int paif_conv_forward(const PaifConvDesc* desc, void* stream);
  * (dx, 8 input channels) form one UMMA B tile of N = 32*k rows; KQ = paif_conv_tc_kq()
  * (8, or 4 when the weights must be split into passes; 0 = shape not supported by the engine). */
 int paif_conv_tc_kq(int nsrc, int k, int dil);
+/* the same for PAIF_STORAGE_BF16: bf16 values, [K-group of KQ 8-channel planes][dx][KQ/2][2][dy][32 cout][8 cin];
+ * KQ = 4 (a whole 32-channel source), 0 = not supported. */
+int paif_conv_tc_kq_bf16(int nsrc, int k, int dil);
 /* number of per-image tiles the chosen engine writes into chan_partials ([B][tiles][cout]) */
 int paif_conv_num_tiles(int H, int W, int engine);
 

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpaif_b200.so")
 
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
+STORAGE_F32, STORAGE_BF16, STORAGE_F32_BF16 = 0, 1, 2      # PaifConvDesc.storage
 
 _f = C.c_void_p      # device pointers travel as integers
 _i = C.c_int
@@ -35,6 +36,7 @@ class ConvDesc(C.Structure):
         ("post_res", _f * 3),
         ("out", _f), ("out_act2", _f), ("slope2", _f),
         ("chan_partials", _f),
+        ("storage", _i),
     ]
 
 
@@ -43,11 +45,17 @@ SIGNATURES = {
     "paif_abi_version": [],
     "paif_last_error_string": [],
     "paif_stem_forward": [_f, _ll, _ll, _ll, _f, _f, _f, _f, _i, _i, _i, _f],
+    "paif_stem_forward_bf16copy": [_f, _ll, _ll, _ll, _f, _f, _f, _f, _f, _i, _i, _i, _f],
+    "paif_dilconv_forward_bf16": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f],
+    "paif_spa_fused_forward_bf16": [_f, _i, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_eca_apply_bf16": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_out_forward_bf16": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_gf_guide_stats": [_f, _f, _i, _i, _i, _f],
     "paif_gf_decomp_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_conv_forward": [C.POINTER(ConvDesc), _f],
     "paif_conv_num_tiles": [_i, _i, _i],
     "paif_conv_tc_kq": [_i, _i, _i],
+    "paif_conv_tc_kq_bf16": [_i, _i, _i],
     "paif_dwconv_forward": [_f, _f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "paif_dilconv_forward": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f],
     "paif_add_act": [_f, _f, _f, _f, _f, _ll, _f],

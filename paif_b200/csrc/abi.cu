@@ -18,7 +18,7 @@ int conv_direct_tiles(int H, int W);
 int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream);
 int conv_tc_tiles(int H, int W);
 bool conv_tc_supported(const PaifConvDesc& d);
-int conv_tc_kq(int nsrc, int k, int dil);
+int conv_tc_kq(int nsrc, int k, int dil, bool bf16);
 
 }  // namespace paif
 
@@ -37,10 +37,12 @@ extern "C" int paif_conv_forward(const PaifConvDesc* d, void* stream) {
     PAIF_REQUIRE(d->out != nullptr, "null output");
     for (int i = 0; i < d->nsrc; ++i) PAIF_REQUIRE(d->src[i] != nullptr, "null source");
     PAIF_REQUIRE(d->B <= 65535, "B exceeds grid.z");
+    PAIF_REQUIRE(d->storage >= PAIF_STORAGE_F32 && d->storage <= PAIF_STORAGE_F32_BF16, "unknown storage mode");
     int engine = d->engine;
     if (engine == PAIF_ENGINE_AUTO) engine = (d->weight_mma && conv_tc_supported(*d)) ? PAIF_ENGINE_TCGEN05 : PAIF_ENGINE_DIRECT;
     if (engine == PAIF_ENGINE_DIRECT) {
         PAIF_REQUIRE(d->weight != nullptr, "direct engine needs weight");
+        PAIF_REQUIRE(d->storage == PAIF_STORAGE_F32, "the direct engine has no bf16 storage mode");
         return conv_direct_launch(*d, (cudaStream_t)stream);
     }
     if (engine == PAIF_ENGINE_TCGEN05) {
@@ -59,5 +61,10 @@ extern "C" int paif_conv_num_tiles(int H, int W, int engine) {
 
 extern "C" int paif_conv_tc_kq(int nsrc, int k, int dil) {
     if (nsrc < 1 || nsrc > 3 || k < 1 || k > 7 || !(k & 1) || dil < 1 || dil > 2) return 0;
-    return conv_tc_kq(nsrc, k, dil);
+    return conv_tc_kq(nsrc, k, dil, false);
+}
+
+extern "C" int paif_conv_tc_kq_bf16(int nsrc, int k, int dil) {
+    if (nsrc < 1 || nsrc > 3 || k < 1 || k > 7 || !(k & 1) || dil < 1 || dil > 2) return 0;
+    return conv_tc_kq(nsrc, k, dil, true);
 }

@@ -44,6 +44,54 @@ __device__ __forceinline__ float4 f4_scale(float4 a, float s) {
     return make_float4(a.x * s, a.y * s, a.z * s, a.w * s);
 }
 
+// C8 bf16 maps ([B][C/8][H][W][8], the bf16 storage mode): a pixel's 8 channels are one 16-byte vector
+__device__ __forceinline__ void bf8_unpack(uint4 u, float4& lo, float4& hi) {
+    lo = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    hi = make_float4(__uint_as_float(u.z << 16), __uint_as_float(u.z & 0xffff0000u),
+                     __uint_as_float(u.w << 16), __uint_as_float(u.w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t bf2_pack(float e0, float e1) {      // round to nearest even; e0 at the lower address
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+__device__ __forceinline__ uint4 bf8_pack(float4 lo, float4 hi) {
+    return make_uint4(bf2_pack(lo.x, lo.y), bf2_pack(lo.z, lo.w), bf2_pack(hi.x, hi.y), bf2_pack(hi.z, hi.w));
+}
+
+// all 32 channels of one pixel of image b: `img` points at the image's first plane (fp32 C4: 8 planes of float4,
+// bf16 C8: 4 planes of uint4), `plane` = H*W, `pix` = y*W + x
+template <bool BF>
+__device__ __forceinline__ void ld_px32(const void* img, size_t plane, size_t pix, float4 (&v)[8]) {
+    if constexpr (BF) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) bf8_unpack(__ldg(static_cast<const uint4*>(img) + p * plane + pix), v[2 * p], v[2 * p + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(static_cast<const float4*>(img) + q * plane + pix);
+    }
+}
+template <bool BF>
+__device__ __forceinline__ void st_px32(void* img, size_t plane, size_t pix, const float4 (&v)[8]) {
+    if constexpr (BF) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) static_cast<uint4*>(img)[p * plane + pix] = bf8_pack(v[2 * p], v[2 * p + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) static_cast<float4*>(img)[q * plane + pix] = v[q];
+    }
+}
+// start of image b of a 32-channel map
+template <bool BF>
+__device__ __forceinline__ const void* img32(const void* map, int b, size_t plane) {
+    return static_cast<const uint4*>(map) + (size_t)b * (BF ? 4 : 8) * plane;      // both layouts: 16-byte pixel vectors
+}
+template <bool BF>
+__device__ __forceinline__ void* img32(void* map, int b, size_t plane) {
+    return static_cast<uint4*>(map) + (size_t)b * (BF ? 4 : 8) * plane;
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }

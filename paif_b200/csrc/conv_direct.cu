@@ -124,7 +124,7 @@ int conv_direct_launch(const PaifConvDesc& d, cudaStream_t stream) {
     ConvGeom g;
     g.B = d.B; g.H = d.H; g.W = d.W; g.nsrc = d.nsrc; g.cin = d.cin_per_src;
     g.kh = d.kh; g.kw = d.kw; g.dil = d.dil;
-    for (int i = 0; i < 3; ++i) g.src[i] = d.src[i];
+    for (int i = 0; i < 3; ++i) g.src[i] = static_cast<const float*>(d.src[i]);
     g.weight = d.weight;
     EpiParams e = make_epi(d);
     const int ph = d.dil * (d.kh - 1) / 2, pw = d.dil * (d.kw - 1) / 2;

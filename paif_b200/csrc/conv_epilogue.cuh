@@ -25,11 +25,14 @@ struct EpiParams {
 inline EpiParams make_epi(const PaifConvDesc& d) {
     EpiParams e;
     e.ch_scale = d.ch_scale; e.ch_shift = d.ch_shift;
-    e.pre_res[0] = d.pre_res[0]; e.pre_res[1] = d.pre_res[1];
-    e.out_pre = d.out_pre; e.mask_src = d.mask_src; e.mask_slope = d.mask_slope;
+    // (map pointers: fp32 C4, or bf16 C8 when the launch's storage mode says so — the tcgen05 engine reinterprets)
+    auto cf = [](const void* p) { return static_cast<const float*>(p); };
+    e.pre_res[0] = cf(d.pre_res[0]); e.pre_res[1] = cf(d.pre_res[1]);
+    e.out_pre = static_cast<float*>(d.out_pre); e.mask_src = cf(d.mask_src); e.mask_slope = d.mask_slope;
     e.slope = d.slope; e.post_scale = d.post_scale;
-    e.post_res[0] = d.post_res[0]; e.post_res[1] = d.post_res[1]; e.post_res[2] = d.post_res[2];
-    e.out = d.out; e.out_act2 = d.out_act2; e.slope2 = d.slope2; e.chan_partials = d.chan_partials;
+    e.post_res[0] = cf(d.post_res[0]); e.post_res[1] = cf(d.post_res[1]); e.post_res[2] = cf(d.post_res[2]);
+    e.out = static_cast<float*>(d.out); e.out_act2 = static_cast<float*>(d.out_act2); e.slope2 = d.slope2;
+    e.chan_partials = d.chan_partials;
     e.H = d.H; e.W = d.W;
     return e;
 }

@@ -49,18 +49,21 @@ struct TcPlan {
     int smem_bytes;
 };
 
-static bool tc_make_plan(int nsrc, int k, int dil, TcPlan* p) {
+// in_bf16: the sources are C8 bf16 maps (4 planes of 16-byte pixel vectors per 32-channel source instead of 8);
+// the byte geometry of rows, stages and B tiles is the same, there are just half as many planes / K steps.
+static bool tc_make_plan(int nsrc, int k, int dil, bool in_bf16, TcPlan* p) {
     if (dil != 1 && dil != 2) return false;              // slot arithmetic uses shifts (log2 dil)
     if ((TC_SLOTS >> (dil >> 1)) < k) return false;      // the k rows fed by one input row need distinct slots
     const int taps = k * k;
     p->pad = dil * (k - 1) / 2;
     p->RW = TC_TW + 2 * p->pad;
-    const int full = nsrc * taps * 4096;                 // all weights (32 cin x 32 cout x 4 B per tap and source)
-    if (full <= TC_WSLAB_MAX) { p->KQ = 8; p->npass = 1; p->gpp = nsrc; }
-    else if (taps * 4096 <= TC_WSLAB_MAX) { p->KQ = 8; p->npass = nsrc; p->gpp = 1; }
-    else if (taps * 2048 <= TC_WSLAB_MAX) { p->KQ = 4; p->npass = nsrc * 2; p->gpp = 1; }
+    const int pps = in_bf16 ? 4 : 8;                     // planes per source
+    const int src_bytes = taps * pps * 512;              // weights of one source (32 cin x 32 cout per tap)
+    if (nsrc * src_bytes <= TC_WSLAB_MAX) { p->KQ = pps; p->npass = 1; p->gpp = nsrc; }
+    else if (src_bytes <= TC_WSLAB_MAX) { p->KQ = pps; p->npass = nsrc; p->gpp = 1; }
+    else if (!in_bf16 && src_bytes / 2 <= TC_WSLAB_MAX) { p->KQ = pps / 2; p->npass = nsrc * 2; p->gpp = 1; }
     else return false;
-    p->gps = 8 / p->KQ;
+    p->gps = pps / p->KQ;
     p->slab_bytes = p->gpp * taps * p->KQ * 512;
     p->unit_bytes = p->KQ * p->RW * 16;
     int stages = (TC_SMEM_BUDGET - p->slab_bytes - 1024) / p->unit_bytes;
@@ -122,14 +125,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// bf16 operands (M128, K16), fp32 accumulation
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-// kind::tf32, D=f32, A/B = TF32 K-major, N=32, M=128 (cute::UMMA::InstrDescriptor bit layout)
-__device__ __forceinline__ uint32_t tc_idesc(uint32_t n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// D = f32, A/B K-major, M = 128 (cute::UMMA::InstrDescriptor bit layout); operand format 2 = TF32 (kind::tf32),
+// 1 = bf16 (kind::f16)
+__device__ __forceinline__ uint32_t tc_idesc(uint32_t n, uint32_t fmt = 2u) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 // TMEM slot of chunk-relative output row ro: rows of one dilation residue class descend through consecutive slots,
 // so the k rows fed by one input row (ro, ro - dil, ...) occupy ascending consecutive slots.
@@ -158,6 +169,18 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
+}
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// one bit per bf16 lane of a packed pair: value > 0
+__device__ __forceinline__ uint32_t bf2_pos_bits(uint32_t u) {
+    const int lo = (int)(u << 16), hi = (int)(u & 0xffff0000u);
+    return (lo > 0 ? 1u : 0u) | (hi > 0 ? 2u : 0u);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -191,8 +214,9 @@ __device__ unsigned long long tc_prof[16];
 
 struct TcGeom {
     int B, H, W, nsrc, k, dil, RCH, tiles_alloc;
-    const float* src[3];
-    const float* wmma;     // [K-group of KQ quads][dx][KQ/2 (k8)][2 (16-B chunk)][dy][32 cout][4 cin], TF32-rounded
+    const void* src[3];
+    const void* wmma;      // [K-group of KQ planes][dx][KQ/2 (K step)][2 (16-B chunk)][dy][32 cout][16 B of cin]:
+                           // 4 TF32-rounded fp32 or 8 bf16 input channels per 16 bytes
     TcPlan plan;
 };
 
@@ -211,9 +235,13 @@ static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservati
 // K, DIL, KQ are compile-time so that the MMA issue loop unrolls into straight-line code whose descriptors differ
 // from a per-row base by immediates: the single issuing thread then sustains the tensor pipe's own rate
 // (max(32 + N/4, N/2) cycles per MMA, scripts/mma_ubench2.cu) instead of ~150 cycles of address arithmetic per MMA.
-template <int K, int DIL, int KQ, bool PARTIALS>
+// ST = storage mode: 0 = fp32 C4 maps in and out (TF32 MMAs); 1 = bf16 C8 maps in and out (bf16 MMAs);
+// 2 = fp32 C4 sources (TF32 MMAs), bf16 C8 residuals / outputs (the layer that enters the bf16 part of the net).
+template <int K, int DIL, int KQ, bool PARTIALS, int ST>
 __global__ void __launch_bounds__(TC_NT, 1)
 conv_tc_kernel(TcGeom g, EpiParams e) {
+    constexpr bool IN_BF = ST == 1, OUT_BF = ST != 0;
+    constexpr int PPS_IN = IN_BF ? 4 : 8;                      // 16-byte planes per 32-channel source map
     extern __shared__ __align__(128) unsigned char smem[];
     const TcPlan& P = g.plan;
     unsigned char* s_w = smem;                                 // weight slab
@@ -283,6 +311,42 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         float4 pn[8], qn[8];
         uint32_t mbits = 0;
         auto fetch_next = [&](int ro) {
+            if constexpr (OUT_BF) {
+                const size_t base = (size_t)b * 4 * plane + (size_t)(r0 + ro) * g.W + x;     // 16-byte units, plane 0
+                auto add_map = [&](const float* m, float4 (&acc)[8]) {
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) {
+                        float4 lo, hi;
+                        bf8_unpack(ld_stream_u4(reinterpret_cast<const uint4*>(m) + base + pl * plane), lo, hi);
+                        acc[2 * pl] = f4_add(acc[2 * pl], lo);
+                        acc[2 * pl + 1] = f4_add(acc[2 * pl + 1], hi);
+                    }
+                };
+                if (any_post) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk)
+                        if (e.post_res[kk]) add_map(e.post_res[kk], pn);
+                }
+                if (any_pre) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) qn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)
+                        if (e.pre_res[kk]) add_map(e.pre_res[kk], qn);
+                }
+                if (e.mask_src) {
+                    uint32_t mb = 0;
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) {
+                        const uint4 m = ld_stream_u4(reinterpret_cast<const uint4*>(e.mask_src) + base + pl * plane);
+                        mb |= (bf2_pos_bits(m.x) | bf2_pos_bits(m.y) << 2 | bf2_pos_bits(m.z) << 4 | bf2_pos_bits(m.w) << 6) << (8 * pl);
+                    }
+                    mbits = mb;
+                }
+                return;
+            }
             const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;
             if (any_post) {
 #pragma unroll
@@ -337,7 +401,53 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32);
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->acc_empty[slot]));
-            if (xin) {
+            if (OUT_BF && xin) {
+                const size_t base = (size_t)b * 4 * plane + (size_t)(r0 + ro) * g.W + x;     // 16-byte units, plane 0
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) {
+                    float tp[8];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int q = 2 * pl + h;
+                        const float4 sc = *reinterpret_cast<const float4*>(&bars->ch_scale[q * 4]);
+                        const float4 sh = *reinterpret_cast<const float4*>(&bars->ch_shift[q * 4]);
+                        float t[4] = {fmaf(v[q * 4 + 0], sc.x, sh.x), fmaf(v[q * 4 + 1], sc.y, sh.y),
+                                      fmaf(v[q * 4 + 2], sc.z, sh.z), fmaf(v[q * 4 + 3], sc.w, sh.w)};
+                        t[0] += qn[q].x; t[1] += qn[q].y; t[2] += qn[q].z; t[3] += qn[q].w;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) tp[h * 4 + j] = t[j];
+                        if (e.mask_src) {
+                            const uint32_t mq = mbits >> (4 * q);
+                            t[0] *= (mq & 1u) ? 1.f : ma; t[1] *= (mq & 2u) ? 1.f : ma;
+                            t[2] *= (mq & 4u) ? 1.f : ma; t[3] *= (mq & 8u) ? 1.f : ma;
+                        } else if (e.slope) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) t[j] = prelu_f(t[j], a);
+                        }
+                        v[q * 4 + 0] = fmaf(t[0], e.post_scale, pn[q].x); v[q * 4 + 1] = fmaf(t[1], e.post_scale, pn[q].y);
+                        v[q * 4 + 2] = fmaf(t[2], e.post_scale, pn[q].z); v[q * 4 + 3] = fmaf(t[3], e.post_scale, pn[q].w);
+                    }
+                    if (e.out_pre)
+                        reinterpret_cast<uint4*>(e.out_pre)[base + pl * plane] =
+                            bf8_pack(make_float4(tp[0], tp[1], tp[2], tp[3]), make_float4(tp[4], tp[5], tp[6], tp[7]));
+                }
+                if (any_fetch && ro + 2 < nrows) fetch_next(ro + 2);      // in flight during the next row's MMAs
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl) {
+                    const float* w8 = &v[pl * 8];
+                    reinterpret_cast<uint4*>(e.out)[base + pl * plane] =
+                        bf8_pack(make_float4(w8[0], w8[1], w8[2], w8[3]), make_float4(w8[4], w8[5], w8[6], w8[7]));
+                    if (e.out_act2)
+                        reinterpret_cast<uint4*>(e.out_act2)[base + pl * plane] =
+                            bf8_pack(make_float4(prelu_f(w8[0], a2), prelu_f(w8[1], a2), prelu_f(w8[2], a2), prelu_f(w8[3], a2)),
+                                     make_float4(prelu_f(w8[4], a2), prelu_f(w8[5], a2), prelu_f(w8[6], a2), prelu_f(w8[7], a2)));
+                }
+                if (PARTIALS) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) csum[c] += v[c];
+                }
+            }
+            if (!OUT_BF && xin) {
                 const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;     // float4 units, quad 0
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -444,23 +554,29 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                                 const uint32_t a_lo = (ring_base + stage * UNIT) >> 4;
                                 const uint32_t w_lo = ((w_base + (uint32_t)gl * (k * nk8 * k * 1024)) >> 4) + dy_lo * 32;
                                 const uint32_t d0 = tmem_base + s0 * 32;
-                                const uint32_t id0 = tc_idesc(32u * n1);
+                                const uint32_t id0 = tc_idesc(32u * n1, IN_BF ? 1u : 2u);
 #pragma unroll
                                 for (int dx = 0; dx < k; ++dx)
 #pragma unroll
-                                    for (int k8 = 0; k8 < nk8; ++k8)
-                                        tc_mma_tf32(d0, a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW),
-                                                    b_desc0 | (uint64_t)(w_lo + (dx * nk8 + k8) * k * 64), id0, 1u);
+                                    for (int k8 = 0; k8 < nk8; ++k8) {
+                                        const uint64_t ad = a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW);
+                                        const uint64_t bd = b_desc0 | (uint64_t)(w_lo + (dx * nk8 + k8) * k * 64);
+                                        if constexpr (IN_BF) tc_mma_bf16(d0, ad, bd, id0, 1u);
+                                        else tc_mma_tf32(d0, ad, bd, id0, 1u);
+                                    }
                                 if (n1 < ndy) {                           // the slot ring wrapped: remaining taps start at s1
                                     const uint32_t d1 = tmem_base + s1 * 32;
-                                    const uint32_t id1 = tc_idesc(32u * (ndy - n1));
+                                    const uint32_t id1 = tc_idesc(32u * (ndy - n1), IN_BF ? 1u : 2u);
                                     const uint32_t w_l1 = w_lo + n1 * 32;
 #pragma unroll
                                     for (int dx = 0; dx < k; ++dx)
 #pragma unroll
-                                        for (int k8 = 0; k8 < nk8; ++k8)
-                                            tc_mma_tf32(d1, a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW),
-                                                        b_desc0 | (uint64_t)(w_l1 + (dx * nk8 + k8) * k * 64), id1, 1u);
+                                        for (int k8 = 0; k8 < nk8; ++k8) {
+                                            const uint64_t ad = a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW);
+                                            const uint64_t bd = b_desc0 | (uint64_t)(w_l1 + (dx * nk8 + k8) * k * 64);
+                                            if constexpr (IN_BF) tc_mma_bf16(d1, ad, bd, id1, 1u);
+                                            else tc_mma_tf32(d1, ad, bd, id1, 1u);
+                                        }
                                 }
                             }
                             __syncwarp();
@@ -505,8 +621,9 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                     for (int gl = 0; gl < P.gpp; ++gl) {
                         TC_WAIT(mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u));
                         const int gk = pass * P.gpp + gl;        // global K-group
-                        const int s = KQ == 8 ? gk : gk >> 1, qoff = KQ == 8 ? 0 : (gk & 1) * KQ;   // 8 / KQ groups per source
-                        const float4* sp = reinterpret_cast<const float4*>(g.src[s]) + ((size_t)b * 8 + qoff) * plane
+                        constexpr int GPS = PPS_IN / KQ;         // K-groups per source (1 or 2)
+                        const int s = GPS == 1 ? gk : gk >> 1, qoff = GPS == 1 ? 0 : (gk & 1) * KQ;
+                        const float4* sp = reinterpret_cast<const float4*>(g.src[s]) + ((size_t)b * PPS_IN + qoff) * plane
                                            + (size_t)y * g.W + xs;
                         const uint32_t dst = smem_u32(s_ring) + stage * UNIT + poff * 16;
                         const uint32_t bar = smem_u32(&bars->full[stage]);
@@ -662,8 +779,9 @@ int dilconv_tc_launch(const float* x, const float* dw, const float* pw, const fl
 
 bool conv_tc_supported(const PaifConvDesc& d) {
     if (d.cout != 32 || d.cin_per_src != 32 || d.kh != d.kw) return false;
+    if (d.storage < 0 || d.storage > 2) return false;
     TcPlan p;
-    return tc_make_plan(d.nsrc, d.kh, d.dil, &p);
+    return tc_make_plan(d.nsrc, d.kh, d.dil, d.storage == PAIF_STORAGE_BF16, &p);
 }
 
 static int tc_num_sms() {
@@ -703,12 +821,12 @@ int conv_tc_tiles(int H, int W) {
 
 int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     TcGeom g;
-    if (!tc_make_plan(d.nsrc, d.kh, d.dil, &g.plan)) { set_error("conv_tc: no plan"); return PAIF_ENOTSUP; }
+    if (!tc_make_plan(d.nsrc, d.kh, d.dil, d.storage == PAIF_STORAGE_BF16, &g.plan)) { set_error("conv_tc: no plan"); return PAIF_ENOTSUP; }
     g.B = d.B; g.H = d.H; g.W = d.W; g.nsrc = d.nsrc; g.k = d.kh; g.dil = d.dil;
     g.RCH = tc_rows_per_cta(d, g.plan);
     g.tiles_alloc = conv_tc_tiles(d.H, d.W);
     for (int i = 0; i < 3; ++i) g.src[i] = d.src[i];
-    g.wmma = reinterpret_cast<const float*>(d.weight_mma);
+    g.wmma = d.weight_mma;
     EpiParams e = make_epi(d);
     dim3 grid(cdiv(d.W, TC_TW), cdiv(d.H, g.RCH), d.B);
     if (d.chan_partials) {
@@ -717,26 +835,32 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
         if (err != cudaSuccess) { set_error("conv_tc memset: %s", cudaGetErrorString(err)); return (int)err; }
     }
     const int kk = d.kh == 1 ? 1 : d.kh, dd = d.kh == 1 ? 1 : d.dil;     // a 1x1 kernel has no dilation
-#define TC_CASE(K_, D_, Q_)                                                                                        \
-    if (kk == K_ && dd == D_ && g.plan.KQ == Q_) {                                                                 \
+#define TC_CASE(K_, D_, Q_, S_)                                                                                    \
+    if (kk == K_ && dd == D_ && g.plan.KQ == Q_ && d.storage == S_) {                                              \
         static unsigned long long attr_done = 0;                                                                    \
         int dev_;                                                                                                   \
         if (attr_needed(attr_done, &dev_)) {                                                                        \
-            cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, false>,                               \
+            cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, false, S_>,                           \
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024); \
             if (err == cudaSuccess)                                                                                 \
-                err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, true>,                                        \
+                err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, true, S_>,                                    \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);     \
             if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; } \
             attr_mark(attr_done, dev_);                                                                             \
         }                                                                                                           \
-        if (d.chan_partials) conv_tc_kernel<K_, D_, Q_, true><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);   \
-        else conv_tc_kernel<K_, D_, Q_, false><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);                  \
+        if (d.chan_partials) conv_tc_kernel<K_, D_, Q_, true, S_><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e); \
+        else conv_tc_kernel<K_, D_, Q_, false, S_><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);              \
         return check_launch("paif_conv_forward(tcgen05)");                                                          \
     }
-    TC_CASE(1, 1, 8) TC_CASE(3, 1, 8) TC_CASE(3, 2, 8) TC_CASE(5, 1, 8) TC_CASE(5, 2, 8) TC_CASE(7, 1, 4) TC_CASE(7, 2, 4)
+    TC_CASE(1, 1, 8, 0) TC_CASE(3, 1, 8, 0) TC_CASE(3, 2, 8, 0) TC_CASE(5, 1, 8, 0) TC_CASE(5, 2, 8, 0)
+    TC_CASE(7, 1, 4, 0) TC_CASE(7, 2, 4, 0)
+    // bf16 storage: a whole 32-channel source is 4 planes, so every shape runs with KQ = 4 (7x7 in a single pass)
+    TC_CASE(1, 1, 4, 1) TC_CASE(3, 1, 4, 1) TC_CASE(3, 2, 4, 1) TC_CASE(5, 1, 4, 1) TC_CASE(5, 2, 4, 1)
+    TC_CASE(7, 1, 4, 1) TC_CASE(7, 2, 4, 1)
+    // fp32 sources, bf16 outputs: the 1x1 convolutions that enter the bf16 part of the network
+    TC_CASE(1, 1, 8, 2)
 #undef TC_CASE
-    set_error("conv_tc: no kernel instance for k=%d dil=%d KQ=%d", d.kh, d.dil, g.plan.KQ);
+    set_error("conv_tc: no kernel instance for k=%d dil=%d KQ=%d storage=%d", d.kh, d.dil, g.plan.KQ, d.storage);
     return PAIF_ENOTSUP;
 }
 
@@ -749,9 +873,9 @@ extern "C" int paif_debug_tc_counters(unsigned long long* out16, int reset) {
 }
 #endif
 
-int conv_tc_kq(int nsrc, int k, int dil) {
+int conv_tc_kq(int nsrc, int k, int dil, bool bf16) {
     TcPlan p;
-    return tc_make_plan(nsrc, k, dil, &p) ? p.KQ : 0;
+    return tc_make_plan(nsrc, k, dil, bf16, &p) ? p.KQ : 0;
 }
 
 }  // namespace paif

@@ -332,6 +332,34 @@ eca_apply_kernel(const float* __restrict__ o, const float* __restrict__ xin, con
     reinterpret_cast<float4*>(out)[off] = r;
 }
 
+// bf16 C8 maps: one thread per (pixel, 8-channel plane)
+__global__ void __launch_bounds__(256)
+eca_apply_bf16_kernel(const uint4* __restrict__ o, const uint4* __restrict__ xin, const float* __restrict__ e,
+                      const float* __restrict__ slope_p, const uint4* __restrict__ post_res,
+                      uint4* __restrict__ out, int P, int H, int W) {
+    const int p = blockIdx.z % P, b = blockIdx.z / P;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const float a = *slope_p;
+    const float4 e0 = reinterpret_cast<const float4*>(e)[((size_t)b * P + p) * 2];
+    const float4 e1 = reinterpret_cast<const float4*>(e)[((size_t)b * P + p) * 2 + 1];
+    const size_t off = ((size_t)b * P + p) * plane + pix;
+    float4 o0, o1, x0, x1;
+    bf8_unpack(__ldg(o + off), o0, o1);
+    bf8_unpack(__ldg(xin + off), x0, x1);
+    float4 r0 = make_float4(prelu_f(fmaf(o0.x, e0.x, x0.x), a), prelu_f(fmaf(o0.y, e0.y, x0.y), a),
+                            prelu_f(fmaf(o0.z, e0.z, x0.z), a), prelu_f(fmaf(o0.w, e0.w, x0.w), a));
+    float4 r1 = make_float4(prelu_f(fmaf(o1.x, e1.x, x1.x), a), prelu_f(fmaf(o1.y, e1.y, x1.y), a),
+                            prelu_f(fmaf(o1.z, e1.z, x1.z), a), prelu_f(fmaf(o1.w, e1.w, x1.w), a));
+    if (post_res) {
+        float4 p0, p1;
+        bf8_unpack(__ldg(post_res + off), p0, p1);
+        r0 = f4_add(r0, p0);
+        r1 = f4_add(r1, p1);
+    }
+    out[off] = bf8_pack(r0, r1);
+}
+
 // backward pass 1: gw = gu * PReLU'(o e + x); per-(b, tile, c) sums of gw * o.  Tile = 32 x 64 px.
 constexpr int ECAB_ROWS = 64;
 __global__ void __launch_bounds__(256)
@@ -430,8 +458,9 @@ constexpr int OF_RX = OF_TX + 4, OF_RY = OF_TY + 4;            // feature region
 constexpr int OF_NQ = OF_RX * OF_RY;                           // 720
 constexpr int OF_SMEM = (25 * OF_NQ + 25 * OUT_C) * 4;
 
+template <bool BF>                                             // BF: feat is a bf16 C8 map
 __global__ void __launch_bounds__(256)
-out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
+out_forward_kernel(const void* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
                    float* __restrict__ out, float* __restrict__ pre_out, int H, int W) {
     extern __shared__ __align__(16) float of_smem[];
     float* sd = of_smem;                         // [25][OF_NQ]
@@ -442,7 +471,7 @@ out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm,
     const int b = blockIdx.z;
     const int x0 = blockIdx.x * OF_TX, y0 = blockIdx.y * OF_TY;
     const size_t plane = (size_t)H * W;
-    const float4* fp = reinterpret_cast<const float4*>(feat) + (size_t)b * (OUT_C / 4) * plane;
+    const void* fp = img32<BF>(feat, b, plane);
     // two feature pixels per thread and pass (q, q + 256): every weight vector read from shared memory feeds 8 FMAs
     // instead of 4 (the loop is LSU-issue bound on the broadcast weight reads)
     for (int q0 = tid; q0 < OF_NQ; q0 += 512) {
@@ -453,17 +482,21 @@ out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm,
             const int ry = q0 / OF_RX, rx = q0 - ry * OF_RX;
             const int yy = y0 - 2 + ry, xx = x0 - 2 + rx;
             const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            if (in) ld_px32<BF>(fp, plane, (size_t)yy * W + xx, v0);
+            else {
 #pragma unroll
-            for (int c = 0; c < OUT_C / 4; ++c)
-                v0[c] = in ? __ldg(fp + c * plane + (size_t)yy * W + xx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < OUT_C / 4; ++c) v0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         {
             const int ry = q1 / OF_RX, rx = q1 - ry * OF_RX;
             const int yy = y0 - 2 + ry, xx = x0 - 2 + rx;
             const bool in = has1 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            if (in) ld_px32<BF>(fp, plane, (size_t)yy * W + xx, v1);
+            else {
 #pragma unroll
-            for (int c = 0; c < OUT_C / 4; ++c)
-                v1[c] = in ? __ldg(fp + c * plane + (size_t)yy * W + xx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int c = 0; c < OUT_C / 4; ++c) v1[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
 #pragma unroll 5
         for (int t = 0; t < 25; ++t) {
@@ -501,8 +534,9 @@ out_forward_kernel(const float* __restrict__ feat, const float* __restrict__ wm,
 
 // The one-pixel image border of the merged stem_out stencil: its weights depend on the border class
 // (which taps of the second 3x3 conv fall on its zero padding).  2(W + H) - 4 pixels per image.
+template <bool BF>
 __global__ void __launch_bounds__(128)
-out_border_kernel(const float* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
+out_border_kernel(const void* __restrict__ feat, const float* __restrict__ wm, const float* __restrict__ slope_p,
                   float* __restrict__ out, float* __restrict__ pre_out, int H, int W) {
     const int b = blockIdx.y;
     const int i = blockIdx.x * 128 + threadIdx.x;
@@ -513,7 +547,7 @@ out_border_kernel(const float* __restrict__ feat, const float* __restrict__ wm, 
     else if (i < 2 * W) { y = H - 1; x = i - W; }
     else { const int j = i - 2 * W; y = 1 + (j >> 1); x = (j & 1) ? W - 1 : 0; }
     const size_t plane = (size_t)H * W;
-    const float4* fp = reinterpret_cast<const float4*>(feat) + (size_t)b * (OUT_C / 4) * plane;
+    const void* fp = img32<BF>(feat, b, plane);
     const int cls = border_class(y, H) * 3 + border_class(x, W);
     float acc = 0.f;
     for (int ty = 0; ty < 5; ++ty) {
@@ -523,9 +557,11 @@ out_border_kernel(const float* __restrict__ feat, const float* __restrict__ wm, 
             const int xx = x + tx - 2;
             if (xx < 0 || xx >= W) continue;
             const float4* wv = reinterpret_cast<const float4*>(wm + ((size_t)cls * 25 + ty * 5 + tx) * OUT_C);
+            float4 fv[OUT_C / 4];
+            ld_px32<BF>(fp, plane, (size_t)yy * W + xx, fv);
 #pragma unroll
             for (int c = 0; c < OUT_C / 4; ++c) {
-                const float4 v = __ldg(fp + c * plane + (size_t)yy * W + xx);
+                const float4 v = fv[c];
                 const float4 ww = __ldg(wv + c);
                 acc = fmaf(v.x, ww.x, acc); acc = fmaf(v.y, ww.y, acc);
                 acc = fmaf(v.z, ww.z, acc); acc = fmaf(v.w, ww.w, acc);
@@ -633,6 +669,114 @@ confusion_kernel(const long long* __restrict__ label, const long long* __restric
 
 using namespace paif;
 #define ST ((cudaStream_t)stream)
+
+// Fused DilConv on bf16 C8 maps: the same thread-per-pixel structure, eight input channels (one 16-byte vector per
+// tap) per step; depthwise and 1x1 arithmetic in fp32 registers, one rounding at the store.
+template <int K, int DIL>
+__global__ void __launch_bounds__(256, 2)
+dilconv_fused_bf16_kernel(const uint4* __restrict__ xin, const float* __restrict__ dw, const float* __restrict__ pw,
+                          const float* __restrict__ ch_scale, const float* __restrict__ ch_shift,
+                          const uint4* __restrict__ r1, const uint4* __restrict__ r2, uint4* __restrict__ out,
+                          int add_x, int H, int W) {
+    constexpr int TAPS = K * K, PAD = DIL * (K - 1) / 2;
+    __shared__ __align__(16) float s_pw[32 * 32];      // [cin][cout], scaled by BN
+    __shared__ __align__(16) float s_dw[TAPS * 32];    // [tap][channel]
+    __shared__ __align__(16) float s_sh[32];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < 1024; i += 256) {
+        const int ci = i >> 5, co = i & 31;
+        s_pw[i] = pw[co * 32 + ci] * (ch_scale ? ch_scale[co] : 1.f);
+    }
+    for (int i = tid; i < TAPS * 32; i += 256) {
+        const int t = i >> 5, c = i & 31;
+        s_dw[i] = dw[c * TAPS + t];
+    }
+    if (tid < 32) s_sh[tid] = ch_shift ? ch_shift[tid] : 0.f;
+    __syncthreads();
+    const int b = blockIdx.z;
+    PIX_SETUP();
+    if (x >= W || y >= H) return;
+    const uint4* xp = xin + (size_t)b * 4 * plane;
+    int toff[TAPS];
+    float tval[TAPS];
+#pragma unroll
+    for (int ty = 0; ty < K; ++ty)
+#pragma unroll
+        for (int tx = 0; tx < K; ++tx) {
+            const int yy = y + ty * DIL - PAD, xx = x + tx * DIL - PAD;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            toff[ty * K + tx] = ok ? yy * W + xx : (int)pix;
+            tval[ty * K + tx] = ok ? 1.f : 0.f;
+        }
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = s_sh[c];
+    uint4 v[TAPS];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) v[t] = __ldg(xp + toff[t]);
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+        float tv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t) {
+            float4 lo, hi;
+            bf8_unpack(v[t], lo, hi);
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_dw[t * 32 + p * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_dw[t * 32 + p * 8 + 4]);
+            const float m = tval[t];
+            tv[0] = fmaf(fmaxf(lo.x, 0.f) * m, w0.x, tv[0]); tv[1] = fmaf(fmaxf(lo.y, 0.f) * m, w0.y, tv[1]);
+            tv[2] = fmaf(fmaxf(lo.z, 0.f) * m, w0.z, tv[2]); tv[3] = fmaf(fmaxf(lo.w, 0.f) * m, w0.w, tv[3]);
+            tv[4] = fmaf(fmaxf(hi.x, 0.f) * m, w1.x, tv[4]); tv[5] = fmaf(fmaxf(hi.y, 0.f) * m, w1.y, tv[5]);
+            tv[6] = fmaf(fmaxf(hi.z, 0.f) * m, w1.z, tv[6]); tv[7] = fmaf(fmaxf(hi.w, 0.f) * m, w1.w, tv[7]);
+        }
+        if (p + 1 < 4) {                                   // next plane's taps are in flight during the 1x1 below
+#pragma unroll
+            for (int t = 0; t < TAPS; ++t) v[t] = __ldg(xp + (size_t)(p + 1) * plane + toff[t]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(&s_pw[(p * 8 + j) * 32]);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 w4 = wr[c4];
+                acc[c4 * 4 + 0] = fmaf(tv[j], w4.x, acc[c4 * 4 + 0]); acc[c4 * 4 + 1] = fmaf(tv[j], w4.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(tv[j], w4.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(tv[j], w4.w, acc[c4 * 4 + 3]);
+            }
+        }
+    }
+    const size_t base = (size_t)b * 4 * plane + pix;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const size_t off = base + p * plane;
+        float4 lo = make_float4(acc[p * 8 + 0], acc[p * 8 + 1], acc[p * 8 + 2], acc[p * 8 + 3]);
+        float4 hi = make_float4(acc[p * 8 + 4], acc[p * 8 + 5], acc[p * 8 + 6], acc[p * 8 + 7]);
+        float4 a0, a1;
+        if (add_x) { bf8_unpack(__ldg(xin + off), a0, a1); lo = f4_add(lo, a0); hi = f4_add(hi, a1); }
+        if (r1) { bf8_unpack(__ldg(r1 + off), a0, a1); lo = f4_add(lo, a0); hi = f4_add(hi, a1); }
+        if (r2) { bf8_unpack(__ldg(r2 + off), a0, a1); lo = f4_add(lo, a0); hi = f4_add(hi, a1); }
+        out[off] = bf8_pack(lo, hi);
+    }
+}
+
+extern "C" int paif_dilconv_forward_bf16(const void* x, const float* dw, const float* pw, const float* ch_scale,
+                                         const float* ch_shift, const void* r1, const void* r2, void* out, int add_x,
+                                         int C, int k, int dil, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(x && dw && pw && out, "null pointer");
+    PAIF_REQUIRE(C == 32, "C must be 32");
+    PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
+    PAIF_REQUIRE((long long)H * W < (1ll << 31), "image too large");
+#define DC_CASE(K_, D_)                                                                                              \
+    if (k == K_ && dil == D_) {                                                                                      \
+        dilconv_fused_bf16_kernel<K_, D_><<<pix_grid(W, H, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(              \
+            static_cast<const uint4*>(x), dw, pw, ch_scale, ch_shift, static_cast<const uint4*>(r1),                 \
+            static_cast<const uint4*>(r2), static_cast<uint4*>(out), add_x, H, W);                                   \
+        return check_launch("paif_dilconv_forward_bf16");                                                            \
+    }
+    DC_CASE(3, 1) DC_CASE(3, 2)
+#undef DC_CASE
+    set_error("paif_dilconv_forward_bf16: kernel %d dilation %d not instantiated (3x3, dilation 1 or 2)", k, dil);
+    return PAIF_ENOTSUP;
+}
 
 extern "C" int paif_dwconv_forward(const float* x, const float* w, int relu_in, const float* mask_src,
                                    const float* post_res, float* out, int C, int k, int dil,
@@ -748,6 +892,76 @@ spa_fused_kernel(const float* __restrict__ w, int k, const float* __restrict__ a
     }
 }
 
+// the same for bf16 C8 maps (C = 32): pooling and blend in fp32 registers, one rounding at the store
+__global__ void __launch_bounds__(256)
+spa_fused_bf16_kernel(const float* __restrict__ w, int k, const void* __restrict__ a, const void* __restrict__ v,
+                      void* __restrict__ agg, int H, int W) {
+    __shared__ float4 sw[49];
+    __shared__ float4 sp[(SF_TY + 6) * (SF_TX + 6)];
+    const int tid = threadIdx.x;
+    const int taps = k * k, pad = (k - 1) / 2;
+    if (tid < taps) sw[tid] = make_float4(w[tid], w[taps + tid], w[2 * taps + tid], w[3 * taps + tid]);
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * SF_TX, y0 = blockIdx.y * SF_TY;
+    const int RX = SF_TX + 2 * pad, RY = SF_TY + 2 * pad;
+    const size_t plane = (size_t)H * W;
+    const void* ap = img32<true>(a, b, plane);
+    const void* vp = img32<true>(v, b, plane);
+    for (int i = tid; i < RX * RY; i += 256) {
+        const int ry = i / RX, rx = i - ry * RX;
+        const int yy = y0 - pad + ry, xx = x0 - pad + rx;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const size_t pix = (size_t)yy * W + xx;
+            float4 t[8], u[8];
+            ld_px32<true>(ap, plane, pix, t);
+            ld_px32<true>(vp, plane, pix, u);
+            float amax = -INFINITY, asum = 0.f, vmax = -INFINITY, vsum = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                amax = fmaxf(fmaxf(amax, fmaxf(t[q].x, t[q].y)), fmaxf(t[q].z, t[q].w));
+                asum += (t[q].x + t[q].y) + (t[q].z + t[q].w);
+                vmax = fmaxf(fmaxf(vmax, fmaxf(u[q].x, u[q].y)), fmaxf(u[q].z, u[q].w));
+                vsum += (u[q].x + u[q].y) + (u[q].z + u[q].w);
+            }
+            p = make_float4(amax, asum * (1.f / 32.f), vmax, vsum * (1.f / 32.f));
+        }
+        sp[i] = p;
+    }
+    __syncthreads();
+    for (int o = tid; o < SF_TX * SF_TY; o += 256) {
+        const int oy = o / SF_TX, ox = o - oy * SF_TX;
+        const int y = y0 + oy, x = x0 + ox;
+        if (y >= H || x >= W) continue;
+        float acc = 0.f;
+        for (int ty = 0; ty < k; ++ty)
+            for (int tx = 0; tx < k; ++tx) {
+                const float4 p = sp[(oy + ty) * RX + ox + tx];
+                const float4 ww = sw[ty * k + tx];
+                acc = fmaf(p.x, ww.x, acc); acc = fmaf(p.y, ww.y, acc);
+                acc = fmaf(p.z, ww.z, acc); acc = fmaf(p.w, ww.w, acc);
+            }
+        const float s = sigmoid_f(acc), s1 = 1.f - s;
+        const size_t pix = (size_t)y * W + x;
+        float4 t[8], u[8];
+        ld_px32<true>(ap, plane, pix, t);
+        ld_px32<true>(vp, plane, pix, u);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            t[q] = make_float4(s * t[q].x + s1 * u[q].x, s * t[q].y + s1 * u[q].y, s * t[q].z + s1 * u[q].z, s * t[q].w + s1 * u[q].w);
+        st_px32<true>(img32<true>(agg, b, plane), plane, pix, t);
+    }
+}
+
+extern "C" int paif_spa_fused_forward_bf16(const float* w, int k, const void* ir_f, const void* vis_f, void* agg,
+                                           int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(w && ir_f && vis_f && agg, "null pointer");
+    PAIF_REQUIRE(C == 32 && k >= 1 && k <= 7 && (k & 1), "unsupported C / kernel size");
+    PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
+    spa_fused_bf16_kernel<<<dim3(cdiv(W, SF_TX), cdiv(H, SF_TY), B), 256, 0, ST>>>(w, k, ir_f, vis_f, agg, H, W);
+    return check_launch("paif_spa_fused_forward_bf16");
+}
+
 extern "C" int paif_spa_fused_forward(const float* w, int k, const float* ir_f, const float* vis_f, float* agg,
                                       float* scale_out, int C, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(w && ir_f && vis_f && agg, "null pointer");
@@ -808,6 +1022,16 @@ extern "C" int paif_eca_apply(const float* o, const float* x, const float* e, co
     return check_launch("paif_eca_apply");
 }
 
+extern "C" int paif_eca_apply_bf16(const void* o, const void* x, const float* e, const float* slope,
+                                   const void* post_res, void* out, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(o && x && e && slope && out, "null pointer");
+    PAIF_REQUIRE(C % 8 == 0 && (long long)B * (C / 8) <= 65535, "C must be a multiple of 8; B*C/8 <= 65535");
+    eca_apply_bf16_kernel<<<pix_grid(W, H, B * (C / 8)), dim3(32, 8), 0, ST>>>(
+        static_cast<const uint4*>(o), static_cast<const uint4*>(x), e, slope, static_cast<const uint4*>(post_res),
+        static_cast<uint4*>(out), C / 8, H, W);
+    return check_launch("paif_eca_apply_bf16");
+}
+
 extern "C" int paif_eca_bwd_tiles(int H, int W) { return cdiv(W, 32) * cdiv(H, ECAB_ROWS); }
 
 extern "C" int paif_eca_bwd_pass1(const float* gu, const float* o, const float* x, const float* e,
@@ -839,8 +1063,9 @@ static int out_smem_attr() {
     int dev;
     if (!attr_needed(done, &dev)) return 0;
     const int bytes = 9 * 25 * OUT_C * sizeof(float);
-    cudaError_t e1 = cudaFuncSetAttribute(out_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);
+    cudaError_t e1 = cudaFuncSetAttribute(out_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);
     cudaError_t e2 = cudaFuncSetAttribute(out_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(out_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OF_SMEM);
     if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("out kernel smem attr failed"); return (int)(e1 ? e1 : e2); }
     attr_mark(done, dev);
     return 0;
@@ -852,10 +1077,22 @@ extern "C" int paif_out_forward(const float* feat, const float* wm, const float*
     PAIF_REQUIRE(C == OUT_C, "C must be 32");
     PAIF_REQUIRE(H >= 2 && W >= 2, "H, W must be >= 2");
     if (int r = out_smem_attr()) return r;
-    out_forward_kernel<<<dim3(cdiv(W, OF_TX), cdiv(H, OF_TY), B), 256, OF_SMEM, ST>>>(feat, wm, slope, out, pre_out, H, W);
+    out_forward_kernel<false><<<dim3(cdiv(W, OF_TX), cdiv(H, OF_TY), B), 256, OF_SMEM, ST>>>(feat, wm, slope, out, pre_out, H, W);
     if (int r = check_launch("paif_out_forward")) return r;
-    out_border_kernel<<<dim3(cdiv(2 * W + 2 * (H - 2), 128), B), 128, 0, ST>>>(feat, wm, slope, out, pre_out, H, W);
+    out_border_kernel<false><<<dim3(cdiv(2 * W + 2 * (H - 2), 128), B), 128, 0, ST>>>(feat, wm, slope, out, pre_out, H, W);
     return check_launch("paif_out_forward");
+}
+
+extern "C" int paif_out_forward_bf16(const void* feat, const float* wm, const float* slope, float* out,
+                                     int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(feat && wm && slope && out, "null pointer");
+    PAIF_REQUIRE(C == OUT_C, "C must be 32");
+    PAIF_REQUIRE(H >= 2 && W >= 2, "H, W must be >= 2");
+    if (int r = out_smem_attr()) return r;
+    out_forward_kernel<true><<<dim3(cdiv(W, OF_TX), cdiv(H, OF_TY), B), 256, OF_SMEM, ST>>>(feat, wm, slope, out, nullptr, H, W);
+    if (int r = check_launch("paif_out_forward_bf16")) return r;
+    out_border_kernel<true><<<dim3(cdiv(2 * W + 2 * (H - 2), 128), B), 128, 0, ST>>>(feat, wm, slope, out, nullptr, H, W);
+    return check_launch("paif_out_forward_bf16");
 }
 
 extern "C" int paif_out_backward(const float* g, const float* out, const float* pre_out, const float* wm,

@@ -10,7 +10,7 @@ constexpr int STEM_C = 32;
 __global__ void __launch_bounds__(256)
 stem_forward_kernel(const float* __restrict__ img, long long sb, long long sy, long long sx,
                     const float* __restrict__ w, const float* __restrict__ slope_p,
-                    float* __restrict__ feat, float* __restrict__ residue, int H, int W) {
+                    float* __restrict__ feat, float* __restrict__ residue, uint4* __restrict__ feat16, int H, int W) {
     __shared__ float sw[STEM_C * 9];
     const int tid = threadIdx.y * 32 + threadIdx.x;
     for (int i = tid; i < STEM_C * 9; i += 256) sw[i] = w[i];
@@ -33,6 +33,7 @@ stem_forward_kernel(const float* __restrict__ img, long long sb, long long sy, l
     float vmax = -INFINITY, vmin = INFINITY;
     const size_t plane = (size_t)H * W;
     float4* out = reinterpret_cast<float4*>(feat) + (size_t)b * (STEM_C / 4) * plane + (size_t)y * W + x;
+    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < STEM_C / 4; ++q) {
         float r[4];
@@ -48,6 +49,12 @@ stem_forward_kernel(const float* __restrict__ img, long long sb, long long sy, l
             r[j] = acc;
         }
         out[q * plane] = make_float4(r[0], r[1], r[2], r[3]);
+        if (feat16) {                 // bf16 C8 copy for the bf16 storage mode (residual of the decomposition branch)
+            if (q & 1)
+                feat16[((size_t)b * (STEM_C / 8) + (q >> 1)) * plane + (size_t)y * W + x] =
+                    bf8_pack(prev, make_float4(r[0], r[1], r[2], r[3]));
+            else prev = make_float4(r[0], r[1], r[2], r[3]);
+        }
     }
     residue[(size_t)b * plane + (size_t)y * W + x] = vmax - vmin;
 }
@@ -154,8 +161,19 @@ extern "C" int paif_stem_forward(const float* img, long long sb, long long sy, l
     PAIF_REQUIRE(img && w && slope && feat && residue, "null pointer");
     PAIF_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
     dim3 grid(cdiv(W, 32), cdiv(H, 8), B), block(32, 8);
-    stem_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, sy, sx, w, slope, feat, residue, H, W);
+    stem_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, sy, sx, w, slope, feat, residue, nullptr, H, W);
     return check_launch("paif_stem_forward");
+}
+
+extern "C" int paif_stem_forward_bf16copy(const float* img, long long sb, long long sy, long long sx,
+                                          const float* w, const float* slope, float* feat, float* residue,
+                                          void* feat_bf16, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(img && w && slope && feat && residue && feat_bf16, "null pointer");
+    PAIF_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+    dim3 grid(cdiv(W, 32), cdiv(H, 8), B), block(32, 8);
+    stem_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, sy, sx, w, slope, feat, residue,
+                                                                  static_cast<uint4*>(feat_bf16), H, W);
+    return check_launch("paif_stem_forward_bf16copy");
 }
 
 extern "C" int paif_stem_backward_pre(const float* feat, const float* slope,

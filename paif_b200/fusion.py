@@ -61,6 +61,13 @@ class _ConvW:
             # [K-group][dx][k8][16-B chunk][dy][cout][4 cin]: all dy taps of one (dx, k8) form one B tile of N = 32*k rows
             wt = _round_tf32(w.float()).reshape(cout, G, kq // 2, 2, 4, kh, kw)
             self.mma = wt.permute(1, 6, 2, 3, 5, 0, 4).contiguous()
+        # bf16 storage mode: the same tile order with 8 bf16 input channels per 16 bytes (paif_conv_tc_kq_bf16)
+        self.mma16 = None
+        kp = _lib.load().paif_conv_tc_kq_bf16(nsrc, k, dil) if (cout == 32 and self.cps == 32) else 0
+        if kp:
+            G = cin_total // (kp * 8)
+            wt = w.float().reshape(cout, G, kp // 2, 2, 8, kh, kw)
+            self.mma16 = wt.permute(1, 6, 2, 3, 5, 0, 4).contiguous().to(torch.bfloat16)
 
 
 def _round_tf32(w):
@@ -88,19 +95,22 @@ def _bn_fold(bn):
 # runtime: thin wrappers over the C ABI
 # ----------------------------------------------------------------------------------------
 class _Runtime:
-    def __init__(self, B, H, W, C, device, engine, save):
+    def __init__(self, B, H, W, C, device, engine, save, bf16=False):
         self.B, self.H, self.W, self.C = B, H, W, C
         self.device = device
         self.engine = engine
         self.save = save
+        self.bf16 = bf16             # bf16 C8 activation maps (forward only)
         self.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         self.launches = 0
         self.profile = None          # optional list: (name, meta, start_event, end_event) per launch
         self._meta = None
 
     # buffers ---------------------------------------------------------------------------
-    def new_map(self, C=None):
+    def new_map(self, C=None, fp32=False):
         C = self.C if C is None else C
+        if self.bf16 and not fp32:
+            return torch.empty((self.B, C // 8, self.H, self.W, 8), device=self.device, dtype=torch.bfloat16)
         return torch.empty((self.B, C // 4, self.H, self.W, 4), device=self.device, dtype=torch.float32)
 
     def new_plane(self, ch=None):
@@ -108,7 +118,7 @@ class _Runtime:
         return torch.empty(shape, device=self.device, dtype=torch.float32)
 
     #: kernels behind one ABI call when it is not exactly one
-    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_gf_decomp_backward": 3}
+    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_out_forward_bf16": 2, "paif_gf_decomp_backward": 3}
 
     def call(self, name, *args):
         self.launches += self._KERNELS_PER_CALL.get(name, 1)
@@ -124,7 +134,8 @@ class _Runtime:
 
     # kernels ---------------------------------------------------------------------------
     def conv(self, srcs, cw, *, ch_scale=None, ch_shift=None, pre_res=(), want_pre=False, mask_src=None,
-             mask_slope=None, slope=None, post_scale=1.0, post_res=(), act2_slope=None, want_partials=False):
+             mask_slope=None, slope=None, post_scale=1.0, post_res=(), act2_slope=None, want_partials=False,
+             src_fp32=False):
         d = ConvDesc()
         d.B, d.H, d.W = self.B, self.H, self.W
         d.nsrc, d.cin_per_src, d.cout = cw.nsrc, cw.cps, cw.cout
@@ -133,12 +144,19 @@ class _Runtime:
         engine = self.engine
         if engine == _lib.ENGINE_AUTO:
             engine = _lib.ENGINE_TCGEN05 if cw.mma is not None else _lib.ENGINE_DIRECT
+        wmma, in_bytes, out_bytes = cw.mma, 4.0, 4.0
+        if self.bf16:
+            # bf16 maps exist on the tensor-core engine only; src_fp32: fp32 sources (TF32 operands), bf16 everything else
+            d.storage = _lib.STORAGE_F32_BF16 if src_fp32 else _lib.STORAGE_BF16
+            wmma, in_bytes, out_bytes = (cw.mma, 4.0, 2.0) if src_fp32 else (cw.mma16, 2.0, 2.0)
+            if engine != _lib.ENGINE_TCGEN05 or wmma is None:
+                raise NotImplementedError("bf16 storage: convolution k=%d dil=%d x%d has no tcgen05 instance" % (cw.k, cw.dil, cw.nsrc))
         d.engine = engine
         assert len(srcs) == cw.nsrc
         for i, s in enumerate(srcs):
             d.src[i] = s.data_ptr()
         d.weight = cw.direct.data_ptr()
-        d.weight_mma = _ptr(cw.mma)
+        d.weight_mma = _ptr(wmma)
         d.ch_scale, d.ch_shift = _ptr(ch_scale), _ptr(ch_shift)
         assert len(pre_res) <= 2 and len(post_res) <= 3
         for i, r in enumerate(pre_res):
@@ -162,15 +180,19 @@ class _Runtime:
             partials = torch.empty((self.B, tiles, cw.cout), device=self.device, dtype=torch.float32)
             d.chan_partials = partials.data_ptr()
         # algorithmic traffic: every source / residual / mask map read once, every output map written once
-        maps = (cw.nsrc * cw.cps + cw.cout * (len(pre_res) + len(post_res) + (mask_src is not None) + 1 +
-                                               bool(want_pre) + (act2_slope is not None)))
+        ch_bytes = (in_bytes * cw.nsrc * cw.cps +
+                    out_bytes * cw.cout * (len(pre_res) + len(post_res) + (mask_src is not None) + 1 +
+                                           bool(want_pre) + (act2_slope is not None)))
         self._meta = {"k": cw.k, "dil": cw.dil, "cin": cw.nsrc * cw.cps, "cout": cw.cout, "engine": engine,
+                      "storage": int(d.storage),
                       "flops": 2.0 * cw.cout * cw.nsrc * cw.cps * cw.k * cw.k * self.B * self.H * self.W,
-                      "bytes": 4.0 * maps * self.B * self.H * self.W}
+                      "bytes": ch_bytes * self.B * self.H * self.W}
         self.call("paif_conv_forward", ctypes.byref(d))
         return out, pre, act2, partials
 
     def add(self, a, b, c=None):
+        if self.bf16:
+            raise NotImplementedError("bf16 storage: this genotype needs a stand-alone map add (fp32 storage only)")
         out = torch.empty_like(a)
         self.call("paif_add_maps", a.data_ptr(), b.data_ptr(), _ptr(c), out.data_ptr(), a.numel())
         return out
@@ -214,6 +236,7 @@ class BasicConv(nn.Module):
 class _Primitive(nn.Module):
     max_extras = 0       # residual maps the forward epilogue can absorb
     max_extra_add = 0    # gradient maps the backward epilogue can absorb
+    bf16_ok = False      # has a bf16-storage forward (the primitives of the shipped genotype do)
 
     def forward(self, x):
         raise RuntimeError("paif_b200 primitives run only inside Network_Fusion_Searched.forward")
@@ -222,6 +245,7 @@ class _Primitive(nn.Module):
 class ResidualDenseBlock(_Primitive):
     """operations_m.py:435-449."""
     max_extras, max_extra_add = 2, 1
+    bf16_ok = True
 
     def __init__(self, in_channels, kernel_size, dialtions=1, bias=False):
         super().__init__()
@@ -264,6 +288,7 @@ class ResidualDenseBlock(_Primitive):
 class DilConv(_Primitive):
     """operations_m.py:494-506 (BN in eval mode, folded to scale/shift)."""
     max_extras, max_extra_add = 2, 0
+    bf16_ok = True
 
     def __init__(self, C_in, C_out, kernel_size, dilation, affine=True):
         super().__init__()
@@ -289,6 +314,13 @@ class DilConv(_Primitive):
 
     def fwd(self, rt, p, x, extras):
         extras = list(extras)
+        if rt.bf16:
+            out = torch.empty_like(x)
+            rt.call("paif_dilconv_forward_bf16", x.data_ptr(), p["dw"].data_ptr(), p["pw_raw"].data_ptr(),
+                    p["s"].data_ptr(), p["sh"].data_ptr(), _ptr(extras[0]) if extras else None,
+                    _ptr(extras[1]) if len(extras) > 1 else None, out.data_ptr(), 1, rt.C, self.k, self.d,
+                    rt.B, rt.H, rt.W)
+            return out, ()
         if (self.k, self.d) not in ((3, 1), (3, 2)):       # only the 3x3 shapes have a fused kernel instance
             t = rt.dwconv(x, p["dw"], self.k, self.d, relu_in=True)
             return rt.conv([t], p["pw"], ch_scale=p["s"], ch_shift=p["sh"], post_res=[x] + extras)[0], ()
@@ -316,6 +348,7 @@ class eca_layer(nn.Module):
 class ECABasicBlock(_Primitive):
     """operations_m.py:368-393."""
     max_extras, max_extra_add = 1, 3
+    bf16_ok = True
 
     def __init__(self, inplanes, planes, kernel=3, dilation=1, stride=1, reduction=64, with_norm=False):
         super().__init__()
@@ -344,8 +377,8 @@ class ECABasicBlock(_Primitive):
         rt.call("paif_eca_scale", partials.data_ptr(), partials.shape[1], p["w1d"].data_ptr(), self.k,
                 e.data_ptr(), rt.C, rt.B, rt.H, rt.W)
         out = rt.new_map()
-        rt.call("paif_eca_apply", o.data_ptr(), x0.data_ptr(), e.data_ptr(), a.data_ptr(),
-                _ptr(extras[0]) if extras else None, out.data_ptr(), rt.C, rt.B, rt.H, rt.W)
+        rt.call("paif_eca_apply_bf16" if rt.bf16 else "paif_eca_apply", o.data_ptr(), x0.data_ptr(), e.data_ptr(),
+                a.data_ptr(), _ptr(extras[0]) if extras else None, out.data_ptr(), rt.C, rt.B, rt.H, rt.W)
         return out, (x0, o, e)
 
     def bwd(self, rt, p, rec, g, extra_add):
@@ -371,6 +404,7 @@ class ResidualModule(_Primitive):
     """operations_m.py:451-464.  The bias-free 3x3(dil 2) and 1x1 convolutions that follow the
     k x k convolution have no activation between them and are merged into one 3x3(dil 2)."""
     max_extras, max_extra_add = 2, 2
+    bf16_ok = True
 
     def __init__(self, in_channels, kernel_size, dialtions=1, bias=False):
         super().__init__()
@@ -706,6 +740,9 @@ class Network_Fusion_Searched(nn.Module):
         self.chain = Cell_Chain(C, self._genotype.normal_3, self._genotype.normal_1_concat)
         #: 'auto' | 'direct' (exact fp32 FFMA) | 'tcgen05' (TF32 tensor cores, fp32 accumulate)
         self.conv_engine = 'auto'
+        #: activation storage: 'fp32' (default; TF32 tensor-core operands, max-abs 1e-3 tier) or 'bf16' (bf16 C8 maps
+        #: and bf16 operands after the decomposition, fp32 accumulation; forward-only, north_star's 1e-2 tier)
+        self.storage = 'fp32'
         self._pack_cache = None
         self.last_launches = 0
         #: set to a list to collect (name, meta, start_event, end_event) for every kernel launch
@@ -745,6 +782,26 @@ class Network_Fusion_Searched(nn.Module):
         self._pack_cache = (key, p)
         return p
 
+    def _bf16_storage(self, save):
+        """True when this forward runs with bf16 activation maps (``self.storage == 'bf16'``)."""
+        if self.storage == 'fp32':
+            return False
+        if self.storage != 'bf16':
+            raise ValueError("storage must be 'fp32' or 'bf16', not %r" % (self.storage,))
+        if save:
+            raise RuntimeError("storage='bf16' is a forward-only mode (run under torch.no_grad()); the "
+                               "backward-to-input path keeps fp32 activations: set storage='fp32' for PGD")
+        if self.conv_engine == 'direct':
+            raise RuntimeError("storage='bf16' runs on the tcgen05 engine; conv_engine='direct' is the exact-fp32 path")
+        if self._C != 32:
+            raise NotImplementedError("storage='bf16' needs C = 32")
+        ops = [m._op for ch in (self.decompation.chain, self.decompation.chain2, self.chain) for m in ch._ops]
+        bad = sorted({type(o).__name__ for o in ops if not o.bf16_ok})
+        if bad:
+            raise NotImplementedError("storage='bf16' covers the primitives of the shipped genotype; no bf16 forward "
+                                      "for: %s" % ", ".join(bad))
+        return True
+
     def _engine(self):
         return {'auto': _lib.ENGINE_AUTO, 'direct': _lib.ENGINE_DIRECT, 'tcgen05': _lib.ENGINE_TCGEN05}[self.conv_engine]
 
@@ -753,41 +810,57 @@ class Network_Fusion_Searched(nn.Module):
         """ir, vis: [B,1,H,W] fp32 CUDA views (any strides).  Returns (out[B,1,H,W], saved)."""
         B, _, H, W = ir.shape
         p = self._packed(save)
-        rt = _Runtime(B, H, W, self._C, ir.device, self._engine(), save)
+        bf16 = self._bf16_storage(save)
+        rt = _Runtime(B, H, W, self._C, ir.device, _lib.ENGINE_TCGEN05 if bf16 else self._engine(), save, bf16=bf16)
         rt.profile = self.profile
         C = self._C
-        feats, guides, gstats = [], [], []
+        feats, guides, gstats, feats16 = [], [], [], []
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
-            f, g = rt.new_map(), rt.new_plane()
-            rt.call("paif_stem_forward", img.data_ptr(), img.stride(0), img.stride(2), img.stride(3),
-                    w.data_ptr(), a.data_ptr(), f.data_ptr(), g.data_ptr(), B, H, W)
+            f, g = rt.new_map(fp32=True), rt.new_plane()
+            if bf16:
+                # stems, guide and guided filter stay fp32; the bf16 copy of the stem features is the branch residual
+                f16 = rt.new_map()
+                rt.call("paif_stem_forward_bf16copy", img.data_ptr(), img.stride(0), img.stride(2), img.stride(3),
+                        w.data_ptr(), a.data_ptr(), f.data_ptr(), g.data_ptr(), f16.data_ptr(), B, H, W)
+                feats16.append(f16)
+            else:
+                rt.call("paif_stem_forward", img.data_ptr(), img.stride(0), img.stride(2), img.stride(3),
+                        w.data_ptr(), a.data_ptr(), f.data_ptr(), g.data_ptr(), B, H, W)
             feats.append(f)
             guides.append(g)
         d = self.decompation
         branch_out, branch_recs = [], []
         for i, (chain, packs) in enumerate(((d.chain, p["chain_ir"]), (d.chain2, p["chain_vis"]))):
-            lf1, lf2 = rt.new_map(), rt.new_map()
+            lf1, lf2 = rt.new_map(fp32=True), rt.new_map(fp32=True)
             stats = torch.empty((3, B, H, W), device=ir.device, dtype=torch.float32)
             rt.call("paif_gf_guide_stats", guides[i].data_ptr(), stats.data_ptr(), B, H, W)
             rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
                     lf1.data_ptr(), lf2.data_ptr(), C, B, H, W)
             gstats.append(stats if save else None)
             del stats
-            x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i])[0]
+            x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i], src_fp32=True)[0]
             del lf1, lf2
-            o, recs = chain.fwd(rt, packs, x, [feats[i]])
+            o, recs = chain.fwd(rt, packs, x, [feats16[i] if bf16 else feats[i]])
             branch_out.append(o)
             branch_recs.append(recs)
         a_f, v_f = branch_out
         agg = rt.new_map()
         scale = rt.new_plane() if save else None
-        rt.call("paif_spa_fused_forward", p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(), v_f.data_ptr(),
-                agg.data_ptr(), _ptr(scale), C, B, H, W)
+        if bf16:
+            rt.call("paif_spa_fused_forward_bf16", p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(), v_f.data_ptr(),
+                    agg.data_ptr(), C, B, H, W)
+        else:
+            rt.call("paif_spa_fused_forward", p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(), v_f.data_ptr(),
+                    agg.data_ptr(), _ptr(scale), C, B, H, W)
         f2, recs3 = self.chain.fwd(rt, p["chain"], agg, [])
         out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
         pre_out = rt.new_plane() if save else None
-        rt.call("paif_out_forward", f2.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(), out.data_ptr(),
-                _ptr(pre_out), C, B, H, W)
+        if bf16:
+            rt.call("paif_out_forward_bf16", f2.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(),
+                    out.data_ptr(), C, B, H, W)
+        else:
+            rt.call("paif_out_forward", f2.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(), out.data_ptr(),
+                    _ptr(pre_out), C, B, H, W)
         self.last_launches = rt.launches
         saved = None
         if save:
