@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", action="store_true", help="print the per-launch CUDA-event table of one step to stderr")
     ap.add_argument("--bwd-steps", type=int, default=3, help="timed forward+backward-to-input steps (0 = skip)")
+    ap.add_argument("--bf16-steps", type=int, default=5,
+                    help="timed forward steps in the bf16 storage mode (SURVEY 8 config D's precision tier; 0 = skip)")
     ap.add_argument("--pgd-consumer-bf16", action="store_true", help="run the stock consumer under bf16 autocast")
     ap.add_argument("--pgd-eager", action="store_true", help="PGD leg without CUDA-graph replay of the PGD iteration")
     ap.add_argument("--pgd-frames", type=int, default=4,
@@ -388,6 +390,45 @@ def run_ours(args):
                 sys.stderr.write("%-44s x%-3d %8.3f ms %5.1f%%\n" % (key, cnt, t, 100 * t / tot))
             sys.stderr.write("sum of launches %.3f ms (fwd+bwd step %.3f ms)\n" % (tot, ms_fb / args.bwd_steps))
 
+    # bf16 storage mode (north_star's 1e-2 tier): the same forward step with bf16 activation maps / bf16 tensor-core
+    # operands after the decomposition; reported beside the headline, never instead of it
+    bf16_leg = None
+    if args.bf16_steps > 0 and args.engine != "direct":
+        with torch.no_grad():
+            out32 = net(ir_d, vis_d)
+        net.storage = 'bf16'
+        try:
+            for _ in range(3):
+                step_resident()
+            net.profile = [] if args.table else None
+            ms16 = timed(step_resident, args.bf16_steps)
+            prof16, net.profile = net.profile, None
+            with torch.no_grad():
+                err16 = (net(ir_d, vis_d) - out32).abs().max().item()
+            bf16_leg = {"value": B * world * args.bf16_steps / (ms16 * 1e-3), "unit": "pairs/s",
+                        "ms_per_step": ms16 / args.bf16_steps, "steps": args.bf16_steps,
+                        "launches_per_step": net.last_launches, "dtype": "bf16 maps + bf16 MMA operands, fp32 accumulate; "
+                        "stems / guided filter / decomposition inputs fp32",
+                        "max_abs_vs_fp32_mode": err16, "tolerance": 1e-2,
+                        "whole_step_frac_of_hbm_roof": (BYTES_PER_PX / 2 * H * W * B * args.bf16_steps / (ms16 * 1e-3) / 1e9) / peaks()["hbm_gbs"],
+                        "whole_step_note": "SURVEY 8d bf16 plan (1891 ch x 2 B per pixel) / step time / HBM peak",
+                        "what": "the headline forward step with net.storage='bf16', batch %d per GPU, inputs resident" % B}
+            if args.table and rank == 0 and prof16:
+                per = len(prof16) // args.bf16_steps
+                tot = sum(a.elapsed_time(b) for (_, _, a, b) in prof16[-per:])
+                sys.stderr.write("--- forward step, bf16 storage mode ---\n")
+                for (n, m, a, b) in prof16[-per:]:
+                    t = a.elapsed_time(b)
+                    extra = ""
+                    if m:
+                        extra = " k%d d%d cin%d  %.1f TFLOP/s  %.0f GB/s" % (m["k"], m["dil"], m["cin"], m["flops"] / (t * 1e-3) / 1e12,
+                                                                             m["bytes"] / (t * 1e-3) / 1e9)
+                    sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
+                sys.stderr.write("sum of launches %.3f ms (step %.3f ms)\n" % (tot, ms16 / args.bf16_steps))
+        finally:
+            net.storage = 'fp32'
+            net.profile = None
+
     if args.table and rank == 0:
         per = len(prof) // args.steps
         tot = sum(a.elapsed_time(b) for (_, _, a, b) in prof[-per:])
@@ -456,6 +497,8 @@ def run_ours(args):
     }
     if fwd_bwd is not None:
         line["fwd_bwd"] = fwd_bwd
+    if bf16_leg is not None:
+        line["bf16_storage"] = bf16_leg
     if pgd is not None:
         line["pgd10"] = pgd
     if not args.no_cpu_baseline and world == 1:
