@@ -101,10 +101,23 @@ class _Runtime:
         self.engine = engine
         self.save = save
         self.bf16 = bf16             # bf16 C8 activation maps (forward only)
+        self.dilconv_dense = True    # DilConv as one dense conv on the tensor-core engine when relu(x) is available
+        self.want_relu = False       # set by Cell_Chain: the next op (DilConv) wants relu(out) as a second map ...
+        self.last_relu = None        # ... which a producer that can emit it leaves here
+        self._zero = None
         self.stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         self.launches = 0
         self.profile = None          # optional list: (name, meta, start_event, end_event) per launch
         self._meta = None
+
+    def zero_slope(self):
+        if self._zero is None:
+            self._zero = torch.zeros(1, device=self.device, dtype=torch.float32)
+        return self._zero
+
+    def tc_engine(self):
+        """True when dense convolutions of this call resolve to the tcgen05 engine."""
+        return self.engine in (_lib.ENGINE_AUTO, _lib.ENGINE_TCGEN05)
 
     # buffers ---------------------------------------------------------------------------
     def new_map(self, C=None, fp32=False):
@@ -269,8 +282,10 @@ class ResidualDenseBlock(_Primitive):
         a = p["a"]
         x1 = rt.conv([x], p["w"][0], slope=a)[0]
         x2 = rt.conv([x, x1], p["w"][1], slope=a)[0]
-        out, pre3, _, _ = rt.conv([x, x1, x2], p["w"][2], slope=a, post_scale=_RDB_SCALE,
-                                  post_res=[x] + list(extras), want_pre=rt.save)
+        out, pre3, relu_out, _ = rt.conv([x, x1, x2], p["w"][2], slope=a, post_scale=_RDB_SCALE,
+                                         post_res=[x] + list(extras), want_pre=rt.save,
+                                         act2_slope=rt.zero_slope() if rt.want_relu else None)
+        rt.last_relu = relu_out
         return out, (x1, x2, pre3)
 
     def bwd(self, rt, p, rec, g, extra_add):
@@ -307,13 +322,20 @@ class DilConv(_Primitive):
         s, sh = _bn_fold(self.op[3])
         p = {"dw": dw.reshape(C, -1).contiguous().float(), "pw": _ConvW(self.op[2].weight.detach(), 1, 1, 1),
              "pw_raw": self.op[2].weight.detach().reshape(C, C).contiguous().float(), "s": s, "sh": sh}
+        # depthwise followed by 1x1 == one dense k x k convolution with rank-1 taps W[co][ci][t] = pw[co][ci] dw[ci][t];
+        # on the tensor-core engine that is cheaper than the FFMA kernel whenever the producer can hand over relu(x)
+        wd = self.op[2].weight.detach()[:, :, 0, 0].double()[:, :, None, None] * dw.double()[:, 0][None]
+        p["wdense"] = _ConvW(wd.float(), 1, self.k, self.d)
         if need_bwd:
             p["dw_t"] = dw.flip(-1, -2).reshape(C, -1).contiguous().float()
             p["pw_d"] = _dgrad_groups(self.op[2].weight.detach(), 1, 1, scale=s)[0]
         return p
 
-    def fwd(self, rt, p, x, extras):
+    def fwd(self, rt, p, x, extras, x_relu=None):
         extras = list(extras)
+        cw = p["wdense"]
+        if x_relu is not None and rt.tc_engine() and (cw.mma16 if rt.bf16 else cw.mma) is not None:
+            return rt.conv([x_relu], cw, ch_scale=p["s"], ch_shift=p["sh"], post_res=[x] + extras)[0], ()
         if rt.bf16:
             out = torch.empty_like(x)
             rt.call("paif_dilconv_forward_bf16", x.data_ptr(), p["dw"].data_ptr(), p["pw_raw"].data_ptr(),
@@ -623,14 +645,23 @@ class Cell_Chain(nn.Module):
         """returns (inp + ops(inp) + sum(extras), records)."""
         s, recs = x, []
         n = len(self._ops)
+        rt.last_relu = None
         for i, m in enumerate(self._ops):
             op = m._op
             want = ([x] + list(extras)) if i == n - 1 else []
             fused, rest = want[:op.max_extras], want[op.max_extras:]
             inp = s
-            s, rec = op.fwd(rt, packs[i], s, fused)
+            relu_in, rt.last_relu = rt.last_relu, None
+            nxt = self._ops[i + 1]._op if i + 1 < n else None
+            rt.want_relu = isinstance(nxt, DilConv) and rt.tc_engine() and rt.dilconv_dense
+            if isinstance(op, DilConv):
+                s, rec = op.fwd(rt, packs[i], s, fused, x_relu=relu_in)
+            else:
+                s, rec = op.fwd(rt, packs[i], s, fused)
+            rt.want_relu = False
             if rest:
                 s = rt.add_all(s, rest)
+                rt.last_relu = None
             recs.append((inp if rt.save else None, rec))
         return s, recs
 
@@ -743,6 +774,9 @@ class Network_Fusion_Searched(nn.Module):
         #: activation storage: 'fp32' (default; TF32 tensor-core operands, max-abs 1e-3 tier) or 'bf16' (bf16 C8 maps
         #: and bf16 operands after the decomposition, fp32 accumulation; forward-only, north_star's 1e-2 tier)
         self.storage = 'fp32'
+        #: run DilConv as one dense k x k convolution on the tensor-core engine (needs relu(x) from the producing
+        #: op's epilogue; False keeps the FFMA depthwise+1x1 kernel, which is also what conv_engine='direct' uses)
+        self.dilconv_dense = True
         self._pack_cache = None
         self.last_launches = 0
         #: set to a list to collect (name, meta, start_event, end_event) for every kernel launch
@@ -813,6 +847,7 @@ class Network_Fusion_Searched(nn.Module):
         bf16 = self._bf16_storage(save)
         rt = _Runtime(B, H, W, self._C, ir.device, _lib.ENGINE_TCGEN05 if bf16 else self._engine(), save, bf16=bf16)
         rt.profile = self.profile
+        rt.dilconv_dense = self.dilconv_dense
         C = self._C
         feats, guides, gstats, feats16 = [], [], [], []
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):

@@ -107,6 +107,32 @@ def test_no_grad_forward_saves_nothing_and_grad_only_where_needed():
     assert all(p.grad is None for p in net.parameters())    # weight gradients are intentionally not produced
 
 
+@pytest.mark.parametrize("shape", [(1, 24, 40), (2, 120, 200)])
+def test_forward_backward_bit_deterministic(shape):
+    """No atomics, fixed-order partial sums: repeated forward+backward calls return identical bits (both DilConv
+    lowerings: dense on the tensor-core engine, and the FFMA depthwise+1x1 kernel)."""
+    B, H, W = shape
+    torch.manual_seed(0)
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at).to(DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    vis, ir = torch.rand(B, 3, H, W, generator=g).to(DEV), torch.rand(B, 1, H, W, generator=g).to(DEV)
+    cot = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    outs = {}
+    for dense in (False, True):
+        net.dilconv_dense = dense
+        runs = []
+        for _ in range(3):
+            a, v = ir.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+            out = net(a, v)
+            out.backward(cot)
+            runs.append((out.detach(), a.grad, v.grad))
+        for r in runs[1:]:
+            assert all(torch.equal(x, y) for x, y in zip(runs[0], r))
+        outs[dense] = runs[0]
+    # the two lowerings agree to TF32-operand accuracy
+    assert (outs[True][0] - outs[False][0]).abs().max().item() < 1e-3
+
+
 def test_full_size_forward_and_gradients_480x640():
     """BASELINE shape (480x640): forward against the CPU oracle, input gradients against the oracle's autograd,
     default ('auto' = tcgen05 TF32) engine; plus batch-position invariance with the full-size tiling (batch 17
