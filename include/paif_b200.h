@@ -92,6 +92,14 @@ int paif_eca_apply_bf16(const void* o, const void* x, const float* e, const floa
                         void* out, int C, int B, int H, int W, void* stream);
 int paif_out_forward_bf16(const void* feat, const float* wm, const float* slope, float* out,
                           int C, int B, int H, int W, void* stream);
+/* paif_out_forward with the interior pixels on the tcgen05 engine (TF32 or bf16 operands, fp32 accumulate): the
+ * merged 5x5 32->1 stencil is an implicit GEMM with its single output channel padded to 16 accumulator columns.
+ * w_mma: interior-class weights packed like a conv weight image with cout = 16 (channel 0 real, the rest zero):
+ *   storage F32 : [dx][4][2][dy][16 cout][4 cin] TF32-rounded fp32;  storage BF16: [dx][2][2][dy][16 cout][8 cin] bf16.
+ * wm: the 9-class fp32 weights of paif_out_forward (the one-pixel image border is recomputed exactly from them).
+ * pre_out may be NULL.  storage: PAIF_STORAGE_F32 (feat fp32 C4) or PAIF_STORAGE_BF16 (feat bf16 C8). */
+int paif_out_forward_tc(const void* feat, const void* w_mma, const float* wm, const float* slope,
+                        float* out, float* pre_out, int storage, int C, int B, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Generic dense "same"-padded stride-1 convolution over 1..3 concatenated C4 source maps

@@ -50,6 +50,7 @@ SIGNATURES = {
     "paif_spa_fused_forward_bf16": [_f, _i, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_eca_apply_bf16": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_out_forward_bf16": [_f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_out_forward_tc": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f],
     "paif_gf_guide_stats": [_f, _f, _i, _i, _i, _f],
     "paif_gf_decomp_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_conv_forward": [C.POINTER(ConvDesc), _f],

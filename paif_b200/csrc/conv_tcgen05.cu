@@ -51,20 +51,21 @@ struct TcPlan {
 
 // in_bf16: the sources are C8 bf16 maps (4 planes of 16-byte pixel vectors per 32-channel source instead of 8);
 // the byte geometry of rows, stages and B tiles is the same, there are just half as many planes / K steps.
-static bool tc_make_plan(int nsrc, int k, int dil, bool in_bf16, TcPlan* p) {
+// cp: accumulator columns per output row (32 = the 32-cout convolutions; 16 = the 1-cout stem_out stencil, padded).
+static bool tc_make_plan(int nsrc, int k, int dil, bool in_bf16, TcPlan* p, int cp = 32) {
     if (dil != 1 && dil != 2) return false;              // slot arithmetic uses shifts (log2 dil)
     if ((TC_SLOTS >> (dil >> 1)) < k) return false;      // the k rows fed by one input row need distinct slots
     const int taps = k * k;
     p->pad = dil * (k - 1) / 2;
     p->RW = TC_TW + 2 * p->pad;
     const int pps = in_bf16 ? 4 : 8;                     // planes per source
-    const int src_bytes = taps * pps * 512;              // weights of one source (32 cin x 32 cout per tap)
+    const int src_bytes = taps * pps * 16 * cp;          // weights of one source (32 cin x cp cout per tap)
     if (nsrc * src_bytes <= TC_WSLAB_MAX) { p->KQ = pps; p->npass = 1; p->gpp = nsrc; }
     else if (src_bytes <= TC_WSLAB_MAX) { p->KQ = pps; p->npass = nsrc; p->gpp = 1; }
     else if (!in_bf16 && src_bytes / 2 <= TC_WSLAB_MAX) { p->KQ = pps / 2; p->npass = nsrc * 2; p->gpp = 1; }
     else return false;
     p->gps = pps / p->KQ;
-    p->slab_bytes = p->gpp * taps * p->KQ * 512;
+    p->slab_bytes = p->gpp * taps * p->KQ * 16 * cp;
     p->unit_bytes = p->KQ * p->RW * 16;
     int stages = (TC_SMEM_BUDGET - p->slab_bytes - 1024) / p->unit_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -162,6 +163,27 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
         ::"r"(taddr), "r"(z) : "memory");
 }
 
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n\t"
+        "tcgen05.wait::st.sync.aligned;"
+        ::"r"(taddr), "r"(z) : "memory");
+}
+// first column of a 16-column accumulator slot (the only real output channel of the padded 1-cout stencil)
+__device__ __forceinline__ float tmem_ld16_first(uint32_t taddr) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    return __uint_as_float(r[0]);
+}
+
 // streaming 16-byte load that does not allocate in L1: with ~190 KB of shared memory per CTA only ~35 KB of L1
 // remain, far less than the epilogue's residual / mask loads in flight (8 warps x 24 x 512 B)
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
@@ -237,9 +259,13 @@ static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservati
 // (max(32 + N/4, N/2) cycles per MMA, scripts/mma_ubench2.cu) instead of ~150 cycles of address arithmetic per MMA.
 // ST = storage mode: 0 = fp32 C4 maps in and out (TF32 MMAs); 1 = bf16 C8 maps in and out (bf16 MMAs);
 // 2 = fp32 C4 sources (TF32 MMAs), bf16 C8 residuals / outputs (the layer that enters the bf16 part of the net).
-template <int K, int DIL, int KQ, bool PARTIALS, int ST>
+// CP = accumulator columns per output row: 32 for the 32-cout convolutions; 16 = single-output mode (stem_out's merged
+// 5x5 32->1 stencil with its cout padded to the smallest MMA N step): e.out / e.out_pre are [B][H][W] planes and the
+// epilogue is PReLU + tanh of channel 0.
+template <int K, int DIL, int KQ, bool PARTIALS, int ST, int CP = 32>
 __global__ void __launch_bounds__(TC_NT, 1)
 conv_tc_kernel(TcGeom g, EpiParams e) {
+    static_assert(CP == 32 || (CP == 16 && !PARTIALS), "accumulator slot width");
     constexpr bool IN_BF = ST == 1, OUT_BF = ST != 0;
     constexpr int PPS_IN = IN_BF ? 4 : 8;                      // 16-byte planes per 32-channel source map
     extern __shared__ __align__(128) unsigned char smem[];
@@ -384,7 +410,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         if (any_fetch && xin && grp < nrows) fetch_next(grp);
         if (grp == 0) {
             // accumulators start from zero: every MMA accumulates (the TMEM allocation holds garbage)
-            for (int sl = 0; sl < TC_SLOTS; ++sl) tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + sl * 32);
+            for (int sl = 0; sl < TC_SLOTS; ++sl) {
+                if constexpr (CP == 16) tmem_zero16(tmem_base + ((uint32_t)(wq * 32) << 16) + sl * CP);
+                else tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + sl * 32);
+            }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->zeroed));
         }
@@ -396,6 +425,19 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             const int slot = tc_slot(ro, dsh), use = ro / TC_SLOTS;
             TC_WAIT(mbar_wait(smem_u32(&bars->acc_full[slot]), use & 1));
             tc_fence_after();
+            if constexpr (CP == 16) {
+                const uint32_t ta = tmem_base + ((uint32_t)(wq * 32) << 16) + slot * CP;
+                const float acc = tmem_ld16_first(ta);
+                tmem_zero16(ta);
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->acc_empty[slot]));
+                if (xin) {
+                    const size_t pi = (size_t)b * plane + (size_t)(r0 + ro) * g.W + x;
+                    if (e.out_pre) e.out_pre[pi] = acc;
+                    e.out[pi] = tanhf(prelu_f(acc, a));
+                }
+                continue;
+            }
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32, v);
             tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32);
@@ -511,7 +553,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             constexpr uint32_t plane_bytes = RW * 16;
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
             const uint64_t a_desc0 = make_desc(0, plane_bytes, 128);
-            const uint64_t b_desc0 = make_desc(0, (uint32_t)k * 512, 128);       // 16-B k-chunks are k*32 rows apart
+            const uint64_t b_desc0 = make_desc(0, (uint32_t)k * CP * 16, 128);   // 16-B k-chunks are k*CP rows apart
             constexpr int nk8 = KQ / 2;
             constexpr int spr = TC_SLOTS >> dsh;
             TC_PROF_DECL;
@@ -552,28 +594,28 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                                 // descriptors differ only in the 14-bit start-address field (units of 16 B); the
                                 // per-(dx, k8) offsets below are immediates after unrolling
                                 const uint32_t a_lo = (ring_base + stage * UNIT) >> 4;
-                                const uint32_t w_lo = ((w_base + (uint32_t)gl * (k * nk8 * k * 1024)) >> 4) + dy_lo * 32;
-                                const uint32_t d0 = tmem_base + s0 * 32;
-                                const uint32_t id0 = tc_idesc(32u * n1, IN_BF ? 1u : 2u);
+                                const uint32_t w_lo = ((w_base + (uint32_t)gl * (k * nk8 * k * CP * 32)) >> 4) + dy_lo * CP;
+                                const uint32_t d0 = tmem_base + s0 * CP;
+                                const uint32_t id0 = tc_idesc((uint32_t)CP * n1, IN_BF ? 1u : 2u);
 #pragma unroll
                                 for (int dx = 0; dx < k; ++dx)
 #pragma unroll
                                     for (int k8 = 0; k8 < nk8; ++k8) {
                                         const uint64_t ad = a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW);
-                                        const uint64_t bd = b_desc0 | (uint64_t)(w_lo + (dx * nk8 + k8) * k * 64);
+                                        const uint64_t bd = b_desc0 | (uint64_t)(w_lo + (dx * nk8 + k8) * k * 2 * CP);
                                         if constexpr (IN_BF) tc_mma_bf16(d0, ad, bd, id0, 1u);
                                         else tc_mma_tf32(d0, ad, bd, id0, 1u);
                                     }
                                 if (n1 < ndy) {                           // the slot ring wrapped: remaining taps start at s1
-                                    const uint32_t d1 = tmem_base + s1 * 32;
-                                    const uint32_t id1 = tc_idesc(32u * (ndy - n1), IN_BF ? 1u : 2u);
-                                    const uint32_t w_l1 = w_lo + n1 * 32;
+                                    const uint32_t d1 = tmem_base + s1 * CP;
+                                    const uint32_t id1 = tc_idesc((uint32_t)CP * (ndy - n1), IN_BF ? 1u : 2u);
+                                    const uint32_t w_l1 = w_lo + n1 * CP;
 #pragma unroll
                                     for (int dx = 0; dx < k; ++dx)
 #pragma unroll
                                         for (int k8 = 0; k8 < nk8; ++k8) {
                                             const uint64_t ad = a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW);
-                                            const uint64_t bd = b_desc0 | (uint64_t)(w_l1 + (dx * nk8 + k8) * k * 64);
+                                            const uint64_t bd = b_desc0 | (uint64_t)(w_l1 + (dx * nk8 + k8) * k * 2 * CP);
                                             if constexpr (IN_BF) tc_mma_bf16(d1, ad, bd, id1, 1u);
                                             else tc_mma_tf32(d1, ad, bd, id1, 1u);
                                         }
@@ -863,6 +905,37 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
 #undef TC_CASE
     set_error("conv_tc: no kernel instance for k=%d dil=%d KQ=%d storage=%d", d.kh, d.dil, g.plan.KQ, d.storage);
     return PAIF_ENOTSUP;
+}
+
+// stem_out's merged 5x5 32->1 stencil (interior-class weights) + PReLU + tanh on the engine: single-output mode (CP = 16).
+// feat: fp32 C4 map, or bf16 C8 map when bf16 != 0; wmma: the 5x5 weights packed like any other weight image with the
+// output channel padded to 16 (channel 0 real).  The one-pixel image border is redone by out_border_kernel afterwards.
+int out_tc_launch(const void* feat, const void* wmma, const float* slope, float* out, float* pre_out,
+                  int bf16, int B, int H, int W, cudaStream_t stream) {
+    TcGeom g;
+    if (!tc_make_plan(1, 5, 1, bf16 != 0, &g.plan, 16)) { set_error("out_tc: no plan"); return PAIF_ENOTSUP; }
+    PaifConvDesc d = {};
+    d.B = B; d.H = H; d.W = W;
+    g.B = B; g.H = H; g.W = W; g.nsrc = 1; g.k = 5; g.dil = 1;
+    g.RCH = tc_rows_per_cta(d, g.plan);
+    g.tiles_alloc = 0;
+    g.src[0] = feat; g.src[1] = g.src[2] = nullptr;
+    g.wmma = wmma;
+    EpiParams e = {};
+    e.slope = slope; e.post_scale = 1.f; e.out = out; e.out_pre = pre_out; e.H = H; e.W = W;
+    dim3 grid(cdiv(W, TC_TW), cdiv(H, g.RCH), B);
+    static unsigned long long attr_done = 0;
+    int dev;
+    if (attr_needed(attr_done, &dev)) {
+        cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<5, 1, 8, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
+        if (err == cudaSuccess)
+            err = cudaFuncSetAttribute(conv_tc_kernel<5, 1, 4, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
+        if (err != cudaSuccess) { set_error("out_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; }
+        attr_mark(attr_done, dev);
+    }
+    if (bf16) conv_tc_kernel<5, 1, 4, false, 1, 16><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);
+    else conv_tc_kernel<5, 1, 8, false, 0, 16><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);
+    return check_launch("paif_out_forward_tc");
 }
 
 #ifdef PAIF_TC_PROFILE

@@ -1083,6 +1083,25 @@ extern "C" int paif_out_forward(const float* feat, const float* wm, const float*
     return check_launch("paif_out_forward");
 }
 
+namespace paif {
+int out_tc_launch(const void* feat, const void* wmma, const float* slope, float* out, float* pre_out,
+                  int bf16, int B, int H, int W, cudaStream_t stream);
+}
+
+extern "C" int paif_out_forward_tc(const void* feat, const void* w_mma, const float* wm, const float* slope,
+                                   float* out, float* pre_out, int storage, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(feat && w_mma && wm && slope && out, "null pointer");
+    PAIF_REQUIRE(C == OUT_C, "C must be 32");
+    PAIF_REQUIRE(H >= 2 && W >= 2, "H, W must be >= 2");
+    PAIF_REQUIRE(storage == PAIF_STORAGE_F32 || storage == PAIF_STORAGE_BF16, "storage must be F32 or BF16");
+    PAIF_REQUIRE(B > 0 && B <= 65535, "B out of range");
+    if (int r = out_tc_launch(feat, w_mma, slope, out, pre_out, storage == PAIF_STORAGE_BF16, B, H, W, ST)) return r;
+    const dim3 bgrid(cdiv(2 * W + 2 * (H - 2), 128), B);
+    if (storage == PAIF_STORAGE_BF16) out_border_kernel<true><<<bgrid, 128, 0, ST>>>(feat, wm, slope, out, pre_out, H, W);
+    else out_border_kernel<false><<<bgrid, 128, 0, ST>>>(feat, wm, slope, out, pre_out, H, W);
+    return check_launch("paif_out_forward_tc");
+}
+
 extern "C" int paif_out_forward_bf16(const void* feat, const float* wm, const float* slope, float* out,
                                      int C, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(feat && wm && slope && out, "null pointer");

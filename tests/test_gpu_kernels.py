@@ -6,6 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+import paif_b200
 from oracle import fusion_oracle as fo
 from paif_b200 import _lib, fusion
 
@@ -254,3 +255,39 @@ def test_conv_tcgen05_full_size_tiling(k, dil, nsrc):
     for i in range(2):
         err = (outs[_lib.ENGINE_TCGEN05][i] - outs[_lib.ENGINE_DIRECT][i]).abs().max().item()
         assert err < 2.0 ** -9 * max(scale, 1.0), (i, err, scale)
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 45), (1, 70, 300), (3, 33, 128)])
+def test_stem_out_on_tensor_cores_matches_ffma_kernel(shape):
+    """paif_out_forward_tc (interior pixels as an implicit GEMM with TF32 / bf16 operands, border pixels exact) against
+    the exact-fp32 stencil kernel on the same features."""
+    B, H, W = shape
+    torch.manual_seed(9)
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at).to(DEV).eval()
+    with torch.no_grad():
+        net.stem_out[0].weight.mul_(3.0)                    # default init gives tiny outputs; make the test bite
+    p = net._packed(False)
+    x = torch.randn(B, 32, H, W)
+    x4 = to_c4(x).to(DEV)
+    o_ref, pre_ref = torch.empty(B, 1, H, W, device=DEV), torch.empty(B, H, W, device=DEV)
+    _lib.call("paif_out_forward", x4.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(), o_ref.data_ptr(),
+              pre_ref.data_ptr(), 32, B, H, W, stream())
+    o_tc, pre_tc = torch.full_like(o_ref, float("nan")), torch.full_like(pre_ref, float("nan"))
+    _lib.call("paif_out_forward_tc", x4.data_ptr(), p["out_mma"].data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(),
+              o_tc.data_ptr(), pre_tc.data_ptr(), _lib.STORAGE_F32, 32, B, H, W, stream())
+    scale = pre_ref.abs().max().item()
+    assert scale > 0.05
+    assert (pre_tc - pre_ref).abs().max().item() < 2.0 ** -9 * max(scale, 1.0)
+    assert (o_tc - o_ref).abs().max().item() < 2.0 ** -9 * max(scale, 1.0)
+    # the one-pixel border is computed by the exact kernel in both paths
+    for sl in ((slice(None), 0), (slice(None), H - 1), (slice(None), slice(None), 0), (slice(None), slice(None), W - 1)):
+        assert torch.equal(pre_tc[sl], pre_ref[sl])
+    # bf16 feature map
+    x16 = x.to(torch.bfloat16)
+    xc8 = x16.reshape(B, 4, 8, H, W).permute(0, 1, 3, 4, 2).contiguous().to(DEV)
+    x4b = to_c4(x16.float()).to(DEV)
+    _lib.call("paif_out_forward", x4b.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(), o_ref.data_ptr(),
+              pre_ref.data_ptr(), 32, B, H, W, stream())
+    _lib.call("paif_out_forward_tc", xc8.data_ptr(), p["out_mma16"].data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(),
+              o_tc.data_ptr(), None, _lib.STORAGE_BF16, 32, B, H, W, stream())
+    assert (o_tc - o_ref).abs().max().item() < 2.0 ** -7 * max(scale, 1.0)          # bf16-rounded weights
