@@ -1,5 +1,5 @@
 """Development tool: role timeline of the tcgen05 conv engine (wait vs busy cycles per role), using the
--DPAIF_TC_PROFILE build.  PAIF_B200_PROFILE_LIB=1 python scripts/tc_timeline.py"""
+-DPAIF_TC_PROFILE build.  python -m paif_b200.build --profile; PAIF_B200_PROFILE_LIB=1 python scripts/tc_timeline.py [--bf16]"""
 import ctypes, os, sys
 os.environ["PAIF_B200_PROFILE_LIB"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,13 +9,15 @@ lib = _lib.load()
 lib.paif_debug_tc_counters.argtypes = [ctypes.c_void_p, ctypes.c_int]
 DEV = torch.device("cuda:0")
 B, H, W = 16, 480, 640
-rt = fusion._Runtime(B, H, W, 32, DEV, _lib.ENGINE_TCGEN05, False)
+BF16 = "--bf16" in sys.argv                      # bf16 storage mode: C8 maps, kind::f16 MMAs
+rt = fusion._Runtime(B, H, W, 32, DEV, _lib.ENGINE_TCGEN05, False, bf16=BF16)
 buf = (ctypes.c_ulonglong * 16)()
 def counters(reset=1):
     lib.paif_debug_tc_counters(buf, reset)
     return list(buf)
 torch.manual_seed(0)
-maps = [torch.randn(B, 8, H, W, 4, device=DEV) for _ in range(6)]
+maps = [torch.randn(B, 4, H, W, 8, device=DEV).to(torch.bfloat16) if BF16 else torch.randn(B, 8, H, W, 4, device=DEV)
+        for _ in range(6)]
 a = torch.tensor([0.25], device=DEV)
 cases = [("k3 cin32 prelu", 1, 3, 1, dict(slope=a)),
          ("k3 cin96 prelu+3res", 3, 3, 1, dict(slope=a, post_scale=0.333, post_res=maps[3:6])),
