@@ -43,7 +43,9 @@ struct TcPlan {
     int gpp;           // K-groups per pass
     int RW;            // halo'd row width in pixels
     int pad;
-    int unit_bytes;    // one ring stage
+    int unit_bytes;    // one K-group of one halo'd input row
+    int upr;           // units per ring stage: gpp (a whole input row of the pass: one barrier round trip per row) or 1
+    int stage_bytes;   // upr * unit_bytes
     int slab_bytes;    // resident weight slab per pass
     int stages;
     int smem_bytes;
@@ -67,11 +69,17 @@ static bool tc_make_plan(int nsrc, int k, int dil, bool in_bf16, TcPlan* p, int 
     p->gps = pps / p->KQ;
     p->slab_bytes = p->gpp * taps * p->KQ * 16 * cp;
     p->unit_bytes = p->KQ * p->RW * 16;
-    int stages = (TC_SMEM_BUDGET - p->slab_bytes - 1024) / p->unit_bytes;
+    // A ring stage holds a whole input row of the pass when at least 4 such rows fit (the MMA issuer then waits and
+    // commits once per row instead of once per K-group); otherwise one K-group per stage, released as it retires.
+    const int room = TC_SMEM_BUDGET - p->slab_bytes - 1024;
+    // (1x1 layers are HBM-bound with 4 MMAs per K-group: finer release granularity wins there, measured 0.396 vs 0.415 ms)
+    p->upr = (k > 1 && room / (p->gpp * p->unit_bytes) >= 4) ? p->gpp : 1;
+    p->stage_bytes = p->upr * p->unit_bytes;
+    int stages = room / p->stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 2) return false;
     p->stages = stages;
-    p->smem_bytes = p->slab_bytes + stages * p->unit_bytes + 1024;
+    p->smem_bytes = p->slab_bytes + stages * p->stage_bytes + 1024;
     return true;
 }
 
@@ -272,7 +280,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     const TcPlan& P = g.plan;
     unsigned char* s_w = smem;                                 // weight slab
     unsigned char* s_ring = smem + P.slab_bytes;               // input ring
-    TcBars* bars = reinterpret_cast<TcBars*>(s_ring + P.stages * P.unit_bytes);   // (P.unit_bytes == UNIT, set by the host)
+    TcBars* bars = reinterpret_cast<TcBars*>(s_ring + P.stages * P.stage_bytes);  // (P.unit_bytes == UNIT, set by the host)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x0 = blockIdx.x * TC_TW, r0 = blockIdx.y * g.RCH, b = blockIdx.z;
@@ -304,7 +312,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     }
     if (npx < RW) {
         // image-border strip: zero the columns no bulk copy will ever write (the conv's zero padding)
-        const int nplanes = P.stages * KQ;
+        const int nplanes = P.stages * P.upr * KQ;
         const int nzero = RW - npx;
         for (int i = tid; i < nplanes * nzero; i += TC_NT) {
             const int pl = i / nzero, j = i - pl * nzero;
@@ -588,12 +596,15 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                             }
                         }
                         if (yok) {
-                            TC_WAIT(mbar_wait(smem_u32(&bars->full[stage]), phase));
-                            tc_fence_after();
+                            const int us = P.upr == 1 ? 0 : gl;                 // unit inside the ring stage
+                            if (us == 0) {
+                                TC_WAIT(mbar_wait(smem_u32(&bars->full[stage]), phase));
+                                tc_fence_after();
+                            }
                             if (ndy > 0 && elect_one()) {
                                 // descriptors differ only in the 14-bit start-address field (units of 16 B); the
                                 // per-(dx, k8) offsets below are immediates after unrolling
-                                const uint32_t a_lo = (ring_base + stage * UNIT) >> 4;
+                                const uint32_t a_lo = (ring_base + stage * P.stage_bytes + us * UNIT) >> 4;
                                 const uint32_t w_lo = ((w_base + (uint32_t)gl * (k * nk8 * k * CP * 32)) >> 4) + dy_lo * CP;
                                 const uint32_t d0 = tmem_base + s0 * CP;
                                 const uint32_t id0 = tc_idesc((uint32_t)CP * n1, IN_BF ? 1u : 2u);
@@ -622,8 +633,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                                 }
                             }
                             __syncwarp();
-                            if (elect_one()) tc_commit(smem_u32(&bars->empty[stage]));   // stage reusable once these MMAs retire
-                            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                            if (us == P.upr - 1) {
+                                if (elect_one()) tc_commit(smem_u32(&bars->empty[stage]));   // stage reusable once these MMAs retire
+                                if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                            }
                         }
                         if (pass == P.npass - 1 && gl == P.gpp - 1) {
                             const int rdone = ri - (k - 1) * dil;           // output row whose last tap row just passed
@@ -661,20 +674,23 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                     const int y = r0 - pad + ri;
                     if (y < 0 || y >= g.H) continue;             // zero padding rows: skipped by the MMA issuer too
                     for (int gl = 0; gl < P.gpp; ++gl) {
-                        TC_WAIT(mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u));
+                        const int us = P.upr == 1 ? 0 : gl;      // unit inside the ring stage
+                        if (us == 0) {
+                            TC_WAIT(mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u));
+                            if (elect_one()) mbar_expect_tx(smem_u32(&bars->full[stage]), row_bytes * KQ * P.upr);
+                        }
                         const int gk = pass * P.gpp + gl;        // global K-group
                         constexpr int GPS = PPS_IN / KQ;         // K-groups per source (1 or 2)
                         const int s = GPS == 1 ? gk : gk >> 1, qoff = GPS == 1 ? 0 : (gk & 1) * KQ;
                         const float4* sp = reinterpret_cast<const float4*>(g.src[s]) + ((size_t)b * PPS_IN + qoff) * plane
                                            + (size_t)y * g.W + xs;
-                        const uint32_t dst = smem_u32(s_ring) + stage * UNIT + poff * 16;
+                        const uint32_t dst = smem_u32(s_ring) + stage * P.stage_bytes + us * UNIT + poff * 16;
                         const uint32_t bar = smem_u32(&bars->full[stage]);
                         if (elect_one()) {
-                            mbar_expect_tx(bar, row_bytes * KQ);
 #pragma unroll
                             for (int q = 0; q < KQ; ++q) bulk_g2s(dst + q * RW * 16, sp + (size_t)q * plane, row_bytes, bar);
                         }
-                        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                        if (us == P.upr - 1 && ++stage == P.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
