@@ -115,7 +115,8 @@ def full_summary(reps, out_txt, out_json, traffic_json, note):
             f.write("%-38s %8.1f %8.3f %8.3f %7.1f %8.1f %7.1f %7.1f %5.0f  %s\n" % (
                 r["kernel"][:38], r["dur_us"], r["dram_read_bytes"] / 1e9, r["dram_write_bytes"] / 1e9, r["dram_pct"],
                 r["tensor_pct"], r["warps_pct"], r["issue_pct"], r["regs"], r["grid"]))
-    conv = [r for r in recs if r["kernel"].startswith("conv_tc_kernel")]
+    # the 32-cout convolutions (what bench.py's roofline counts); the single-output stem_out instance (<..., 16>) is listed but not averaged
+    conv = [r for r in recs if r["kernel"].startswith("conv_tc_kernel") and not r["kernel"].rstrip().endswith(", 16>")]
     if conv and traffic_json:
         per = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in conv) / len(conv)
         old = {}
