@@ -41,3 +41,21 @@ for name, nsrc, k, dil, kw in cases:
         return c[2 * i] / max(c[2 * i + 1], 1)
     print("%-30s %.3f ms | epilogue warps: wait %.0f%% of %.0f kcyc | mma warps: wait %.0f%% of %.0f kcyc | producer: wait %.0f%% of %.0f kcyc" % (
         name, ms, 100 * f(0, 8), c[1] / (8 * ctas) / 1e3, 100 * f(1, 4), c[3] / (4 * ctas) / 1e3, 100 * f(2, 1), c[5] / ctas / 1e3), flush=True)
+
+# stem_out on the engine (single-output mode)
+import paif_b200
+net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at).to(DEV).eval()
+p = net._packed(False)
+out = torch.empty(B, 1, H, W, device=DEV)
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+args = (maps[0].data_ptr(), (p["out_mma16"] if BF16 else p["out_mma"]).data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(),
+        out.data_ptr(), None, _lib.STORAGE_BF16 if BF16 else _lib.STORAGE_F32, 32, B, H, W, st)
+for _ in range(2):
+    _lib.call("paif_out_forward_tc", *args)
+counters()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); _lib.call("paif_out_forward_tc", *args); e1.record()
+torch.cuda.synchronize()
+c = counters()
+print("stem_out k5 CP16: %.3f ms | epilogue wait %.0f%% of %.0f kcyc-total | mma wait %.0f%% | producer wait %.0f%%" % (
+    e0.elapsed_time(e1), 100 * c[0] / max(c[1], 1), c[1] / 1e3, 100 * c[2] / max(c[3], 1), 100 * c[4] / max(c[5], 1)))
