@@ -304,9 +304,25 @@ def run_ours(args):
             return net(ir_d, vis_d)
 
     # end to end: host buffers in, host buffer out, through the public nn.Module call.  The H2D copies of step
-    # i+1 and the D2H copy of step i run on a copy stream while the kernels of step i run on the compute stream
-    # (two device input slots); every step's copies are issued inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
+    # i+1 and the D2H copy of step i run on their own streams (the two PCIe directions are independent) while the
+    # kernels of step i run on the compute stream (two device input slots); every step's copies are issued inside
+    # the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)          # host -> device
+    d2h_stream = torch.cuda.Stream(device=dev)           # device -> host
+
+    def probe_gbs(dst, src, stream):
+        """one timed pinned copy: reported next to e2e so that a slow PCIe path on a box is visible in the line"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            dst.copy_(src, non_blocking=True)
+            e0.record(stream)
+            dst.copy_(src, non_blocking=True)
+            e1.record(stream)
+        e1.synchronize()
+        return src.numel() * src.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    h2d_gbs = probe_gbs(torch.empty_like(vis_d), vis_h, copy_stream)
+    d2h_gbs = probe_gbs(out_h, torch.empty(B, 1, H, W, device=dev), d2h_stream)
     slots = [(torch.empty_like(ir_d), torch.empty_like(vis_d)) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]      # inputs of slot landed
     freed = [torch.cuda.Event() for _ in range(2)]      # kernels that read slot finished
@@ -333,14 +349,15 @@ def run_ours(args):
         freed[cur].record(main)
         done = torch.cuda.Event()
         done.record(main)
-        out.record_stream(copy_stream)                       # keep the allocator from recycling it under the copy
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
+        out.record_stream(d2h_stream)                        # keep the allocator from recycling it under the copy
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
             out_h.copy_(out, non_blocking=True)              # D2H of the fused images
         state["i"] += 1
 
     def e2e_drain():
         torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        torch.cuda.current_stream(dev).wait_stream(d2h_stream)
 
     # per-step working set (> 30 fp32 maps of B*39 MB) is far larger than the 126 MB L2
     for _ in range(max(args.warmup, 3)):
@@ -482,7 +499,11 @@ def run_ours(args):
                    "l2": "per-step working set (>30 fp32 maps x %.0f MB) exceeds the 126 MB L2; no flush needed" % (B * H * W * 128 / 1e6),
                    "parallelism": "dp%d (independent batches, no data-path collective)" % world},
         "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(ir_h.numel() * 4 + vis_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                "h2d_bytes_per_step": int(ir_h.numel() * 4 + vis_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
+                "pinned": bool(ir_h.is_pinned() and vis_h.is_pinned() and out_h.is_pinned()),
+                "h2d_gbs": h2d_gbs, "d2h_gbs": d2h_gbs,
+                "note": "H2D of step i+1 and D2H of step i overlap the kernels of step i (separate copy streams); "
+                        "h2d_gbs / d2h_gbs = this box's pinned PCIe copy rates"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "dense-conv engine conv_tc_kernel (all %d conv launches per step)" % (len(conv) // max(args.steps, 1)),
                      "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
