@@ -10,8 +10,10 @@
 //    (cp.async.bulk, one contiguous copy per quad plane) through a shared-memory ring; each input row is used by all
 //    k*k taps on arrival.  Input row ri feeds output rows ri - dy*dil (dy = 0..k-1): their accumulators sit in
 //    CONSECUTIVE 32-column TMEM slots, so all dy taps of one (dx, 8 input channels) are ONE tcgen05.mma with
-//    N = 32*k (B tile rows = (dy, cout)).  A tcgen05.mma occupies its issuing thread for >= 91 cycles whatever its
-//    size (scripts/mma_ubench.cu), so wide N is what makes a single issuer HBM-bound instead of issue-bound.
+//    N = 32*k (B tile rows = (dy, cout)).  tcgen05.mma issue is blocking — the issuing thread stays at most ~1 MMA
+//    ahead of the pipe, an M128 K8 MMA costs max(32 + N/4, N/2) cycles, and every cycle of issuer-side work between
+//    MMAs adds to the row time (scripts/mma_ubench2.cu, mma_ubench3.cu) — so few wide MMAs issued straight-line are
+//    what keeps a single issuer from pacing the kernel.
 //    Accumulators form a 16-slot ring in TMEM (512 columns), so input is read once (+x/y halo); slots are
 //    zeroed by the epilogue after it drains them, every MMA accumulates.
 //  * Weights (TF32-rounded, pre-packed as UMMA B tiles) stay resident in shared memory; when they do
