@@ -144,6 +144,113 @@ __global__ void __launch_bounds__(160, 1) ubench(int rows, long long* out, const
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// The conv kernel's issuer-loop skeleton around the same 12 MMAs, one element at a time (warp-uniform loop, elected lane
+// issues).  SK bit 0: mbarrier try_wait on an already-complete phase + tcgen05.fence::after   bit 1: elect.sync +
+// __syncwarp around the issue   bit 2: second elect + commit(empty)   bit 3: third elect + commit(acc_full)
+// bit 4: the row bookkeeping arithmetic (tap range, slot ring position, wrap split)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int slot_of(int ro) { return 15 - (ro & 15); }
+template <int SK>
+__global__ void __launch_bounds__(160, 1) skeleton(int rows, long long* out, int nrows_chunk) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar, ready, scratch[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 200 * 1024 / 4; i += 160) reinterpret_cast<float*>(smem)[i] = 0.001f * (i & 255);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&ready)), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&scratch[0])), "r"(1u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&scratch[1])), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+    if (warp == 0) {
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem) + 100 * 1024;
+        const uint64_t a_desc0 = make_desc(0, RW * 16, 128), b_desc0 = make_desc(0, 3 * 512, 128);
+        const long long t0 = clock64();
+        int stage = 0;
+        for (int r = 0; r < rows; ++r) {
+            const int ri = r % (nrows_chunk + 2);
+            int dy_lo = 0, ndy = 3, s0 = 0, n1 = 3, s1 = 0;
+            if (SK & 16) {
+                dy_lo = ri > nrows_chunk - 1 ? ri - (nrows_chunk - 1) : 0;
+                const int dy_hi = min(2, ri);
+                ndy = dy_hi - dy_lo + 1;
+                const int ro_top = ri - dy_lo;
+                s0 = slot_of(ro_top);
+                n1 = min(ndy, 16 - s0);
+            }
+            if (SK & 1) {
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(smem_u32(&ready)), "r"(1u) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            if (((SK & 2) ? elect_one() : (tid == 0)) && ndy > 0) {
+                const uint32_t a_lo = (a0 + stage * 16640) >> 4;
+                const uint32_t w_lo = (b0 >> 4) + dy_lo * 32;
+                const uint32_t d0 = tmem_base + s0 * 32;
+                const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((32 * n1) >> 3) << 17) | ((128u >> 4) << 24);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                    for (int k8 = 0; k8 < 4; ++k8)
+                        mma(d0, a_desc0 | (uint64_t)(a_lo + dx + k8 * 2 * RW), b_desc0 | (uint64_t)(w_lo + (dx * 4 + k8) * 192), idesc);
+                if (n1 < ndy) {
+                    const uint32_t id1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((32 * (ndy - n1)) >> 3) << 17) | ((128u >> 4) << 24);
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8)
+                            mma(tmem_base + s1 * 32, a_desc0 | (uint64_t)(a_lo + dx + k8 * 2 * RW),
+                                b_desc0 | (uint64_t)(w_lo + n1 * 32 + (dx * 4 + k8) * 192), id1);
+                }
+            }
+            if (SK & 2) __syncwarp();
+            if ((SK & 4) && elect_one()) commit(smem_u32(&scratch[0]));
+            if (++stage == 4) stage = 0;
+            if ((SK & 8) && elect_one()) commit(smem_u32(&scratch[1]));
+        }
+        if (tid == 0) {
+            commit(smem_u32(&bar));
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+            out[blockIdx.x] = clock64() - t0;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+template <int SK>
+void run_skeleton(long long* d_out, const char* what) {
+    const int rows = 3000;
+    cudaFuncSetAttribute(skeleton<SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    for (int rep = 0; rep < 2; ++rep) skeleton<SK><<<148, 160, 210 * 1024>>>(rows, d_out, 69);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("skeleton %d: CUDA error %s\n", SK, cudaGetErrorString(e)); return; }
+    std::vector<long long> t(148);
+    cudaMemcpy(t.data(), d_out, 148 * 8, cudaMemcpyDeviceToHost);
+    std::sort(t.begin(), t.end());
+    printf("skeleton %2d  %-66s %.0f cycles per row (12 MMAs = 672)\n", SK, what, (double)t[74] / rows);
+}
+
 template <int MODE>
 void run(long long* d_out, const float* gsrc, const char* what) {
     const int rows = 3000;
@@ -178,5 +285,11 @@ int main() {
         std::sort(t.begin(), t.begin() + 148);
         printf("issuer busy %3d cycles between rows of 12 MMAs (672 cycles of tensor work): %.0f cycles per row\n", delay, (double)t[74] / 3000.0);
     }
+    run_skeleton<0>(d_out, "single thread, nothing but the MMAs");
+    run_skeleton<2>(d_out, "warp-uniform loop, elect.sync + __syncwarp");
+    run_skeleton<3>(d_out, "+ try_wait on a complete phase + tcgen05.fence::after");
+    run_skeleton<7>(d_out, "+ elect + commit(empty)");
+    run_skeleton<15>(d_out, "+ elect + commit(acc_full)");
+    run_skeleton<31>(d_out, "+ row bookkeeping (tap range, slot, ring-wrap split)");
     return 0;
 }
