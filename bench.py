@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--bwd-steps", type=int, default=3, help="timed forward+backward-to-input steps (0 = skip)")
     ap.add_argument("--bf16-steps", type=int, default=5,
                     help="timed forward steps in the bf16 storage mode (SURVEY 8 config D's precision tier; 0 = skip)")
+    ap.add_argument("--eager-steps", type=int, default=3,
+                    help="timed steps of the stock-PyTorch eager baseline on the same GPU (rank 0, N=1 only; 0 = skip)")
     ap.add_argument("--pgd-consumer-bf16", action="store_true", help="run the stock consumer under bf16 autocast")
     ap.add_argument("--pgd-eager", action="store_true", help="PGD leg without CUDA-graph replay of the PGD iteration")
     ap.add_argument("--pgd-frames", type=int, default=4,
@@ -146,6 +148,29 @@ def cpu_port_pairs_per_s(steps, H, W, warmup=1):
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     return steps / sum(times), cores, times
+
+
+def torch_eager_gpu_pairs_per_s(dev, B, H, W, steps=3):
+    """SURVEY.md 8d's second reported baseline: the reference's operator structure in STOCK PyTorch CUDA ops (the oracle
+    port: F.conv2d / cat / cumsum box filters, fp32, cuDNN with PyTorch's default TF32 setting) on the same B200.
+    A baseline leg only — the oracle never runs on the product path."""
+    import torch
+    import paif_b200
+    from oracle import fusion_oracle as fo
+    _, sd = synth_state()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    ir, vis = synth_inputs(B, H, W)
+    ir, vis = ir.to(dev), vis.to(dev)
+    with torch.no_grad():
+        fo.fusion_forward(sd, paif_b200.fusion_at, ir, vis)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fo.fusion_forward(sd, paif_b200.fusion_at, ir, vis)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    return B * steps / (e0.elapsed_time(e1) * 1e-3)
 
 
 class SyntheticFrames:
@@ -520,6 +545,16 @@ def run_ours(args):
         line["fwd_bwd"] = fwd_bwd
     if bf16_leg is not None:
         line["bf16_storage"] = bf16_leg
+    if args.eager_steps > 0 and world == 1:
+        eb = min(B, 4)                                       # eager keeps ~25 map-sized temporaries per guided filter
+        try:
+            torch.cuda.empty_cache()
+            line["torch_eager_same_gpu"] = {
+                "value": torch_eager_gpu_pairs_per_s(dev, eb, H, W, args.eager_steps), "unit": "pairs/s", "batch": eb,
+                "what": "the reference's operator structure in stock PyTorch CUDA ops (oracle port, fp32, no_grad) on "
+                        "this GPU: the eager implementation a user of the reference runs today; reported, not a target"}
+        except Exception as ex:                              # a baseline leg must never take the bench line down
+            line["torch_eager_same_gpu"] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
     if pgd is not None:
         line["pgd10"] = pgd
     if not args.no_cpu_baseline and world == 1:
