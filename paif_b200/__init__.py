@@ -5,9 +5,9 @@
 ``test_original.py`` / ``robust_test.py`` pick it up unchanged.
 """
 from .genotypes import Genotype, fusion_at
-from .fusion import Network_Fusion_Searched
+from .fusion import Network_Fusion_Searched, Network_Fusion_Searched_showfeatures
 
-__all__ = ["Network_Fusion_Searched", "Genotype", "fusion_at", "install"]
+__all__ = ["Network_Fusion_Searched", "Network_Fusion_Searched_showfeatures", "Genotype", "fusion_at", "install"]
 
 
 def install(module=None):
@@ -19,4 +19,6 @@ def install(module=None):
     if module is None:
         import core.model_fusion_auto as module
     module.Network_Fusion_Searched = Network_Fusion_Searched
+    if hasattr(module, "Network_Fusion_Searched_showfeatures"):
+        module.Network_Fusion_Searched_showfeatures = Network_Fusion_Searched_showfeatures
     return module

@@ -849,8 +849,9 @@ class Network_Fusion_Searched(nn.Module):
         return {'auto': _lib.ENGINE_AUTO, 'direct': _lib.ENGINE_DIRECT, 'tcgen05': _lib.ENGINE_TCGEN05}[self.conv_engine]
 
     # -------------------------------------------------------------------------------------
-    def _run_forward(self, ir, vis, save):
-        """ir, vis: [B,1,H,W] fp32 CUDA views (any strides).  Returns (out[B,1,H,W], saved)."""
+    def _run_forward(self, ir, vis, save, capture=None):
+        """ir, vis: [B,1,H,W] fp32 CUDA views (any strides).  Returns (out[B,1,H,W], saved).
+        ``capture``: optional dict that receives the intermediate maps ``forward2`` returns (fp32 storage only)."""
         B, _, H, W = ir.shape
         p = self._packed(save)
         bf16 = self._bf16_storage(save)
@@ -883,6 +884,8 @@ class Network_Fusion_Searched(nn.Module):
             gstats.append(stats if save else None)
             del stats
             x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i], src_fp32=True)[0]
+            if capture is not None:
+                capture.setdefault("lf", []).append((lf1, lf2))
             del lf1, lf2
             o, recs = chain.fwd(rt, packs, x, [feats16[i] if bf16 else feats[i]])
             branch_out.append(o)
@@ -911,6 +914,8 @@ class Network_Fusion_Searched(nn.Module):
             rt.call("paif_out_forward", f2.data_ptr(), p["out_wm"].data_ptr(), p["out_a"].data_ptr(), out.data_ptr(),
                     _ptr(pre_out), C, B, H, W)
         self.last_launches = rt.launches
+        if capture is not None:
+            capture.update(feats=feats, guides=guides, branch_out=branch_out)
         saved = None
         if save:
             saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, gstats=gstats, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
@@ -993,7 +998,7 @@ class Network_Fusion_Searched(nn.Module):
         return gs
 
     # -------------------------------------------------------------------------------------
-    def forward(self, ir, vis):
+    def _check_inputs(self, ir, vis):
         if self.training:
             raise RuntimeError("paif_b200.Network_Fusion_Searched supports eval() mode only (BatchNorm batch "
                                "statistics are out of scope; the reference scripts always call .eval())")
@@ -1005,6 +1010,9 @@ class Network_Fusion_Searched(nn.Module):
             raise ValueError("expected ir [B,>=1,H,W] and vis [B,>=1,H,W] of the same batch and size")
         if ir.shape[2] <= 9 or ir.shape[3] <= 9:
             raise AssertionError("guided filter (radius 4) needs H, W > 9")
+
+    def forward(self, ir, vis):
+        self._check_inputs(ir, vis)
         if ir.dtype != torch.float32:
             ir = ir.float()
         if vis.dtype != torch.float32:
@@ -1015,6 +1023,32 @@ class Network_Fusion_Searched(nn.Module):
     def _loss(self, ir, vis, mask):
         logits = self(ir, vis)
         return self._criterion(ir, vis, logits, mask)
+
+    def forward2(self, ir, vis):
+        """``Network_Fusion_Searched_showfeatures.forward2`` (core/model_fusion_auto.py:669-679): the fused image and
+        the intermediate maps the reference exposes for visualisation, as NCHW fp32 tensors:
+        ``(output, ir_feature, vis_feature, lf_ir, hf_ir, res_ir, lf_vis, hf_vis, res_vis)`` with
+        ``lf_* = cat[LF(eps=1e-3), LF(eps=1e-4)]`` (64 ch), ``hf_* = cat[x - LF1, x - LF2]``, ``res_*`` the
+        channel max-min guide (Cell_Decom_decom, :554-585).  Inference only (runs under ``no_grad``, fp32 storage)."""
+        if self.storage != 'fp32':
+            raise RuntimeError("forward2 returns fp32 intermediates: use storage='fp32'")
+        self._check_inputs(ir, vis)
+        cap = {}
+        with torch.no_grad(), torch.cuda.device(ir.device):
+            out, _ = self._run_forward(ir.float()[:, 0:1], vis.float()[:, 0:1], False, capture=cap)
+
+            def nchw(m):                              # C4 map [B][C/4][H][W][4] -> [B][C][H][W]
+                b, q, h, w, _ = m.shape
+                return m.permute(0, 1, 4, 2, 3).reshape(b, q * 4, h, w)
+
+            res = []
+            for i in range(2):
+                x = nchw(cap["feats"][i])
+                lf = torch.cat([nchw(cap["lf"][i][0]), nchw(cap["lf"][i][1])], 1)
+                res.append((lf, torch.cat([x, x], 1) - lf, cap["guides"][i].unsqueeze(1)))
+            (lf_ir, hf_ir, res_ir), (lf_vis, hf_vis, res_vis) = res
+            return (out, nchw(cap["branch_out"][0]), nchw(cap["branch_out"][1]),
+                    lf_ir, hf_ir, res_ir, lf_vis, hf_vis, res_vis)
 
 
 class _FusionFn(torch.autograd.Function):
@@ -1047,3 +1081,10 @@ class _FusionFn(torch.autograd.Function):
                 full[:, 0] = gi
                 outs.append(full)
         return outs[0], outs[1], None
+
+
+class Network_Fusion_Searched_showfeatures(Network_Fusion_Searched):
+    """core/model_fusion_auto.py:641-697: same parameters and ``forward`` as ``Network_Fusion_Searched`` (its
+    ``Cell_Decom_decom`` holds the same sub-modules as ``Cell_Decom``); ``forward2`` additionally returns the
+    decomposition intermediates."""
+

@@ -75,3 +75,27 @@ def test_edge_sizes_forward_and_input_gradients(shape):
     out.backward(cot.to(DEV))
     for got, want in ((a.grad.cpu(), g_ir), (v.grad.cpu()[:, 0:1], g_vis[:, 0:1])):
         assert ((got - want).norm() / want.norm()).item() < 1e-1      # gross-error gate; the calibrated TF32 gates are in test_gpu_backward.py
+
+
+def test_forward2_returns_the_reference_intermediates():
+    """Network_Fusion_Searched_showfeatures.forward2 (core/model_fusion_auto.py:669-679) against the oracle's
+    intermediates (which equal the reference's forward2 outputs bit for bit on CPU, checked in the build container)."""
+    g = load_golden("seed1_random_1x48x72")
+    sd = g["state_dict"]
+    net = paif_b200.Network_Fusion_Searched_showfeatures(32, None, paif_b200.fusion_at)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).eval()
+    net.conv_engine = 'direct'
+    ir, vis = g["ir"], g["vis"]
+    outs = [t.cpu() for t in net.forward2(ir.to(DEV), vis.to(DEV))]
+    inter = {}
+    out = fo.fusion_forward(sd, paif_b200.fusion_at, ir, vis, inter)
+    want = [out, inter["ir_feature"], inter["vis_feature"]]
+    for f in (inter["fir"], inter["fvis"]):
+        lf, hf = fo.decomposition(f)
+        want += [lf, hf, fo.get_residue(f)]
+    assert len(outs) == 9
+    for i, (a, b) in enumerate(zip(outs, want)):
+        assert a.shape == b.shape, i
+        assert (a - b).abs().max().item() < (5e-4 if i in (3, 4, 6, 7) else 5e-5), (i, (a - b).abs().max().item())
+

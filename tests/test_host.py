@@ -126,6 +126,22 @@ def test_install_rebinds_reference_symbol():
     m.Network_Fusion_Searched = object
     paif_b200.install(m)
     assert m.Network_Fusion_Searched is paif_b200.Network_Fusion_Searched
+    assert not hasattr(m, "Network_Fusion_Searched_showfeatures")
+    m.Network_Fusion_Searched_showfeatures = object
+    paif_b200.install(m)
+    assert m.Network_Fusion_Searched_showfeatures is paif_b200.Network_Fusion_Searched_showfeatures
+
+
+def test_showfeatures_variant_has_the_reference_state_dict():
+    """core/model_fusion_auto.py:641-697 builds the same sub-module tree (Cell_Decom_decom holds what Cell_Decom holds):
+    checked in the build container against the reference class itself — keys AND default-init values equal the
+    seed-0 fixture of Network_Fusion_Searched."""
+    torch.manual_seed(0)
+    net = paif_b200.Network_Fusion_Searched_showfeatures(32, None, paif_b200.fusion_at)
+    ref_sd = load_golden("seed0_default_2x40x56")["state_dict"]
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(ref_sd.keys()) and all(torch.equal(sd[k], ref_sd[k]) for k in sd)
+    assert hasattr(net, "forward2")
 
 
 def test_library_loads_and_exports_every_declared_symbol():
