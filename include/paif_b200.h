@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PAIF_ABI_VERSION 1
+#define PAIF_ABI_VERSION 2   /* 2: PaifConvDesc.storage, bf16 storage entry points, paif_out_forward_tc */
 
 #define PAIF_EINVAL   (-1)   /* bad argument (null pointer, unsupported size) */
 #define PAIF_ENOTSUP  (-2)   /* configuration not supported by this build     */

@@ -11,6 +11,7 @@ from . import build as _build
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpaif_b200.so")
 
+ABI_VERSION = 2                                             # PAIF_ABI_VERSION of include/paif_b200.h
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 STORAGE_F32, STORAGE_BF16, STORAGE_F32_BF16 = 0, 1, 2      # PaifConvDesc.storage
 
@@ -109,7 +110,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name == "paif_last_error_string" else
                       _ll if name == "paif_gf_backward_work_floats" else _i)
-    if lib.paif_abi_version() != 1:
+    if lib.paif_abi_version() != ABI_VERSION:
         raise PaifError("libpaif_b200.so ABI version mismatch")
     _lib = lib
     return lib
