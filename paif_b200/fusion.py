@@ -329,6 +329,7 @@ class DilConv(_Primitive):
         if need_bwd:
             p["dw_t"] = dw.flip(-1, -2).reshape(C, -1).contiguous().float()
             p["pw_d"] = _dgrad_groups(self.op[2].weight.detach(), 1, 1, scale=s)[0]
+            p["wdense_d"] = _dgrad_groups(wd.float(), self.k, self.d, scale=s)[0]     # dgrad of the dense form
         return p
 
     def fwd(self, rt, p, x, extras, x_relu=None):
@@ -353,6 +354,10 @@ class DilConv(_Primitive):
         return out, ()
 
     def bwd(self, rt, p, rec, g, extra_add, x=None):
+        cw = p["wdense_d"]
+        if rt.tc_engine() and rt.dilconv_dense and cw.mma is not None:
+            # one dense dgrad convolution on the engine: ReLU' (mask of x with slope 0) and the "+ x" branch in the epilogue
+            return rt.conv([g], cw, mask_src=x, mask_slope=rt.zero_slope(), post_res=[g])[0]
         u = rt.conv([g], p["pw_d"])[0]
         return rt.dwconv(u, p["dw_t"], self.k, self.d, relu_in=False, mask_src=x, post_res=g)
 
@@ -928,6 +933,7 @@ class Network_Fusion_Searched(nn.Module):
         p = saved["packed"]
         rt = _Runtime(B, H, W, C, g.device, self._engine(), False)
         rt.profile = self.profile
+        rt.dilconv_dense = self.dilconv_dense
         # stem_out + tanh; if the last op of the final chain is a ResidualModule its PReLU' mask is fused here
         gf2 = rt.new_map()
         last = self.chain._ops[-1]._op
