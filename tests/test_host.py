@@ -154,3 +154,41 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert lib.paif_abi_version() == 2
     assert ctypes.sizeof(_lib.ConvDesc) > 0
+
+
+def test_weight_images_follow_the_documented_tile_layout():
+    """PaifConvDesc.weight_mma as documented in include/paif_b200.h: [K-group][dx][K step][16-B chunk][dy][cout][cin in
+    chunk], TF32-rounded fp32 (4 cin per chunk) and bf16 (8 cin per chunk)."""
+    torch.manual_seed(0)
+    w = torch.randn(32, 64, 3, 3)
+    cw = fusion._ConvW(w, 2, 3, 1)
+    assert cw.mma.shape == (2, 3, 4, 2, 3, 32, 4) and cw.mma.dtype == torch.float32
+    assert cw.mma16.shape == (2, 3, 2, 2, 3, 32, 8) and cw.mma16.dtype == torch.bfloat16
+    wt = fusion._round_tf32(w)
+    for (g, dx, ks, ch, dy, co, c) in [(0, 0, 0, 0, 0, 0, 0), (1, 2, 3, 1, 1, 17, 2), (0, 1, 2, 0, 2, 31, 3), (1, 0, 1, 1, 0, 5, 1)]:
+        assert cw.mma[g, dx, ks, ch, dy, co, c] == wt[co, g * 32 + ks * 8 + ch * 4 + c, dy, dx]
+    for (g, dx, ks, ch, dy, co, c) in [(0, 0, 0, 0, 0, 0, 0), (1, 2, 1, 1, 1, 17, 6), (0, 1, 1, 0, 2, 31, 7), (1, 0, 0, 1, 0, 5, 3)]:
+        assert cw.mma16[g, dx, ks, ch, dy, co, c] == w[co, g * 32 + ks * 16 + ch * 8 + c, dy, dx].to(torch.bfloat16)
+    # TF32 rounding: nearest, 10-bit mantissa kept in an fp32 container
+    assert ((wt.view(torch.int32) & 0x1FFF) == 0).all() and (wt - w).abs().max() <= w.abs().max() * 2.0 ** -11
+
+
+def test_bf16_storage_mode_rules():
+    """storage='bf16' is forward-only, tensor-core only and covers the primitives of the shipped genotype."""
+    net = _net().eval()
+    assert net.storage == 'fp32' and net._bf16_storage(False) is False and net._bf16_storage(True) is False
+    net.storage = 'bf16'
+    assert net._bf16_storage(False) is True
+    with pytest.raises(RuntimeError):
+        net._bf16_storage(True)                              # a backward was requested
+    net.conv_engine = 'direct'
+    with pytest.raises(RuntimeError):
+        net._bf16_storage(False)
+    net.conv_engine, net.storage = 'auto', 'fp16'
+    with pytest.raises(ValueError):
+        net._bf16_storage(False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        alt = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at._replace(normal_3=[('SepConv_3_1', 0)]))
+    alt.storage = 'bf16'
+    with pytest.raises(NotImplementedError):
+        alt._bf16_storage(False)
