@@ -10,7 +10,23 @@ import os
 import sys
 from collections import namedtuple
 
-REFERENCE_ROOT = os.environ.get("PAIF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+#: where build() stages a copy of the reference tree for the GPU box (git-ignored, shipped by gpurun)
+STAGED_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def reference_root():
+    """PAIF_REFERENCE_ROOT, else /root/reference (build container), else the staged copy baseline/_ref."""
+    env = os.environ.get("PAIF_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", STAGED_ROOT):
+        if os.path.isfile(os.path.join(cand, "core", "model_fusion_auto.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = reference_root()
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 # test_original.py:709-713 == robust_test.py:253-257 (the only shipped genotype)

@@ -19,6 +19,7 @@ Sharding invariance needs three things besides the integer reduction, all handle
 The segmentation consumer is any stock-PyTorch ``nn.Module`` mapping ``[B,3,H,W] -> [B,K,h,w]``
 logits (the reference uses SegFormer MiT-B3, which stays stock PyTorch by the scope contract).
 """
+import collections
 import ctypes
 
 import torch
@@ -97,12 +98,27 @@ def seeded_delta(shape, epsilon, seed, global_index, device):
     return ((torch.rand(shape, generator=g) * 2.0 - 1.0) * epsilon).to(device)
 
 
+#: PGD perturbations in the order the reference's ``attack_both`` returns them (attack/attack.py:514:
+#: ``return delta_ir, delta_vis``) — NOT (vis, ir): the two broadcast against each other's image
+#: ([B,3,H,W] + [B,1,H,W]) without an error, so the order is pinned by name and by tests/test_eval_host.py.
+PGDDelta = collections.namedtuple("PGDDelta", "delta_ir delta_vis")
+
+
+def _replay_signature(model, vis_shape, ir_shape, label_shape, device, epsilon, alpha):
+    """Everything a captured PGD iteration depends on besides the data it copies in: the shapes, the step sizes and,
+    for every paif_b200 fusion net inside ``model``, the identity of its packed weights (a graph replay never
+    re-enters Python, so it would keep reading the device pointers of a pack that ``load_state_dict`` or an engine
+    switch has since replaced and freed)."""
+    sigs = tuple(m.pack_signature(True) for m in model.modules() if hasattr(m, "pack_signature"))
+    return (tuple(vis_shape), tuple(ir_shape), tuple(label_shape), str(device), float(epsilon), float(alpha), sigs)
+
+
 def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255., attack_iters=10,
                     seed=0, global_index=0, ignore_index=255):
     """``attack_both(..., attack_loss='l_seg', attack_way='PGD')`` (attack/attack.py:417-514) for one
     frame, with a seeded start.  ``model(ir, vis) -> (fused, seg_logits)``.  Faithful to the reference
     including its quirk of never zeroing ``delta.grad`` (the step uses the sign of the running sum of
-    gradients, attack/attack.py:501-512).  Returns (delta_vis, delta_ir)."""
+    gradients, attack/attack.py:501-512).  Returns :class:`PGDDelta` ``(delta_ir, delta_vis)``, the reference's order."""
     dev = x_vis.device
     d_vis = seeded_delta(x_vis.shape, epsilon, seed, 2 * global_index, dev)
     d_ir = seeded_delta(x_ir.shape, epsilon, seed, 2 * global_index + 1, dev)
@@ -118,7 +134,7 @@ def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255.,
             for d, x in ((d_vis, x_vis), (d_ir, x_ir)):
                 d.data = torch.clamp(d + alpha * torch.sign(d.grad), min=-epsilon, max=epsilon)
                 d.data = torch.max(torch.min(d, 1 - x), 0 - x)
-    return d_vis.detach(), d_ir.detach()
+    return PGDDelta(delta_ir=d_ir.detach(), delta_vis=d_vis.detach())
 
 
 class GraphedPGD:
@@ -136,6 +152,7 @@ class GraphedPGD:
         self.d_vis = torch.zeros(vis_shape, device=device, requires_grad=True)
         self.d_ir = torch.zeros(ir_shape, device=device, requires_grad=True)
         self.model, self.ignore_index = model, ignore_index
+        self.signature = None
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -146,6 +163,12 @@ class GraphedPGD:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._iteration()
+        # taken AFTER capture: the warm-up iterations are what (re)build the pack the graph points into
+        self.signature = _replay_signature(model, vis_shape, ir_shape, label_shape, device, epsilon, alpha)
+
+    def matches(self, vis_shape, ir_shape, label_shape, device, epsilon, alpha):
+        """True when replaying this graph is still valid for such a call (same shapes / steps / packed weights)."""
+        return self.signature == _replay_signature(self.model, vis_shape, ir_shape, label_shape, device, epsilon, alpha)
 
     def _iteration(self):
         with torch.enable_grad():
@@ -160,6 +183,10 @@ class GraphedPGD:
 
     def attack(self, x_vis, x_ir, label, attack_iters, seed, global_index):
         dev = self.x_vis.device
+        if not self.matches(x_vis.shape, x_ir.shape, label.shape, dev, self.eps, self.alpha):
+            raise RuntimeError("GraphedPGD: the captured graph no longer matches this call (input shapes changed, or "
+                               "the fusion net's weights / engine switches changed after capture, so the graph "
+                               "points at a stale weight pack); build a new GraphedPGD")
         with torch.no_grad():
             self.x_vis.copy_(x_vis)
             self.x_ir.copy_(x_ir)
@@ -170,7 +197,7 @@ class GraphedPGD:
                 d.grad.zero_()                      # a fresh delta per frame, as attack/attack.py:433-441
         for _ in range(attack_iters):
             self.graph.replay()
-        return self.d_vis.detach().clone(), self.d_ir.detach().clone()
+        return PGDDelta(delta_ir=self.d_ir.detach().clone(), delta_vis=self.d_vis.detach().clone())
 
 
 def robust_eval(model, frames, num_classes=9, attack_iters=10, epsilon=8 / 255., alpha=2 / 255., seed=0,
@@ -187,14 +214,13 @@ def robust_eval(model, frames, num_classes=9, attack_iters=10, epsilon=8 / 255.,
         label = label.to(dev)[None].long()
         if attack_iters > 0:
             if use_cuda_graph:
-                if (runner is None or runner.x_vis.shape != vis.shape or runner.eps != float(epsilon)
-                        or runner.alpha != float(alpha)):
+                if runner is None or not runner.matches(vis.shape, ir.shape, label.shape, dev, epsilon, alpha):
                     runner = GraphedPGD(model, vis.shape, ir.shape, label.shape, dev, epsilon, alpha)
                     object.__setattr__(model, "_paif_pgd_runner", runner)
-                d_vis, d_ir = runner.attack(vis, ir, label, attack_iters, seed, gi)
+                delta = runner.attack(vis, ir, label, attack_iters, seed, gi)
             else:
-                d_vis, d_ir = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gi)
-            vis, ir = vis + d_vis, ir + d_ir
+                delta = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gi)
+            vis, ir = vis + delta.delta_vis, ir + delta.delta_ir
         with torch.no_grad():
             _, seg = model(ir, vis)
             seg = F.interpolate(seg, size=label.shape[1:], mode="bilinear", align_corners=False)

@@ -86,6 +86,11 @@ def _dgrad_groups(w, k, dil, scale=None):
     return [_ConvW(wf[:, g:g + 32].transpose(0, 1).contiguous(), 1, k, dil) for g in range(0, cin_total, 32)]
 
 
+def _slope(w):
+    """PReLU slope as the fp32 scalar the kernels read (a .half() / .double() module still feeds fp32)."""
+    return w.detach().float().contiguous()
+
+
 def _bn_fold(bn):
     s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
     return s.float().contiguous(), (bn.bias - bn.running_mean * s).float().contiguous()
@@ -273,7 +278,7 @@ class ResidualDenseBlock(_Primitive):
         k, d = self.k, self.d
         p = {"w": [_ConvW(c.conv.weight.detach(), n, k, d)
                    for n, c in ((1, self.conv1), (2, self.conv2), (3, self.conv3))],
-             "a": self.lrelu.weight.detach()}
+             "a": _slope(self.lrelu.weight)}
         if need_bwd:
             p["wd"] = [_dgrad_groups(c.conv.weight.detach(), k, d) for c in (self.conv1, self.conv2, self.conv3)]
         return p
@@ -390,7 +395,7 @@ class ECABasicBlock(_Primitive):
         p = {"w1": _ConvW(self.conv1.weight.detach(), 1, 3, 1),
              "w2": _ConvW(self.conv2.conv.weight.detach(), 1, self.k, 1),
              "w1d": self.se.conv.weight.detach().reshape(-1).contiguous().float(),
-             "a": self.relu.weight.detach()}
+             "a": _slope(self.relu.weight)}
         if need_bwd:
             p["w1_d"] = _dgrad_groups(self.conv1.weight.detach(), 3, 1)[0]
             p["w2_d"] = _dgrad_groups(self.conv2.conv.weight.detach(), self.k, 1)[0]
@@ -451,7 +456,7 @@ class ResidualModule(_Primitive):
                           self.op[1].weight.detach().double()).float()
         s, sh = _bn_fold(self.op[3])
         p = {"w0": _ConvW(w0, 1, self.k, self.d), "wm": _ConvW(wm, 1, 3, 2), "s": s, "sh": sh,
-             "a": self.op[4].weight.detach()}
+             "a": _slope(self.op[4].weight)}
         if need_bwd:
             p["w0_d"] = _dgrad_groups(w0, self.k, self.d)[0]
             p["wm_d"] = _dgrad_groups(wm, 3, 2, scale=s)[0]
@@ -557,7 +562,7 @@ class Spatial_BasicBlock(_Primitive):
         w4 = torch.cat([w.reshape(2, -1), torch.zeros_like(w.reshape(2, -1))], 0).contiguous().float()
         p = {"w1": _ConvW(self.conv1.weight.detach(), 1, 3, 1),
              "w2": _ConvW(self.conv2.conv.weight.detach(), 1, self.k, 1),
-             "w4": w4, "a": self.relu.weight.detach()}
+             "w4": w4, "a": _slope(self.relu.weight)}
         if need_bwd:
             p["w1_d"] = _dgrad_groups(self.conv1.weight.detach(), 3, 1)[0]
             p["w2_d"] = _dgrad_groups(self.conv2.conv.weight.detach(), self.k, 1)[0]
@@ -785,6 +790,7 @@ class Network_Fusion_Searched(nn.Module):
         #: stem_out's merged 5x5 stencil on the tensor-core engine (False / conv_engine='direct': the FFMA kernel)
         self.out_tensor_core = True
         self._pack_cache = None
+        self._pack_epoch = 0
         self.last_launches = 0
         #: set to a list to collect (name, meta, start_event, end_event) for every kernel launch
         self.profile = None
@@ -793,6 +799,32 @@ class Network_Fusion_Searched(nn.Module):
     def _pack_key(self, need_bwd):
         ts = list(self.parameters()) + list(self.buffers())
         return (need_bwd,) + tuple((t.data_ptr(), t._version) for t in ts)
+
+    def invalidate_packed(self):
+        """Drop the packed / TF32-rounded / BN-folded weight cache.  The cache key is (data_ptr, _version) per
+        parameter and buffer, which in-place edits through ``.data`` (``p.data.copy_()``, older EMA / checkpoint
+        code) do not bump: call this after such an edit.  ``load_state_dict`` and ``.to()/.cuda()/.half()`` clear
+        the cache by themselves."""
+        self._pack_cache = None
+        self._pack_epoch = getattr(self, "_pack_epoch", 0) + 1
+
+    def pack_signature(self, need_bwd=True):
+        """Hashable identity of the packed weights a forward would use now (parameter versions, engine switches):
+        holders of device pointers into the pack (CUDA-graph replays) compare it before reuse."""
+        return (self._pack_key(need_bwd), getattr(self, "_pack_epoch", 0), self.conv_engine, self.storage,
+                self.dilconv_dense, self.out_tensor_core)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_packed()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
 
     def _packed(self, need_bwd):
         key = self._pack_key(need_bwd)
@@ -804,7 +836,7 @@ class Network_Fusion_Searched(nn.Module):
             d = self.decompation
             p = {
                 "stem_w": [s[0].weight.detach().reshape(self._C, 9).contiguous().float() for s in (self.stem_1, self.stem_2)],
-                "stem_a": [s[1].weight.detach() for s in (self.stem_1, self.stem_2)],
+                "stem_a": [_slope(s[1].weight) for s in (self.stem_1, self.stem_2)],
                 "c1x1": [_ConvW(_fold_decomp_1x1(c.weight), 3, 1, 1) for c in (d.conv1x1_lf, d.conv1x1_hf)],
                 "c1x1_b": [c.bias.detach().float().contiguous() for c in (d.conv1x1_lf, d.conv1x1_hf)],
                 "chain_ir": d.chain.pack(need_bwd), "chain_vis": d.chain2.pack(need_bwd),
@@ -812,7 +844,7 @@ class Network_Fusion_Searched(nn.Module):
                 "spa_w": self.spa.spatial.conv.weight.detach().reshape(4, -1).contiguous().float(),
                 "spa_k": self.spa.spatial.conv.weight.shape[-1],
                 "out_wm": _merge_stem_out(self.stem_out[0].weight, self.stem_out[1].weight),
-                "out_a": self.stem_out[2].weight.detach(),
+                "out_a": _slope(self.stem_out[2].weight),
             }
             # interior class (1, 1) of the merged stencil as a tensor-core weight image, cout padded 1 -> 16
             # (paif_out_forward_tc); same tile order as _ConvW.mma / .mma16
@@ -1062,7 +1094,14 @@ class _FusionFn(torch.autograd.Function):
     def forward(ctx, ir, vis, net):
         need = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])   # False under no_grad
         out, saved = net._run_forward(ir[:, 0:1], vis[:, 0:1], need)
+        if saved is not None:
+            # `out` is an output of this node: keeping it in a plain attribute would form the cycle
+            # out -> grad_fn(ctx) -> saved['out'] -> out and pin ~2 GB of activations per 480x640 frame until the
+            # cyclic GC runs (robust_test.py:166 builds such a graph and never calls backward)
+            saved.pop("out")
+            ctx.save_for_backward(out)
         ctx.net, ctx.saved = net, saved
+        ctx.had_saved = saved is not None
         ctx.shapes = (ir.shape, vis.shape)
         return out
 
@@ -1070,10 +1109,14 @@ class _FusionFn(torch.autograd.Function):
     def backward(ctx, g):
         net, saved = ctx.net, ctx.saved
         if saved is None:
+            if ctx.had_saved:
+                raise RuntimeError("Trying to backward through the paif_b200 fusion graph a second time: the saved "
+                                   "activations are freed after the first backward (retain_graph is not supported)")
             return None, None, None
         g = g.contiguous().float()
+        (out,) = ctx.saved_tensors
         with torch.cuda.device(g.device):
-            g_ir, g_vis = net._run_backward(saved, g)
+            g_ir, g_vis = net._run_backward(dict(saved, out=out), g)
         ctx.saved = None
         outs = []
         for gi, shape, need in ((g_ir, ctx.shapes[0], ctx.needs_input_grad[0]),

@@ -116,3 +116,40 @@ def test_task_glue_matches_reference_colour_conventions_and_consumer_shapes():
     rgb = (rgb - rgb.min()) / (rgb.max() - rgb.min())
     x = (rgb * 255 - task.mean) / task.std
     torch.testing.assert_close(task.denoise_net(x), seg, rtol=1e-4, atol=1e-4)
+
+
+def test_pgd_delta_order_is_the_references():
+    """``attack_both`` returns ``(delta_ir, delta_vis)`` (attack/attack.py:514) and robust_test.py:145 swaps
+    the names at the call site; paif_b200 returns a named tuple in that order.  The statement is pinned against the
+    reference source when the tree is present (build container / staged baseline/_ref)."""
+    assert ev.PGDDelta._fields == ("delta_ir", "delta_vis")
+    from oracle import ref_loader
+    if ref_loader.reference_available():
+        src = open(os.path.join(ref_loader.reference_root(), "attack", "attack.py")).read()
+        body = src[src.index("def attack_both("):]
+        assert "return delta_ir, delta_vis" in body[:body.index("\ndef ", 1)]
+
+
+def test_pack_cache_is_invalidated_by_load_state_dict_and_apply():
+    """stale packed weights.  ``load_state_dict`` / ``.to()`` / ``invalidate_packed()`` drop the pack and
+    change ``pack_signature`` (what a captured PGD graph compares before replaying)."""
+    import paif_b200
+    torch.manual_seed(0)
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at).eval()
+    net._pack_cache = ("sentinel", {})
+    sig0 = net.pack_signature()
+    net.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
+    assert net._pack_cache is None and net.pack_signature() != sig0
+    net._pack_cache = ("sentinel", {})
+    sig1 = net.pack_signature()
+    net.double()
+    assert net._pack_cache is None and net.pack_signature() != sig1
+    net.float()
+    sig2 = net.pack_signature()
+    with torch.no_grad():
+        net.stem_1[1].weight.data.mul_(2.0)          # .data edits do not bump _version: explicit invalidation
+    assert net.pack_signature() == sig2
+    net.invalidate_packed()
+    assert net.pack_signature() != sig2
+    net.conv_engine = 'direct'
+    assert net.pack_signature() != sig2

@@ -91,10 +91,11 @@ def test_cuda_graph_pgd_matches_eager_pgd():
     g = torch.Generator().manual_seed(4)
     vis, ir = torch.rand(1, 3, 24, 40, generator=g).to(DEV), torch.rand(1, 1, 24, 40, generator=g).to(DEV)
     label = torch.randint(0, 9, (1, 24, 40), generator=g).to(DEV)
-    e_vis, e_ir = ev.pgd_attack_both(model, vis, ir, label, attack_iters=3, seed=5, global_index=2)
+    e_ir, e_vis = ev.pgd_attack_both(model, vis, ir, label, attack_iters=3, seed=5, global_index=2)
+    assert e_ir.shape == ir.shape and e_vis.shape == vis.shape      # (delta_ir, delta_vis): attack/attack.py:514
     runner = ev.GraphedPGD(model, vis.shape, ir.shape, label.shape, torch.device(DEV), 8 / 255., 2 / 255.)
     for _ in range(2):                                   # twice: state is reset per frame
-        g_vis, g_ir = runner.attack(vis, ir, label, 3, seed=5, global_index=2)
+        g_ir, g_vis = runner.attack(vis, ir, label, 3, seed=5, global_index=2)
         for got, want in ((g_vis, e_vis), (g_ir, e_ir)):
             diff = (got - want).abs()
             assert int((diff > 1e-6).sum()) <= got.numel() // 50, int((diff > 1e-6).sum())
