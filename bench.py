@@ -28,6 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+CPU_KIND_NOTE = {"reference": "the UNMODIFIED reference Network_Fusion_Searched from the staged tree baseline/_ref, torch CPU ops",
+                 "port": "oracle port, torch CPU ops: no reference tree on this box"}
 FLOP_PER_PX = 519336.0          # conv MACs x 2 per pixel of one pair
 BYTES_PER_PX = 1891 * 4.0       # layer-granular algorithmic traffic, fp32 storage (1202 ch read + 689 written)
 
@@ -113,41 +115,76 @@ def synth_inputs(B, H, W, seed=1):
     return torch.rand(B, 1, H, W, generator=g), torch.rand(B, 3, H, W, generator=g)
 
 
-def cpu_port_fwd_bwd_pairs_per_s(steps, H, W):
-    """Forward + backward-to-input of the CPU oracle port (autograd), one pair per step."""
+def reference_fusion_module(sd, device="cpu"):
+    """The UNMODIFIED reference ``Network_Fusion_Searched`` (core/model_fusion_auto.py:599-640) imported from the
+    staged tree (``baseline/_ref`` on the GPU box, /root/reference in the build container) through
+    ``oracle/ref_loader`` (import shims for its absent third-party modules; the un-vendored ``guided_filter_pytorch``
+    is the restatement in oracle/shims), loaded with the bench's seed-0 weights.  None when no tree is present."""
+    import contextlib
+    import io
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        return None
+    m = ref_loader.load_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = m.Network_Fusion_Searched(32, None, ref_loader.fusion_at)
+    net.load_state_dict(sd, strict=True)
+    return net.to(device).eval()
+
+
+def cpu_arm(sd):
+    """(kind, forward(ir, vis), input_grads(ir, vis, gout)) of the CPU arm: the reference module itself when its
+    tree travelled with the repo (kind "reference"), else the oracle port (kind "port")."""
     import torch
     import paif_b200
     from oracle import fusion_oracle as fo
+    ref = reference_fusion_module(sd)
+    if ref is None:
+        return ("port", lambda ir, vis: fo.fusion_forward(sd, paif_b200.fusion_at, ir, vis),
+                lambda ir, vis, g: fo.fusion_input_grads(sd, paif_b200.fusion_at, ir, vis, g))
+    for p in ref.parameters():
+        p.requires_grad_(False)                       # backward-to-input only, like the drop-in
+
+    def grads(ir, vis, g):
+        a, v = ir.clone().requires_grad_(True), vis.clone().requires_grad_(True)
+        return torch.autograd.grad(ref(a, v), [a, v], g)
+
+    return "reference", ref, grads
+
+
+def cpu_port_fwd_bwd_pairs_per_s(steps, H, W):
+    """Forward + backward-to-input of the CPU arm (autograd), one pair per step."""
+    import torch
     torch.set_num_threads(os.cpu_count() or 1)
     _, sd = synth_state()
+    _, _, grads = cpu_arm(sd)
     ir, vis = synth_inputs(1, H, W)
     gout = torch.rand(1, 1, H, W) - 0.5
     times = []
     for i in range(steps + 1):
         t0 = time.perf_counter()
-        fo.fusion_input_grads(sd, paif_b200.fusion_at, ir, vis, gout)
+        grads(ir, vis, gout)
         if i >= 1:
             times.append(time.perf_counter() - t0)
     return steps / sum(times)
 
 
 def cpu_port_pairs_per_s(steps, H, W, warmup=1):
-    """The CPU oracle port on all host cores, one pair per step (bounded sample)."""
+    """The CPU arm on all host cores, one pair per step (bounded sample).  Returns (pairs/s, cores, times, kind)."""
     import torch
-    import paif_b200
-    from oracle import fusion_oracle as fo
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     _, sd = synth_state()
+    kind, fwd, _ = cpu_arm(sd)
     ir, vis = synth_inputs(1, H, W)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            fo.fusion_forward(sd, paif_b200.fusion_at, ir, vis)
+            fwd(ir, vis)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return steps / sum(times), cores, times
+    return steps / sum(times), cores, times, kind
 
 
 def torch_eager_gpu_pairs_per_s(dev, B, H, W, steps=3):
@@ -238,16 +275,16 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    v, cores, times = cpu_port_pairs_per_s(args.steps, args.height, args.width, warmup=min(args.warmup, 1))
-    sample = "%d timed forward passes of 1 pair %dx%d (fp32, no_grad) after %d warm-up" % (
-        args.steps, args.height, args.width, min(args.warmup, 1))
+    v, cores, times, kind = cpu_port_pairs_per_s(args.steps, args.height, args.width, warmup=min(args.warmup, 1))
+    sample = "%d timed forward passes of 1 pair %dx%d (fp32, no_grad, %s) after %d warm-up" % (
+        args.steps, args.height, args.width, CPU_KIND_NOTE[kind], min(args.warmup, 1))
     line = {"impl": "reference", "metric": "fused %dx%d pairs/s (fusion-net forward)" % (args.height, args.width),
             "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Network_Fusion_Searched forward, fusion_at genotype, random-init (seed 0), "
                                    "%dx%d IR+RGB pairs; CPU arm processes 1 pair per step" % (args.height, args.width)},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
@@ -558,14 +595,14 @@ def run_ours(args):
     if pgd is not None:
         line["pgd10"] = pgd
     if not args.no_cpu_baseline and world == 1:
-        v, cores, times = cpu_port_pairs_per_s(args.cpu_baseline_steps, H, W)
+        v, cores, times, kind = cpu_port_pairs_per_s(args.cpu_baseline_steps, H, W)
         st = sorted(times)
-        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": "%d timed forward passes of 1 pair %dx%d on the host (oracle port, torch CPU ops) after 1 warm-up"
-                                          % (args.cpu_baseline_steps, H, W),
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
+                                "sample": "%d timed forward passes of 1 pair %dx%d on the host (%s) after 1 warm-up"
+                                          % (args.cpu_baseline_steps, H, W, CPU_KIND_NOTE[kind]),
                                 "min_ms": 1e3 * st[0], "median_ms": 1e3 * st[len(st) // 2],
                                 "fwd_bwd_pairs_per_s": cpu_port_fwd_bwd_pairs_per_s(2, H, W),
-                                "fwd_bwd_sample": "2 timed forward+backward-to-input passes of 1 pair (oracle autograd) after 1 warm-up"}
+                                "fwd_bwd_sample": "2 timed forward+backward-to-input passes of 1 pair (autograd of the same module) after 1 warm-up"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
