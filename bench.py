@@ -460,7 +460,7 @@ def run_ours(args):
             per = len(prof_fb) // args.bwd_steps
             agg = {}
             for (n, m, a, b) in prof_fb[-per:]:
-                key = n if not m else "%s k%d d%d cin%d" % (n, m["k"], m["dil"], m["cin"])
+                key = n if not (m and "k" in m) else "%s k%d d%d cin%d" % (n, m["k"], m["dil"], m["cin"])
                 t = a.elapsed_time(b)
                 agg[key] = (agg.get(key, (0, 0.0))[0] + 1, agg.get(key, (0, 0.0))[1] + t)
             tot = sum(t for _, t in agg.values())
@@ -499,7 +499,7 @@ def run_ours(args):
                 for (n, m, a, b) in prof16[-per:]:
                     t = a.elapsed_time(b)
                     extra = ""
-                    if m:
+                    if m and "k" in m:
                         extra = " k%d d%d cin%d  %.1f TFLOP/s  %.0f GB/s" % (m["k"], m["dil"], m["cin"], m["flops"] / (t * 1e-3) / 1e12,
                                                                              m["bytes"] / (t * 1e-3) / 1e9)
                     sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
@@ -514,7 +514,7 @@ def run_ours(args):
         for (n, m, a, b) in prof[-per:]:
             t = a.elapsed_time(b)
             extra = ""
-            if m:
+            if m and "k" in m:
                 extra = " k%d d%d cin%d  %.1f TFLOP/s  %.0f GB/s" % (m["k"], m["dil"], m["cin"], m["flops"] / (t * 1e-3) / 1e12,
                                                                      m["bytes"] / (t * 1e-3) / 1e9)
             sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))

@@ -70,6 +70,19 @@ int paif_gf_guide_stats(const float* residue, float* stats, int B, int H, int W,
 int paif_gf_decomp_forward(const float* feat, const float* residue, const float* stats,
                            float* lf1, float* lf2, int C, int B, int H, int W, void* stream);
 
+/* Fused decomposition + folded 1x1: Cell_Decom.decomposition followed by conv1x1_lf / conv1x1_hf
+ * (core/model_fusion_auto.py:509-535) in ONE kernel that never writes the LF maps:
+ *     out = Wa LF_1e-3 + Wb LF_1e-4 + Wc feat + bias,
+ * Wa = W[:,0:32]-W[:,64:96], Wb = W[:,32:64]-W[:,96:128], Wc = W[:,64:96]+W[:,96:128] of the 128->32 1x1 weight W
+ * (HF = feat - LF folded in).  The channel mix runs between the two box-filter levels on tcgen05 (TF32 operands,
+ * fp32 accumulate), so only 64 level-2 box filters remain; guided-filter statistics stay fp32.
+ * wpack: 16 KB of TF32-rounded UMMA B tiles [K8 step][16-B chunk][n][4 k]: [Wa;Wb] (n = 64), Wa+Wb (n = 32), Wc (n = 32).
+ * stats: paif_gf_guide_stats output.  out: fp32 C4 map, or a bf16 C8 map when out_bf16 != 0.
+ * paif_gf_mix_supported: C == 32 and W % 4 == 0 (otherwise use paif_gf_decomp_forward + paif_conv_forward). */
+int paif_gf_mix_supported(int C, int H, int W);
+int paif_gf_mix_forward(const float* feat, const float* residue, const float* stats, const void* wpack,
+                        const float* bias, void* out, int out_bf16, int C, int B, int H, int W, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * bf16 storage mode (forward only; north_star's 1e-2 tier).  Stems, guide and guided-filter
  * statistics stay fp32; from the 1x1 that follows the decomposition (PaifConvDesc.storage = PAIF_STORAGE_F32_BF16)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "paif_out_forward_tc": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f],
     "paif_gf_guide_stats": [_f, _f, _i, _i, _i, _f],
     "paif_gf_decomp_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_gf_mix_supported": [_i, _i, _i],
+    "paif_gf_mix_forward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f],
     "paif_conv_forward": [C.POINTER(ConvDesc), _f],
     "paif_conv_num_tiles": [_i, _i, _i],
     "paif_conv_tc_kq": [_i, _i, _i],

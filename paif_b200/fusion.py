@@ -723,14 +723,27 @@ class Cell_Decom(nn.Module):
         self.chain2 = Cell_Chain(C, types[1], concat)
 
 
-def _fold_decomp_1x1(w):
+def _fold_decomp_1x1(w, double=False):
     """conv1x1(cat[LF1, LF2, z-LF1, z-LF2]) == conv1x1'(cat[LF1, LF2, z]) (core/model_fusion_auto.py:512, :533-534)."""
     C = w.shape[0]
     w = w.detach()[:, :, 0, 0].double()
     wa = w[:, 0:C] - w[:, 2 * C:3 * C]
     wb = w[:, C:2 * C] - w[:, 3 * C:4 * C]
     wc = w[:, 2 * C:3 * C] + w[:, 3 * C:4 * C]
+    if double:
+        return wa, wb, wc
     return torch.cat([wa, wb, wc], 1).float().reshape(C, 3 * C, 1, 1)
+
+
+def _pack_gf_mix(w):
+    """Weight image of ``paif_gf_mix_forward``: TF32-rounded UMMA B tiles ``[K8 step][16-B chunk][n][4 k]`` of
+    [Wa; Wb] (n = 64), Wa + Wb (n = 32) and Wc (n = 32), 16 KB (see include/paif_b200.h)."""
+    wa, wb, wc = _fold_decomp_1x1(w, double=True)
+
+    def tile(m):                                     # [n][32 k] -> [4 steps][2 chunks][n][4]
+        return _round_tf32(m.float()).reshape(m.shape[0], 4, 2, 4).permute(1, 2, 0, 3).contiguous().reshape(-1)
+
+    return torch.cat([tile(torch.cat([wa, wb], 0)), tile(wa + wb), tile(wc)]).contiguous()
 
 
 def _merge_stem_out(w1, w2):
@@ -789,6 +802,9 @@ class Network_Fusion_Searched(nn.Module):
         self.dilconv_dense = True
         #: stem_out's merged 5x5 stencil on the tensor-core engine (False / conv_engine='direct': the FFMA kernel)
         self.out_tensor_core = True
+        #: decomposition + folded 1x1 in one kernel (paif_gf_mix_forward: channel mix between the two box-filter levels
+        #: on tcgen05, no LF maps); False / conv_engine='direct' / forward2: guided filter, then the 1x1 as a convolution
+        self.gf_fused = True
         self._pack_cache = None
         self._pack_epoch = 0
         self.last_launches = 0
@@ -812,7 +828,7 @@ class Network_Fusion_Searched(nn.Module):
         """Hashable identity of the packed weights a forward would use now (parameter versions, engine switches):
         holders of device pointers into the pack (CUDA-graph replays) compare it before reuse."""
         return (self._pack_key(need_bwd), getattr(self, "_pack_epoch", 0), self.conv_engine, self.storage,
-                self.dilconv_dense, self.out_tensor_core)
+                self.dilconv_dense, self.out_tensor_core, self.gf_fused)
 
     def _load_from_state_dict(self, *args, **kwargs):
         self.invalidate_packed()
@@ -839,6 +855,7 @@ class Network_Fusion_Searched(nn.Module):
                 "stem_a": [_slope(s[1].weight) for s in (self.stem_1, self.stem_2)],
                 "c1x1": [_ConvW(_fold_decomp_1x1(c.weight), 3, 1, 1) for c in (d.conv1x1_lf, d.conv1x1_hf)],
                 "c1x1_b": [c.bias.detach().float().contiguous() for c in (d.conv1x1_lf, d.conv1x1_hf)],
+                "gfmix_w": [_pack_gf_mix(c.weight) for c in (d.conv1x1_lf, d.conv1x1_hf)],
                 "chain_ir": d.chain.pack(need_bwd), "chain_vis": d.chain2.pack(need_bwd),
                 "chain": self.chain.pack(need_bwd),
                 "spa_w": self.spa.spatial.conv.weight.detach().reshape(4, -1).contiguous().float(),
@@ -912,18 +929,26 @@ class Network_Fusion_Searched(nn.Module):
             guides.append(g)
         d = self.decompation
         branch_out, branch_recs = [], []
+        fused_gf = (self.gf_fused and capture is None and rt.tc_engine()
+                    and bool(_lib.load().paif_gf_mix_supported(C, H, W)))
         for i, (chain, packs) in enumerate(((d.chain, p["chain_ir"]), (d.chain2, p["chain_vis"]))):
-            lf1, lf2 = rt.new_map(fp32=True), rt.new_map(fp32=True)
             stats = torch.empty((3, B, H, W), device=ir.device, dtype=torch.float32)
             rt.call("paif_gf_guide_stats", guides[i].data_ptr(), stats.data_ptr(), B, H, W)
-            rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
-                    lf1.data_ptr(), lf2.data_ptr(), C, B, H, W)
+            if fused_gf:
+                x = rt.new_map()
+                rt._meta = {"bytes": (4.0 * (C + 4) + (2.0 if bf16 else 4.0) * C) * B * H * W}
+                rt.call("paif_gf_mix_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
+                        p["gfmix_w"][i].data_ptr(), p["c1x1_b"][i].data_ptr(), x.data_ptr(), int(bf16), C, B, H, W)
+            else:
+                lf1, lf2 = rt.new_map(fp32=True), rt.new_map(fp32=True)
+                rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
+                        lf1.data_ptr(), lf2.data_ptr(), C, B, H, W)
+                x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i], src_fp32=True)[0]
+                if capture is not None:
+                    capture.setdefault("lf", []).append((lf1, lf2))
+                del lf1, lf2
             gstats.append(stats if save else None)
             del stats
-            x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i], src_fp32=True)[0]
-            if capture is not None:
-                capture.setdefault("lf", []).append((lf1, lf2))
-            del lf1, lf2
             o, recs = chain.fwd(rt, packs, x, [feats16[i] if bf16 else feats[i]])
             branch_out.append(o)
             branch_recs.append(recs)

