@@ -52,10 +52,20 @@ def parse():
                     help="timed forward steps in the bf16 storage mode (SURVEY 8 config D's precision tier; 0 = skip)")
     ap.add_argument("--eager-steps", type=int, default=3,
                     help="timed steps of the stock-PyTorch eager baseline on the same GPU (rank 0, N=1 only; 0 = skip)")
-    ap.add_argument("--pgd-consumer-bf16", action="store_true", help="run the stock consumer under bf16 autocast")
+    ap.add_argument("--pgd-consumer-dtype", default="bf16", choices=["bf16", "tf32"],
+                    help="the stock consumer runs under bf16 autocast (default) or in fp32 with TF32 matmul/conv")
     ap.add_argument("--pgd-eager", action="store_true", help="PGD leg without CUDA-graph replay of the PGD iteration")
-    ap.add_argument("--pgd-frames", type=int, default=4,
-                    help="frames per GPU for the PGD-10 robust-eval leg (0 = skip); stock-PyTorch MiT-B3-shaped consumer")
+    ap.add_argument("--pgd-frames", type=int, default=32,
+                    help="GLOBAL frames of the PGD-10 robust-eval leg, split over the GPUs (BASELINE configs[2]: "
+                         "global batch 32, strong scaling; 0 = skip)")
+    ap.add_argument("--pgd-weak-frames", type=int, default=8,
+                    help="frames PER GPU of the weak-scaling PGD-10 leg (0 = skip)")
+    ap.add_argument("--pgd-micro-batch", type=int, default=8, help="frames attacked together (per-sample min-max wrapper)")
+    ap.add_argument("--config-e-batch", type=int, default=32, help="batch of the forward+backward leg (BASELINE configs[4])")
+    ap.add_argument("--config-d-steps", type=int, default=3,
+                    help="timed steps of the 64x768x1024 fp32 / bf16 sweep (BASELINE configs[3]; N=1 only; 0 = skip)")
+    ap.add_argument("--config-b-steps", type=int, default=3,
+                    help="timed steps of fusion + SegFormer inference at batch 16 (BASELINE configs[1]; N=1 only; 0 = skip)")
     return ap.parse_args()
 
 
@@ -227,31 +237,76 @@ class SyntheticFrames:
                 torch.randint(0, 9, (self.H, self.W), generator=g))
 
 
-def run_pgd_leg(net, args, world, rank, dev, barrier):
-    """BASELINE's second metric: PGD-10 (eps 8/255, alpha 2/255, robust_test.py:40-41) robust-eval frames/s.
-    Every frame: 10 x (fusion + consumer forward, backward to the inputs) + 1 clean forward + confusion update;
-    frames are sharded over the ranks; ONE int64 all-reduce of the 9x9 confusion matrix at the end (inside the
-    timed region).  The consumer is the stock-PyTorch MiT-B3-shaped SegFormerLite (random init)."""
+def build_consumer(dev, seed=3):
+    """The segmentation consumer of the PGD / config-B legs: the reference's OWN SegFormer
+    (``core.model_fusion_auto.WeTr('mit_b3', 9, 256)`` = core/mix_transformer.py + core/segformer_head.py, unmodified,
+    imported from the staged tree with the timm / mmcv import shims) when the tree travelled with the repo, else the
+    from-scratch MiT-B3-shaped stand-in.  Stock PyTorch either way (north_star), random init, parameters frozen."""
+    import contextlib
+    import io
     import torch
-    import torch.distributed as dist
-    from paif_b200.consumer import FusionSegTask, SegFormerLite
-    from paif_b200.evaluate import robust_eval
-    torch.backends.cuda.matmul.allow_tf32 = True            # the stock consumer may use TF32 matmuls (SURVEY.md 7)
-    torch.manual_seed(3)
-    seg = SegFormerLite(9, 256).to(dev).eval()
+    from oracle import ref_loader
+    torch.manual_seed(seed)
+    if ref_loader.reference_available():
+        m = ref_loader.load_reference()
+        with contextlib.redirect_stdout(io.StringIO()):
+            seg = m.WeTr('mit_b3', 9, 256, None)
+        name = "reference WeTr('mit_b3', 9, 256) (core/mix_transformer.py + core/segformer_head.py, unmodified, staged tree)"
+    else:
+        from paif_b200.consumer import SegFormerLite
+        seg = SegFormerLite(9, 256)
+        name = "stand-in SegFormerLite (MiT-B3 shape): no reference tree on this box"
+    seg = seg.to(dev).eval()
     for p in seg.parameters():
         p.requires_grad_(False)
-    task = FusionSegTask(net, seg, consumer_autocast=torch.bfloat16 if args.pgd_consumer_bf16 else None).to(dev).eval()
+    return seg, name
+
+
+def run_pgd_leg(net, seg, seg_name, args, world, rank, dev, barrier, n_total, tag):
+    """BASELINE's second metric: PGD-10 (eps 8/255, alpha 2/255, robust_test.py:40-41) robust-eval frames/s.
+    Every frame: 10 x (fusion + consumer forward, backward to the inputs) + 1 attacked forward + confusion update;
+    ``n_total`` frames are sharded over the ranks and attacked in micro-batches through the per-sample min-max
+    wrapper (= the reference at batch 1 applied to each frame); ONE int64 all-reduce of the 9x9
+    confusion matrix at the end (inside the timed region)."""
+    import torch
+    import torch.distributed as dist
+    from paif_b200.consumer import FusionSegTask
+    from paif_b200.evaluate import robust_eval, shard_range
+    torch.backends.cuda.matmul.allow_tf32 = True            # the stock consumer may use TF32 matmuls (SURVEY.md 7)
+    torch.backends.cudnn.allow_tf32 = True
+    cast = None if args.pgd_consumer_dtype == "tf32" else torch.bfloat16
+    task = FusionSegTask(net, seg, consumer_autocast=cast, per_sample_minmax=True).to(dev).eval()
     H, W = args.height, args.width
-    n_total = args.pgd_frames * world
-    frames = SyntheticFrames(n_total + world, H, W)
+    per_gpu = len(shard_range(n_total, 0, world))
+    mb = max(1, min(args.pgd_micro_batch, per_gpu))
     graphed = not args.pgd_eager
-    robust_eval(task, [frames[n_total + rank]], attack_iters=2, use_cuda_graph=graphed)   # warm-up (allocator, autotune, capture)
+    warm = SyntheticFrames(n_total + mb * world, H, W)
+    robust_eval(task, [warm[n_total + rank * mb + i] for i in range(mb)], attack_iters=2, use_cuda_graph=graphed,
+                micro_batch=mb)                                  # warm-up: allocator, autotune, graph capture
+    barrier()
+    # fusion-only share: forward + backward-to-input of the fusion net alone at the micro-batch size
+    gout = torch.rand(mb, 1, H, W, device=dev) - 0.5
+    xi, xv = torch.rand(mb, 1, H, W, device=dev), torch.rand(mb, 1, H, W, device=dev)
+
+    def fusion_fb():
+        a, v = xi.detach().requires_grad_(True), xv.detach().requires_grad_(True)
+        net(a, v).backward(gout)
+
+    for _ in range(2):
+        fusion_fb()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(3):
+        fusion_fb()
+    f1.record()
+    torch.cuda.synchronize()
+    fusion_fb_ms = f0.elapsed_time(f1) / 3
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     meter = robust_eval(task, SyntheticFrames(n_total, H, W), attack_iters=10, rank=rank, world_size=world,
-                        use_cuda_graph=graphed)
+                        use_cuda_graph=graphed, micro_batch=mb)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -260,14 +315,53 @@ def run_pgd_leg(net, args, world, rank, dev, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     conf = meter.conf.cpu()
+    batches = (per_gpu + mb - 1) // mb
+    fusion_ms = batches * 10.5 * fusion_fb_ms                  # 10 fwd+bwd + one forward (~ half a fwd+bwd) per micro-batch
     return {"metric": "PGD-10 robust-eval frames/s", "value": n_total / (ms * 1e-3), "unit": "frames/s",
-            "frames": n_total, "frames_per_gpu": args.pgd_frames, "ms_per_frame_per_gpu": ms / max(args.pgd_frames, 1),
+            "scaling": tag, "frames": n_total, "frames_per_gpu": per_gpu, "micro_batch": mb,
+            "ms_per_frame_per_gpu": ms / max(per_gpu, 1),
+            "fusion_share": {"fusion_fwd_bwd_ms_per_micro_batch": fusion_fb_ms, "estimated_fusion_ms": fusion_ms,
+                             "fraction_of_leg": fusion_ms / ms,
+                             "note": "fusion net forward+backward-to-input timed alone at the micro-batch size x "
+                                     "(10 + 0.5) per micro-batch; the rest is the stock consumer, the loss head and the delta update"},
             "attack": "PGD-10 eps 8/255 alpha 2/255, l_seg loss, seeded start per global frame index",
-            "consumer": "stock-PyTorch SegFormerLite (MiT-B3 shape, random init, %s, params frozen)"
-                        % ("bf16 autocast" if args.pgd_consumer_bf16 else "fp32 with TF32 matmul"),
+            "consumer": "%s, %s, params frozen" % (seg_name, "fp32 with TF32 matmul/conv" if cast is None else "bf16 autocast"),
             "cuda_graph": graphed,
             "confusion_sum": int(conf.sum()), "confusion_all_reduce": "int64 SUM over %d rank(s)" % world,
             "confusion_trace": int(conf.diag().sum())}
+
+
+def measure_tf32_peak(dev, seconds=1.5):
+    """cuBLAS TF32 8192^3 the way MEASURED_PEAKS.json measures bf16: best of 10 (burst) and back to back (sustained)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        for _ in range(3):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        flops = 2.0 * n ** 3
+        return {"burst_tflops": flops / (best * 1e-3) / 1e12, "sustained_tflops": flops * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12,
+                "how": "torch.matmul fp32 inputs with allow_tf32 (cuBLAS TF32) 8192^3: best of 10, and %d back to back" % reps}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def run_reference(args):
@@ -282,8 +376,11 @@ def run_reference(args):
             "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "Network_Fusion_Searched forward, fusion_at genotype, random-init (seed 0), "
-                                   "%dx%d IR+RGB pairs; CPU arm processes 1 pair per step" % (args.height, args.width)},
+            "config": {"workload": "Network_Fusion_Searched forward, fusion_at genotype, random-init (seed 0), batch %d "
+                                   "synthetic %dx%d IR+RGB pairs per GPU (BASELINE configs[1] without the stock-PyTorch "
+                                   "SegFormer consumer)" % (args.batch, args.height, args.width),
+                       "batch_per_gpu": args.batch, "height": args.height, "width": args.width,
+                       "note": "CPU arm: each step is a bounded sample of that workload (1 pair of the batch)"},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
@@ -439,11 +536,14 @@ def run_ours(args):
     # attack inner step (BASELINE configs[4]): forward + backward-to-input on resident inputs
     fwd_bwd = None
     if args.bwd_steps > 0:
-        gout = torch.rand(B, 1, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) - 0.5
+        Be = args.config_e_batch
+        ir_e, vis_e = synth_inputs(Be, H, W, seed=11 + rank)
+        ir_e, vis_e = ir_e.to(dev), vis_e.to(dev)
+        gout = torch.rand(Be, 1, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) - 0.5
 
         def step_fwd_bwd():
-            a = ir_d.detach().requires_grad_(True)
-            v = vis_d.detach().requires_grad_(True)
+            a = ir_e.detach().requires_grad_(True)
+            v = vis_e.detach().requires_grad_(True)
             net(a, v).backward(gout)
             return a.grad, v.grad
 
@@ -452,10 +552,17 @@ def run_ours(args):
         net.profile = [] if args.table else None
         ms_fb = timed(step_fwd_bwd, args.bwd_steps)
         prof_fb, net.profile = net.profile, None
-        fwd_bwd = {"value": B * world * args.bwd_steps / (ms_fb * 1e-3), "unit": "pairs/s", "ms_per_step": ms_fb / args.bwd_steps,
-                   "steps": args.bwd_steps, "launches_per_step": net.last_launches,
-                   "what": "forward + backward-to-input (the PGD inner step of attack/attack.py:444-501 without the "
-                           "segmentation consumer), batch %d per GPU, inputs resident" % B}
+        fb_gbs = 2.0 * BYTES_PER_PX * H * W * Be * args.bwd_steps / (ms_fb * 1e-3) / 1e9
+        fwd_bwd = {"value": Be * world * args.bwd_steps / (ms_fb * 1e-3), "unit": "pairs/s", "ms_per_step": ms_fb / args.bwd_steps,
+                   "steps": args.bwd_steps, "launches_per_step": net.last_launches, "batch_per_gpu": Be,
+                   "roofline": {"bound": "hbm", "achieved": fb_gbs, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
+                                "frac": fb_gbs / peaks()["hbm_gbs"],
+                                "note": "algorithmic bytes = 2 x the forward's layer-granular plan (SURVEY 8d: 1891 ch x 4 B "
+                                        "per pixel; every backward layer reads its output gradient and writes its input "
+                                        "gradient once, mirroring the forward) / step time / measured HBM peak"},
+                   "what": "BASELINE configs[4]: forward + backward-to-input (the PGD inner step of attack/attack.py:444-501 "
+                           "without the segmentation consumer), batch %d per GPU at %dx%d, inputs resident" % (Be, H, W)}
+        del ir_e, vis_e, gout
         if args.table and rank == 0 and prof_fb:
             per = len(prof_fb) // args.bwd_steps
             agg = {}
@@ -519,7 +626,80 @@ def run_ours(args):
                                                                      m["bytes"] / (t * 1e-3) / 1e9)
             sys.stderr.write("%-28s %8.3f ms %5.1f%%%s\n" % (n, t, 100 * t / tot, extra))
         sys.stderr.write("sum of launches %.3f ms (step %.3f ms)\n" % (tot, ms / args.steps))
-    pgd = run_pgd_leg(net, args, world, rank, dev, barrier) if args.pgd_frames > 0 else None
+    torch.cuda.empty_cache()
+    pgd = pgd_weak = None
+    seg = seg_name = None
+    if args.pgd_frames > 0 or args.pgd_weak_frames > 0 or (args.config_b_steps > 0 and world == 1):
+        seg, seg_name = build_consumer(dev)
+    if args.pgd_frames > 0:
+        pgd = run_pgd_leg(net, seg, seg_name, args, world, rank, dev, barrier, max(args.pgd_frames, world), "strong")
+    if args.pgd_weak_frames > 0:
+        pgd_weak = run_pgd_leg(net, seg, seg_name, args, world, rank, dev, barrier, args.pgd_weak_frames * world, "weak")
+    for m_ in ([seg] if seg is not None else []):
+        if hasattr(m_, "_paif_pgd_runner"):
+            object.__delattr__(m_, "_paif_pgd_runner")
+    torch.cuda.empty_cache()
+
+    # BASELINE configs[1] as written: fusion + SegFormer inference at batch 16 (N = 1 only; the consumer is stock PyTorch)
+    config_b = None
+    if args.config_b_steps > 0 and world == 1 and seg is not None:
+        from paif_b200.consumer import FusionSegTask
+        cast = None if args.pgd_consumer_dtype == "tf32" else torch.bfloat16
+        task = FusionSegTask(net, seg, consumer_autocast=cast, per_sample_minmax=True).to(dev).eval()
+
+        def step_b():
+            with torch.no_grad():
+                return task(ir_d, vis_d)
+
+        for _ in range(2):
+            step_b()
+        ms_b = timed(step_b, args.config_b_steps)
+        config_b = {"value": B * args.config_b_steps / (ms_b * 1e-3), "unit": "pairs/s", "ms_per_step": ms_b / args.config_b_steps,
+                    "fusion_ms_per_step": ms / args.steps, "batch": B,
+                    "what": "BASELINE configs[1] (test_original.py path): colour glue + fusion drop-in + SegFormer inference, "
+                            "batch %d synthetic %dx%d, 1 GPU" % (B, H, W),
+                    "consumer": "%s, %s" % (seg_name, "fp32 with TF32 matmul/conv" if cast is None else "bf16 autocast")}
+        del task
+    seg = None
+    torch.cuda.empty_cache()
+
+    # BASELINE configs[3]: fusion-only sweep at the M3FD shape 768x1024, batch 64, fp32 storage vs bf16 storage, with a
+    # max-abs check of one sample of each against the CPU arm (N = 1 only)
+    config_d = None
+    if args.config_d_steps > 0 and world == 1 and args.engine != "direct":
+        Bd, Hd, Wd = 64, 768, 1024
+        ir_b, vis_b = synth_inputs(Bd, Hd, Wd, seed=21)
+        ir_b, vis_b = ir_b.to(dev), vis_b.to(dev)
+        config_d = {"what": "BASELINE configs[3]: fusion-only forward at %dx%d, batch %d, fp32 (TF32 MMA) vs bf16 storage" % (Hd, Wd, Bd)}
+        outs = {}
+        for mode in ("fp32", "bf16"):
+            net.storage = mode
+
+            def step_d():
+                with torch.no_grad():
+                    return net(ir_b, vis_b)
+
+            for _ in range(2):
+                step_d()
+            ms_d = timed(step_d, args.config_d_steps)
+            outs[mode] = step_d()[0:1].cpu()
+            bpp = BYTES_PER_PX if mode == "fp32" else BYTES_PER_PX / 2
+            config_d[mode] = {"value": Bd * args.config_d_steps / (ms_d * 1e-3), "unit": "pairs/s",
+                              "ms_per_step": ms_d / args.config_d_steps,
+                              "whole_step_frac_of_hbm_roof": (bpp * Hd * Wd * Bd * args.config_d_steps / (ms_d * 1e-3) / 1e9) / peaks()["hbm_gbs"]}
+        net.storage = 'fp32'
+        if not args.no_cpu_baseline:
+            _, sd_ = synth_state()
+            kind_, fwd_, _g = cpu_arm(sd_)
+            torch.set_num_threads(os.cpu_count() or 1)
+            with torch.no_grad():
+                ref_d = fwd_(ir_b[0:1].cpu(), vis_b[0:1].cpu())
+            config_d["parity"] = {"cpu_arm": kind_, "sample": "pair 0 of the timed batch",
+                                  "max_abs_fp32_storage": (outs["fp32"] - ref_d).abs().max().item(), "tolerance_fp32": 1e-3,
+                                  "max_abs_bf16_storage": (outs["bf16"] - ref_d).abs().max().item(), "tolerance_bf16": 1e-2}
+        del ir_b, vis_b, outs
+        torch.cuda.empty_cache()
+    tf32_peak = measure_tf32_peak(dev) if (rank == 0 and world == 1) else None
     clocks = sampler.summary() if sampler else None          # sampled across every timed GPU leg above
 
     # dominant kernel: the dense-conv engine (all conv launches of the timed steps).  After the wide-N MMA
@@ -532,7 +712,25 @@ def run_ours(args):
     conv_bytes = sum(m["bytes"] for m, _ in conv)
     pk = peaks()
     engine_id = conv[0][0]["engine"] if conv else 0
-    peak_tf = pk["bf16_tflops_sustained"] / 2.0
+    peak_tf = tf32_peak["sustained_tflops"] if tf32_peak else pk["bf16_tflops_sustained"] / 2.0
+    # every launch of the step against its own roofline (algorithmic bytes / flops from the call site, CUDA-event time)
+    per = len(prof) // max(args.steps, 1)
+    agg = {}
+    for i, (n, m, a, b) in enumerate(prof):
+        key = (i % per, n)
+        e = agg.setdefault(key, {"name": n, "ms": 0.0, "bytes": (m or {}).get("bytes"), "flops": (m or {}).get("flops"),
+                                 "shape": ("k%d d%d cin%d" % (m["k"], m["dil"], m["cin"])) if (m and "k" in m) else None})
+        e["ms"] += a.elapsed_time(b) / max(args.steps, 1)
+    per_kernel = []
+    for key in sorted(agg):
+        e = agg[key]
+        if e["bytes"]:
+            gbs = e["bytes"] / (e["ms"] * 1e-3) / 1e9
+            e["gbs"], e["frac_hbm"] = gbs, gbs / pk["hbm_gbs"]
+        if e["flops"]:
+            e["tflops"] = e["flops"] / (e["ms"] * 1e-3) / 1e12
+            e["frac_tf32"] = e["tflops"] / peak_tf
+        per_kernel.append({k: v for k, v in e.items() if v is not None})
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     achieved_gbs = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
     traffic = None
@@ -569,11 +767,15 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "dense-conv engine conv_tc_kernel (all %d conv launches per step)" % (len(conv) // max(args.steps, 1)),
                      "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
-                     "traffic": traffic, "peak_note": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % pk["source"],
+                     "traffic": traffic, "traffic_source": "static: profiles/conv_traffic.json (ncu --set full capture of the "
+                                                           "conv launches; not re-measured by this run)",
+                     "peak_note": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % pk["source"],
                      "bytes_per_launch": conv_bytes / max(len(conv), 1), "avg_launch_ms": conv_ms / max(len(conv), 1),
                      "conv_share_of_step": conv_ms / (conv_ms + other_ms) if conv_ms + other_ms > 0 else None,
                      "tensor_tflops": achieved_tf, "tensor_frac_of_tf32_peak": achieved_tf / peak_tf,
-                     "tf32_peak_note": "TF32 = 1/2 x %s sustained bf16 cuBLAS peak" % pk["source"],
+                     "tf32_peak_note": ("cuBLAS TF32 8192^3 measured by this run (sustained)" if tf32_peak else
+                                        "TF32 = 1/2 x %s sustained bf16 cuBLAS peak" % pk["source"]),
+                     "per_kernel": per_kernel,
                      "whole_step_frac_of_hbm_roof": (BYTES_PER_PX * H * W * B * args.steps / (ms * 1e-3) / 1e9) / pk["hbm_gbs"],
                      "whole_step_note": "SURVEY 8d layer-granular bytes (1891 ch x 4 B per pixel) / step time / HBM peak"},
         "clocks": clocks,
@@ -594,6 +796,14 @@ def run_ours(args):
             line["torch_eager_same_gpu"] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
     if pgd is not None:
         line["pgd10"] = pgd
+    if pgd_weak is not None:
+        line["pgd10_weak"] = pgd_weak
+    if config_b is not None:
+        line["config_b"] = config_b
+    if config_d is not None:
+        line["config_d"] = config_d
+    if tf32_peak is not None:
+        line["tf32_peak"] = tf32_peak
     if not args.no_cpu_baseline and world == 1:
         v, cores, times, kind = cpu_port_pairs_per_s(args.cpu_baseline_steps, H, W)
         st = sorted(times)
@@ -603,6 +813,16 @@ def run_ours(args):
                                 "min_ms": 1e3 * st[0], "median_ms": 1e3 * st[len(st) // 2],
                                 "fwd_bwd_pairs_per_s": cpu_port_fwd_bwd_pairs_per_s(2, H, W),
                                 "fwd_bwd_sample": "2 timed forward+backward-to-input passes of 1 pair (autograd of the same module) after 1 warm-up"}
+        _, sd0 = synth_state()
+        kind0, fwd0, _g0 = cpu_arm(sd0)
+        with torch.no_grad():
+            ref0 = fwd0(ir_h[0:1], vis_h[0:1])
+            got0 = net(ir_d[0:1].contiguous(), vis_d[0:1].contiguous()).cpu()
+            got16 = net(ir_d, vis_d)[0:1].cpu()
+        line["parity"] = {"cpu_arm": kind0, "what": "pair 0 of the timed batch: the drop-in's output (alone and inside the timed "
+                          "batch of %d) against the CPU arm on the same weights and inputs" % B,
+                          "max_abs_batch1": (got0 - ref0).abs().max().item(), "max_abs_in_timed_batch": (got16 - ref0).abs().max().item(),
+                          "tolerance": 1e-3 if engine_id == _lib.ENGINE_TCGEN05 else 5e-5}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -118,10 +118,14 @@ class FusionSegTask(nn.Module):
     """``Network_MM_CompModel``-style task model (core/model_fusion_auto.py:698-729) around any fusion
     module with ``forward(ir, vis) -> [B,1,H,W]`` and any consumer ``[B,3,H,W] -> logits``."""
 
-    def __init__(self, fusion, consumer, consumer_autocast=None):
+    def __init__(self, fusion, consumer, consumer_autocast=None, per_sample_minmax=False):
         super().__init__()
         self.enhance_net = fusion
         self.denoise_net = consumer
+        #: False: min-max over the whole batch, exactly as the reference wrapper (core/model_fusion_auto.py:721-723),
+        #: which only ever sees batch 1.  True: min-max per sample = "the reference at B = 1 applied to each sample"
+        #: (SURVEY.md 8e caveat 1): what lets an evaluation harness batch frames without coupling them.
+        self.per_sample_minmax = per_sample_minmax
         #: optional torch dtype (e.g. torch.bfloat16): run the stock consumer under torch.autocast — one of the
         #: mitigations SURVEY.md 7 allows for the consumer; the fusion path is unaffected (it takes and returns fp32)
         self.consumer_autocast = consumer_autocast
@@ -146,7 +150,10 @@ class FusionSegTask(nn.Module):
         ycc = self.rgb_to_ycrcb(vis)
         fused = self.enhance_net(ir[:, 0:1], ycc[:, 0:1])
         rgb = self.ycrcb_to_rgb(torch.cat([fused, ycc[:, 1:3]], 1)).clamp(0.0, 1.0)
-        lo, hi = rgb.min(), rgb.max()                      # spans the batch, as the reference does (:721-723)
+        if self.per_sample_minmax:
+            lo, hi = rgb.amin((1, 2, 3), keepdim=True), rgb.amax((1, 2, 3), keepdim=True)
+        else:
+            lo, hi = rgb.min(), rgb.max()                  # spans the batch, as the reference does (:721-723)
         rgb = (rgb - lo) / (hi - lo).clamp_min(1e-12)
         x = (rgb * 255.0 - self.mean) / self.std
         if self.consumer_autocast is not None:

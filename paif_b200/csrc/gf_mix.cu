@@ -21,10 +21,26 @@
 //              of (A', b') that the vertical running sum needs lives in TMEM (tcgen05.st / ld, 32 columns per row and
 //              warp: 9 x 32 columns next to the 128 accumulator columns); output = mean2(A') g + mean2(b') + C.
 // The level-2 history is what bounds the strip width: 9 rows x 64 values x 4 B = 2.3 KB per pixel column.
+#define PAIF_MBAR_SPIN_LIMIT (1u << 21)        // a lost arrival traps after a few seconds instead of minutes
+#define PAIF_MBAR_QUIET
+#define PAIF_MBAR_SUSPEND_NS 20000
 #include "tc_ptx.cuh"
 
 namespace paif {
 namespace gx {
+
+#ifdef PAIF_TC_PROFILE
+// development-only role timeline: wait / busy cycles summed over all CTAs (read with paif_debug_gx_counters)
+__device__ unsigned long long gx_prof[16];
+#define GX_PROF_DECL long long prof_wait = 0, prof_t0 = clock64()
+#define GX_WAIT(stmt) do { const long long t_ = clock64(); stmt; prof_wait += clock64() - t_; } while (0)
+#define GX_PROF_END(slot) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&gx_prof[(slot) * 2], (unsigned long long)prof_wait); \
+                                   atomicAdd(&gx_prof[(slot) * 2 + 1], (unsigned long long)(clock64() - prof_t0)); } } while (0)
+#else
+#define GX_PROF_DECL
+#define GX_WAIT(stmt) stmt
+#define GX_PROF_END(slot)
+#endif
 
 constexpr int OUTW = 48;                       // output columns per strip (64 raw -> 56 level-1 -> 48 output)
 constexpr int NWARPS = 14, NT = NWARPS * 32;
@@ -32,16 +48,18 @@ constexpr int MMA_WARP = 12;            // warp 13: producer
 constexpr int AOP_SBO = 144;                   // core-matrix pitch of the A operand (128 B + 16 B pad: conflict-free 4-column stores)
 constexpr int AOP_PLANE = 16 * AOP_SBO;        // one 16-byte K chunk (4 channels) x 128 rows
 constexpr int AOP_BYTES = 16 * AOP_PLANE;      // planes 0-7: cov quads, 8-15: mean_z quads
-constexpr int X_PLANE = 2048;                  // exchange: [plane][row half][64 slots][16 B]
+constexpr int X_PLANE = 1024;                  // exchange, one buffer per row of the pair: [plane][64 slots][16 B]
 constexpr int X_BYTES = 24 * X_PLANE;          // planes 0-7 A', 8-15 b', 16-23 C
 constexpr int Z_BYTES = 8 * 2048;              // 8 quad planes x 128 rows x 16 B (rows 0-63: first output row, 64-127: second)
 constexpr int W_BYTES = 16384;                 // [Wa|Wb] 8 KB, Wa+Wb 4 KB, Wc 4 KB (TF32, UMMA B tiles)
+constexpr int RS = 6;                          // raw-row ring stages (entering rows of the level-1 window, fetched by the producer)
+constexpr int R_BYTES = 8 * 1024 + 256;        // 8 quad planes x 64 pixels x 16 B + 64 guide values
 constexpr int OFF_W = 0, OFF_AOP = OFF_W + W_BYTES, OFF_X = OFF_AOP + 2 * AOP_BYTES, OFF_Z = OFF_X + 2 * X_BYTES,
-              OFF_BARS = OFF_Z + 2 * Z_BYTES, SMEM_BYTES = OFF_BARS + 1024;
+              OFF_R = OFF_Z + 2 * Z_BYTES, OFF_BARS = OFF_R + RS * R_BYTES, SMEM_BYTES = OFF_BARS + 1024;
 constexpr int RING_COL0 = 128, RING_SLOTS = 9;
 
 struct Bars {
-    uint64_t aop_full[2], aop_empty[2], z_full[2], x_full[2], x_empty[2], d_full, d_empty;
+    uint64_t aop_full[2], aop_empty[2], z_full[2], x_full[2], x_empty[2], d_full, d_empty, r_full[RS], r_empty[RS];
     uint32_t tmem_base;
     alignas(16) float bias[32];
 };
@@ -79,18 +97,31 @@ __device__ __forceinline__ void hsum9c(const float (&s)[4][4], int c, float (&o)
 }
 // 4 consecutive floats of a plane row (x multiple of 4, W multiple of 4): zero outside [0, W)
 __device__ __forceinline__ void ld_cols4(const float* __restrict__ row, int x, int W, float (&v)[4]) {
-    if (x >= 0 && x < W) { const float4 t = __ldg(reinterpret_cast<const float4*>(row + x)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else { v[0] = v[1] = v[2] = v[3] = 0.f; }
+    // branch-free: the address is clamped into the row, the value selected afterwards (no divergence around the shuffles)
+    const bool ok = x >= 0 && x < W;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(row + (ok ? x : 0)));
+    v[0] = ok ? t.x : 0.f; v[1] = ok ? t.y : 0.f; v[2] = ok ? t.z : 0.f; v[3] = ok ? t.w : 0.f;
 }
 // the 4 channels of one quad at pixels x..x+3 of a C4 map row (`row` -> (quad plane, row y, pixel 0)); zero outside
 __device__ __forceinline__ void ld_quad(const float* __restrict__ row, int x, int W, float (&z)[4][4]) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int xx = x + k;
-        if (xx >= 0 && xx < W) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(row + (size_t)xx * 4));
-            z[k][0] = t.x; z[k][1] = t.y; z[k][2] = t.z; z[k][3] = t.w;
-        } else { z[k][0] = z[k][1] = z[k][2] = z[k][3] = 0.f; }
+        const bool ok = xx >= 0 && xx < W;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(row + (size_t)(ok ? xx : 0) * 4));
+        z[k][0] = ok ? t.x : 0.f; z[k][1] = ok ? t.y : 0.f; z[k][2] = ok ? t.z : 0.f; z[k][3] = ok ? t.w : 0.f;
+    }
+}
+// Unmasked variants: the address is clamped into the row and the caller applies the column mask where the value is USED
+// (one iteration later) — a select placed next to the load would make the warp wait for the load right there.
+__device__ __forceinline__ float4 ld_cols4_raw(const float* __restrict__ row, int x, int W) {
+    return __ldg(reinterpret_cast<const float4*>(row + ((x >= 0 && x < W) ? x : 0)));
+}
+__device__ __forceinline__ void ld_quad_raw(const float* __restrict__ row, int x, int W, float4 (&z)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xx = x + k;
+        z[k] = __ldg(reinterpret_cast<const float4*>(row + (size_t)((xx >= 0 && xx < W) ? xx : 0) * 4));
     }
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
@@ -109,6 +140,48 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
           "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
           "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
         : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32_nowait(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+// tcgen05.ld without the wait: the caller issues tcgen05.wait::ld before it reads v[]
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// completes a tmem_ld32_nowait: the registers are operands of the wait so that no use of v[] can be scheduled above it
+__device__ __forceinline__ void tmem_wait_ld32(float (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]),
+                   "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]),
+                   "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
 }
 
 // one work chunk: rows [y0, y0 + rows) of strip `strip` of image b
@@ -137,11 +210,12 @@ struct Walker {
 __device__ __forceinline__ int xslot(int j, int k) { return (k << 4) + (j ^ (k << 1)); }
 
 template <bool OUT_BF>
-__global__ void __maxnreg__(144)          // 448 threads x 144 registers: one CTA per SM
+__global__ void __launch_bounds__(NT, 1)    // 14 warps = up to 4 per SM sub-partition (16 K registers each): 128 registers per thread
 gf_mix_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + OFF_BARS);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: the role branches do not diverge
     const int H = p.H, W = p.W;
     const size_t plane = (size_t)H * W;
 
@@ -150,9 +224,10 @@ gf_mix_kernel(const Params p) {
             mbar_init(smem_u32(&bars->aop_full[i]), 128);
             mbar_init(smem_u32(&bars->aop_empty[i]), 1);
             mbar_init(smem_u32(&bars->z_full[i]), 1);
-            mbar_init(smem_u32(&bars->x_full[i]), 128);
+            mbar_init(smem_u32(&bars->x_full[i]), 64);        // the 64 EP threads of that row of the pair
             mbar_init(smem_u32(&bars->x_empty[i]), 128);
         }
+        for (int i = 0; i < RS; ++i) { mbar_init(smem_u32(&bars->r_full[i]), 1); mbar_init(smem_u32(&bars->r_empty[i]), 128); }
         mbar_init(smem_u32(&bars->d_full), 1);
         mbar_init(smem_u32(&bars->d_empty), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -180,6 +255,9 @@ gf_mix_kernel(const Params p) {
         unsigned char* aop = smem + OFF_AOP;
         // byte offset of row m = half*64 + 4j + k inside a plane: (m >> 3) * SBO + (m & 7) * 16
         const int aoff = (j >> 1) * AOP_SBO + (j & 1) * 64;
+        const unsigned char* ring = smem + OFF_R;
+        uint32_t rcount = 0;                                   // raw rows taken from the ring so far
+        GX_PROF_DECL;
         while (walk.next(ck)) {
             const int x0 = ck.strip * OUTW, y0 = ck.y0, rows = ck.rows;
             const int xr = x0 - 8 + 4 * j, xs = xr + 4;
@@ -187,60 +265,84 @@ gf_mix_kernel(const Params p) {
             const float* gp = p.guide + (size_t)ck.b * plane;
             const float* mxp = p.stats + (size_t)ck.b * plane;
             float cs[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                cs[k] = (xs + k >= 0 && xs + k < W && 4 * j + k < 56) ? __frcp_rn(win_count(xs + k, W)) : 0.f;
-            float Sz[4][4], Sgz[4][4], zn[4][4], zq[4][4], gn[4], gq[4];
+            bool cin[4];                                           // raw column inside the image
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                gq[k] = 0.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) { Sz[k][c] = Sgz[k][c] = zq[k][c] = 0.f; }
+                cs[k] = (xs + k >= 0 && xs + k < W && 4 * j + k < 56) ? __frcp_rn(win_count(xs + k, W)) : 0.f;
+                cin[k] = xr + k >= 0 && xr + k < W;
             }
-            {
-                const int yr = y0 - 8;
-                if (yr >= 0) { ld_quad(zp + (size_t)yr * W * 4, xr, W, zn); ld_cols4(gp + (size_t)yr * W, xr, W, gn); }
-                else {
+            float Sz[4][4], Sgz[4][4];
+            float4 zq4[4], gq4, mx4;                               // leaving row / mean_g of the next iteration, unmasked
+            bool lvq = false;                                      // ... and whether that leaving row exists
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { gn[k] = 0.f; zn[k][0] = zn[k][1] = zn[k][2] = zn[k][3] = 0.f; }
-                }
+            for (int k = 0; k < 4; ++k) {
+                zq4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) Sz[k][c] = Sgz[k][c] = 0.f;
             }
+            gq4 = mx4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const int n1 = rows + 8, nt = rows + 16;
             for (int t = 0; t < nt; ++t) {
                 const int yr = y0 - 8 + t;
+                // ---- leaving row (fetched from global memory one iteration ago): masks applied here, at the use
+                float zq[4][4], gq[4];
+                {
+                    const float gqr[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        Sz[k][c] += zn[k][c] - zq[k][c];
-                        Sgz[k][c] = __fmaf_rn(-gq[k], zq[k][c], __fmaf_rn(gn[k], zn[k][c], Sgz[k][c]));
+                    for (int k = 0; k < 4; ++k) {
+                        const bool m = lvq && cin[k];
+                        gq[k] = m ? gqr[k] : 0.f;
+                        zq[k][0] = m ? zq4[k].x : 0.f; zq[k][1] = m ? zq4[k].y : 0.f;
+                        zq[k][2] = m ? zq4[k].z : 0.f; zq[k][3] = m ? zq4[k].w : 0.f;
                     }
-                {   // rows of iteration t+1: entering yr+1, leaving yr-8
-                    const int yn = yr + 1, yl = yr - 8;
-                    if (t + 1 < nt && yn >= 0 && yn < H) { ld_quad(zp + (size_t)yn * W * 4, xr, W, zn); ld_cols4(gp + (size_t)yn * W, xr, W, gn); }
-                    else {
+                }
+                const float mxc[4] = {mx4.x, mx4.y, mx4.z, mx4.w};     // mean_g of the level-1 row this iteration completes
+                {   // global loads for iteration t+1: leaving row yr-8 (an L2 hit: it entered 9 rows ago), mean_g of row yr-3.
+                    // Always issued, with row and column clamped into the image: whether they count is decided at the use.
+                    const int yl = yr - 8, ysn = yr - 3;
+                    lvq = t + 1 < nt && t + 1 >= 9 && yl >= 0 && yl < H;
+                    const int ylc = min(max(yl, 0), H - 1), ysc = min(max(ysn, 0), H - 1);
+                    ld_quad_raw(zp + (size_t)ylc * W * 4, xr, W, zq4);
+                    gq4 = ld_cols4_raw(gp + (size_t)ylc * W, xr, W);
+                    mx4 = ld_cols4_raw(mxp + (size_t)ysc * W, xs, W);
+                }
+                // ---- entering row: from the shared-memory ring the producer fills a few rows ahead
+                float zn[4][4], gn[4];
+                {
+                    const uint32_t st = rcount % RS;
+                    GX_WAIT(mbar_wait(smem_u32(&bars->r_full[st]), (rcount / RS) & 1u));
+                    if (yr >= 0 && yr < H) {
+                        const unsigned char* rs_ = ring + st * R_BYTES;
+                        const float4 g4 = *reinterpret_cast<const float4*>(rs_ + 8192 + j * 16);
+                        gn[0] = cin[0] ? g4.x : 0.f; gn[1] = cin[1] ? g4.y : 0.f; gn[2] = cin[2] ? g4.z : 0.f; gn[3] = cin[3] ? g4.w : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 v = *reinterpret_cast<const float4*>(rs_ + q * 1024 + (4 * j + k) * 16);
+                            zn[k][0] = cin[k] ? v.x : 0.f; zn[k][1] = cin[k] ? v.y : 0.f;
+                            zn[k][2] = cin[k] ? v.z : 0.f; zn[k][3] = cin[k] ? v.w : 0.f;
+                        }
+                    } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { gn[k] = 0.f; zn[k][0] = zn[k][1] = zn[k][2] = zn[k][3] = 0.f; }
                     }
-                    if (t + 1 >= 9 && yl >= 0 && yl < H) { ld_quad(zp + (size_t)yl * W * 4, xr, W, zq); ld_cols4(gp + (size_t)yl * W, xr, W, gq); }
-                    else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) { gq[k] = 0.f; zq[k][0] = zq[k][1] = zq[k][2] = zq[k][3] = 0.f; }
-                    }
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            Sz[k][c] += zn[k][c] - zq[k][c];
+                            Sgz[k][c] = __fmaf_rn(-gq[k], zq[k][c], __fmaf_rn(gn[k], zn[k][c], Sgz[k][c]));
+                        }
+                    mbar_arrive(smem_u32(&bars->r_empty[st]));       // after the values were consumed
+                    ++rcount;
                 }
                 if (t < 8) continue;
                 const int r1 = t - 8, ys = yr - 4, half = r1 & 1;
                 const uint32_t gpair = gp0 + (uint32_t)(r1 >> 1), buf = gpair & 1u;
-                if (half == 0) mbar_wait(smem_u32(&bars->aop_empty[buf]), ((gpair >> 1) & 1u) ^ 1u);
-                float mx[4], rn[4];
-                if (ys >= 0 && ys < H) {
-                    ld_cols4(mxp + (size_t)ys * W, xs, W, mx);
-                    const float rcy = __frcp_rn(win_count(ys, H));
+                float rn[4];
+                {
+                    const float rcy = (ys >= 0 && ys < H) ? __frcp_rn(win_count(ys, H)) : 0.f;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) rn[k] = rcy * cs[k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) mx[k] = rn[k] = 0.f;
                 }
                 float mz[4][4], cov[4][4];
 #pragma unroll
@@ -251,9 +353,10 @@ gf_mix_kernel(const Params p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         mz[k][c] = bz[k] * rn[k];
-                        cov[k][c] = __fmaf_rn(-mx[k], mz[k][c], bg[k] * rn[k]);
+                        cov[k][c] = __fmaf_rn(-mxc[k], mz[k][c], bg[k] * rn[k]);
                     }
                 }
+                if (half == 0) GX_WAIT(mbar_wait(smem_u32(&bars->aop_empty[buf]), ((gpair >> 1) & 1u) ^ 1u));
                 unsigned char* base = aop + buf * AOP_BYTES + half * (8 * AOP_SBO) + aoff;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -267,6 +370,7 @@ gf_mix_kernel(const Params p) {
             }
             gp0 += (uint32_t)((n1 + 1) >> 1);
         }
+        GX_PROF_END(0);
     } else if (warp < 8) {
         // ============================ L2: level-2 box filters -> output ============================
         const int w2 = warp & 3, h = lane >> 4, j = lane & 15, q = 2 * w2 + h;
@@ -275,6 +379,7 @@ gf_mix_kernel(const Params p) {
         int xo_slot[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) xo_slot[k] = xslot(j, k) * 16;
+        GX_PROF_DECL;
         while (walk.next(ck)) {
             const int x0 = ck.strip * OUTW, y0 = ck.y0, rows = ck.rows;
             const int xo = x0 + 4 * j;
@@ -286,96 +391,115 @@ gf_mix_kernel(const Params p) {
             float S[32];                                           // [A' | b'] x [column k][channel c]: index e*16 + k*4 + c
 #pragma unroll
             for (int i = 0; i < 32; ++i) S[i] = 0.f;
-            const int n1 = rows + 8, npairs = (n1 + 1) >> 1;
+            const int n1 = rows + 8;
             int slot = 0;
-            for (int pl = 0; pl < npairs; ++pl) {
-                const uint32_t gpair = gp0 + (uint32_t)pl, xb = gpair & 1u;
-                mbar_wait(smem_u32(&bars->x_full[xb]), (gpair >> 1) & 1u);
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);           // guide at the next output row (fetched one row ahead)
+            for (int r1 = 0; r1 < ((n1 + 1) & ~1); ++r1) {
+                const int half = r1 & 1;
+                const uint32_t gpair = gp0 + (uint32_t)(r1 >> 1);
+                if (r1 >= n1) {
+                    // odd row count: the second row of the last pair does not exist, but EP hands over both rows of
+                    // every pair — take it and give it back so that the barrier phases stay in step
+                    GX_WAIT(mbar_wait(smem_u32(&bars->x_full[half]), gpair & 1u));
+                    mbar_arrive(smem_u32(&bars->x_empty[half]));
+                    continue;
+                }
+                float od[32];
+                if (r1 >= RING_SLOTS) tmem_ld32_nowait(ring + slot * 32, od);      // the row leaving the vertical window
+                GX_WAIT(mbar_wait(smem_u32(&bars->x_full[half]), gpair & 1u));
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // the previous row's ring store has read its registers
+                const unsigned char* xrow = xbuf + half * X_BYTES;
+                float nw[32];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int r1 = 2 * pl + half;
-                    if (r1 < n1) {
-                        const unsigned char* xrow = xbuf + xb * X_BYTES + half * 1024;
-                        float nw[32];
+                for (int k = 0; k < 4; ++k) {
+                    const float4 a = *reinterpret_cast<const float4*>(xrow + q * X_PLANE + xo_slot[k]);
+                    const float4 bb = *reinterpret_cast<const float4*>(xrow + (8 + q) * X_PLANE + xo_slot[k]);
+                    nw[k * 4 + 0] = a.x; nw[k * 4 + 1] = a.y; nw[k * 4 + 2] = a.z; nw[k * 4 + 3] = a.w;
+                    nw[16 + k * 4 + 0] = bb.x; nw[16 + k * 4 + 1] = bb.y; nw[16 + k * 4 + 2] = bb.z; nw[16 + k * 4 + 3] = bb.w;
+                }
+                float4 cc[4];
+                if (r1 >= 8) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float4 a = *reinterpret_cast<const float4*>(xrow + q * X_PLANE + xo_slot[k]);
-                            const float4 bb = *reinterpret_cast<const float4*>(xrow + (8 + q) * X_PLANE + xo_slot[k]);
-                            nw[k * 4 + 0] = a.x; nw[k * 4 + 1] = a.y; nw[k * 4 + 2] = a.z; nw[k * 4 + 3] = a.w;
-                            nw[16 + k * 4 + 0] = bb.x; nw[16 + k * 4 + 1] = bb.y; nw[16 + k * 4 + 2] = bb.z; nw[16 + k * 4 + 3] = bb.w;
-                        }
-                        if (r1 >= RING_SLOTS) {
-                            float od[32];
-                            tmem_ld32(ring + slot * 32, od);
+                    for (int k = 0; k < 4; ++k) cc[k] = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]);
+                }
+                if (r1 >= RING_SLOTS) {
+                    tmem_wait_ld32(od);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) S[i] += nw[i] - od[i];
-                        } else {
+                    for (int i = 0; i < 32; ++i) S[i] += nw[i] - od[i];
+                } else {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) S[i] += nw[i];
-                        }
-                        tmem_st32(ring + slot * 32, nw);
-                        slot = slot == RING_SLOTS - 1 ? 0 : slot + 1;
-                        if (r1 >= 8) {
-                            const int yo = y0 + r1 - 8;
-                            float g[4], rno[4];
-                            ld_cols4(gp + (size_t)yo * W, xo, W, g);
-                            const float rcy = __frcp_rn(win_count(yo, H));
+                    for (int i = 0; i < 32; ++i) S[i] += nw[i];
+                }
+                tmem_st32_nowait(ring + slot * 32, nw);
+                slot = slot == RING_SLOTS - 1 ? 0 : slot + 1;
+                mbar_arrive(smem_u32(&bars->x_empty[half]));           // (A', b', C) of this row are in registers
+                const float gc[4] = {g4.x, g4.y, g4.z, g4.w};
+                {   // guide of the NEXT output row (row clamped into the chunk, columns into the image: only stored pixels
+                    // use it): in flight during this row's horizontal sums
+                    const int yon = min(max(y0 + r1 - 7, y0), y0 + rows - 1);
+                    g4 = ld_cols4_raw(gp + (size_t)yon * W, xo, W);
+                }
+                if (r1 >= 8) {
+                    const int yo = y0 + r1 - 8;
+                    float rno[4];
+                    const float rcy = __frcp_rn(win_count(yo, H));
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) rno[k] = rcy * co[k];
-                            float o[4][4];
+                    for (int k = 0; k < 4; ++k) rno[k] = rcy * co[k];
+                    float o[4][4];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const float sa[4] = {S[c], S[4 + c], S[8 + c], S[12 + c]};
-                                const float sb[4] = {S[16 + c], S[20 + c], S[24 + c], S[28 + c]};
-                                float hA[4], hb[4];
-                                hsum9(sa, hA);
-                                hsum9(sb, hb);
+                    for (int c = 0; c < 4; ++c) {
+                        const float sa[4] = {S[c], S[4 + c], S[8 + c], S[12 + c]};
+                        const float sb[4] = {S[16 + c], S[20 + c], S[24 + c], S[28 + c]};
+                        float hA[4], hb[4];
+                        hsum9(sa, hA);
+                        hsum9(sb, hb);
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) o[k][c] = __fmaf_rn(hA[k] * rno[k], g[k], hb[k] * rno[k]);
-                            }
+                        const float ccc[4] = {c == 0 ? cc[0].x : c == 1 ? cc[0].y : c == 2 ? cc[0].z : cc[0].w,
+                                              c == 0 ? cc[1].x : c == 1 ? cc[1].y : c == 2 ? cc[1].z : cc[1].w,
+                                              c == 0 ? cc[2].x : c == 1 ? cc[2].y : c == 2 ? cc[2].z : cc[2].w,
+                                              c == 0 ? cc[3].x : c == 1 ? cc[3].y : c == 2 ? cc[3].z : cc[3].w};
+                        // mean2(A') g + mean2(b') + C = (hA g + hb) / N2 + C
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float4 cc = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]);
-                                o[k][0] += cc.x; o[k][1] += cc.y; o[k][2] += cc.z; o[k][3] += cc.w;
-                            }
-                            if constexpr (!OUT_BF) {
-                                float* orow = static_cast<float*>(p.out) + (((size_t)ck.b * 8 + q) * plane + (size_t)yo * W) * 4;
+                        for (int k = 0; k < 4; ++k) o[k][c] = __fmaf_rn(__fmaf_rn(hA[k], gc[k], hb[k]), rno[k], ccc[k]);
+                    }
+                    if constexpr (!OUT_BF) {
+                        float* orow = static_cast<float*>(p.out) + (((size_t)ck.b * 8 + q) * plane + (size_t)yo * W) * 4;
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (co[k] > 0.f)
-                                        *reinterpret_cast<float4*>(orow + (size_t)(xo + k) * 4) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
-                            } else {
-                                // C8 bf16 pixel vectors: the two half-warps hold the two quads of oct w2; lanes of half 0
-                                // assemble columns 0-1, lanes of half 1 columns 2-3
-                                float r[2][4];
+                        for (int k = 0; k < 4; ++k)
+                            if (co[k] > 0.f)
+                                *reinterpret_cast<float4*>(orow + (size_t)(xo + k) * 4) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+                    } else {
+                        // C8 bf16 pixel vectors: the two half-warps hold the two quads of oct w2; lanes of half 0
+                        // assemble columns 0-1, lanes of half 1 columns 2-3
+                        float r[2][4];
 #pragma unroll
-                                for (int i = 0; i < 2; ++i)
+                        for (int i = 0; i < 2; ++i)
 #pragma unroll
-                                    for (int c = 0; c < 4; ++c)
-                                        r[i][c] = __shfl_xor_sync(0xffffffffu, h == 0 ? o[2 + i][c] : o[i][c], 16);
-                                uint4* orow = static_cast<uint4*>(p.out) + ((size_t)ck.b * 4 + w2) * plane + (size_t)yo * W;
+                            for (int c = 0; c < 4; ++c)
+                                r[i][c] = __shfl_xor_sync(0xffffffffu, h == 0 ? o[2 + i][c] : o[i][c], 16);
+                        uint4* orow = static_cast<uint4*>(p.out) + ((size_t)ck.b * 4 + w2) * plane + (size_t)yo * W;
 #pragma unroll
-                                for (int i = 0; i < 2; ++i) {
-                                    const int kk = h == 0 ? i : 2 + i;
-                                    const float4 mine = make_float4(o[kk][0], o[kk][1], o[kk][2], o[kk][3]);
-                                    const float4 peer = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
-                                    const bool ok = (4 * j + kk < OUTW) && (xo + kk < W);
-                                    if (ok) orow[xo + kk] = h == 0 ? bf8_pack(mine, peer) : bf8_pack(peer, mine);
-                                }
-                            }
+                        for (int i = 0; i < 2; ++i) {
+                            const int kk = h == 0 ? i : 2 + i;
+                            const float4 mine = make_float4(o[kk][0], o[kk][1], o[kk][2], o[kk][3]);
+                            const float4 peer = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
+                            const bool ok = (4 * j + kk < OUTW) && (xo + kk < W);
+                            if (ok) orow[xo + kk] = h == 0 ? bf8_pack(mine, peer) : bf8_pack(peer, mine);
                         }
                     }
                 }
-                mbar_arrive(smem_u32(&bars->x_empty[xb]));
             }
-            gp0 += (uint32_t)npairs;
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            gp0 += (uint32_t)((n1 + 1) >> 1);
         }
+        GX_PROF_END(1);
     } else if (warp < 12) {
         // ============================ EP: accumulators -> (A', b', C) exchange rows ============================
         const int quarter = warp & 3, m = quarter * 32 + lane, half = m >> 6, pc = m & 63;
         const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16);
         unsigned char* xbuf = smem + OFF_X;
-        const int xoff = half * 1024 + xslot(pc >> 2, pc & 3) * 16;
+        const int xoff = half * X_BYTES + xslot(pc >> 2, pc & 3) * 16;
+        GX_PROF_DECL;
         while (walk.next(ck)) {
             const int x0 = ck.strip * OUTW, y0 = ck.y0, rows = ck.rows;
             const int xs = x0 - 4 + pc;
@@ -383,14 +507,14 @@ gf_mix_kernel(const Params p) {
             const size_t bplane = (size_t)p.B * plane;
             const int n1 = rows + 8, npairs = (n1 + 1) >> 1;
             for (int pl = 0; pl < npairs; ++pl) {
-                const uint32_t gpair = gp0 + (uint32_t)pl, xb = gpair & 1u;
+                const uint32_t gpair = gp0 + (uint32_t)pl;
                 const int ys = y0 - 4 + 2 * pl + half;
                 float mx = 0.f, i1 = 0.f, i2 = 0.f;
                 if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
                     const size_t o = sb + (size_t)ys * W + xs;
                     mx = __ldg(p.stats + o); i1 = __ldg(p.stats + bplane + o); i2 = __ldg(p.stats + 2 * bplane + o);
                 }
-                mbar_wait(smem_u32(&bars->d_full), gpair & 1u);
+                GX_WAIT(mbar_wait(smem_u32(&bars->d_full), gpair & 1u));
                 tc_fence_after();
                 float a[32], t[32], bq[32];
                 tmem_ld32(tacc + 0, a);
@@ -405,30 +529,32 @@ gf_mix_kernel(const Params p) {
                 mbar_arrive(smem_u32(&bars->d_empty));
 #pragma unroll
                 for (int c = 0; c < 32; ++c) t[c] += bars->bias[c];
-                mbar_wait(smem_u32(&bars->x_empty[xb]), ((gpair >> 1) & 1u) ^ 1u);
-                unsigned char* xr_ = xbuf + xb * X_BYTES + xoff;
+                GX_WAIT(mbar_wait(smem_u32(&bars->x_empty[half]), (gpair & 1u) ^ 1u));     // L2 took this row of pair gpair-1
+                unsigned char* xr_ = xbuf + xoff;
 #pragma unroll
                 for (int qq = 0; qq < 8; ++qq) {
                     *reinterpret_cast<float4*>(xr_ + qq * X_PLANE) = make_float4(a[qq * 4], a[qq * 4 + 1], a[qq * 4 + 2], a[qq * 4 + 3]);
                     *reinterpret_cast<float4*>(xr_ + (8 + qq) * X_PLANE) = make_float4(bq[qq * 4], bq[qq * 4 + 1], bq[qq * 4 + 2], bq[qq * 4 + 3]);
                     *reinterpret_cast<float4*>(xr_ + (16 + qq) * X_PLANE) = make_float4(t[qq * 4], t[qq * 4 + 1], t[qq * 4 + 2], t[qq * 4 + 3]);
                 }
-                mbar_arrive(smem_u32(&bars->x_full[xb]));
+                mbar_arrive(smem_u32(&bars->x_full[half]));
             }
             gp0 += (uint32_t)npairs;
         }
+        GX_PROF_END(2);
     } else if (warp == MMA_WARP) {
         // ============================ MMA issuer ============================
         const uint32_t w_base = smem_u32(smem + OFF_W), aop_base = smem_u32(smem + OFF_AOP), z_base = smem_u32(smem + OFF_Z);
         const uint32_t id64 = tc_idesc(64u, 2u), id32 = tc_idesc(32u, 2u);
         uint32_t zcnt[2] = {0u, 0u};
+        GX_PROF_DECL;
         while (walk.next(ck)) {
             const int n1 = ck.rows + 8, npairs = (n1 + 1) >> 1;
             for (int pl = 0; pl < npairs; ++pl) {
                 const uint32_t gpair = gp0 + (uint32_t)pl, buf = gpair & 1u;
                 const bool zvalid = 2 * pl + 1 >= 8 && 2 * pl - 8 < ck.rows;      // any of the two output rows inside the chunk
-                mbar_wait(smem_u32(&bars->aop_full[buf]), (gpair >> 1) & 1u);
-                if (gpair > 0) mbar_wait(smem_u32(&bars->d_empty), (gpair - 1) & 1u);
+                GX_WAIT(mbar_wait(smem_u32(&bars->aop_full[buf]), (gpair >> 1) & 1u));
+                if (gpair > 0) GX_WAIT(mbar_wait(smem_u32(&bars->d_empty), (gpair - 1) & 1u));
                 if (zvalid) { mbar_wait(smem_u32(&bars->z_full[buf]), zcnt[buf] & 1u); ++zcnt[buf]; }
                 tc_fence_after();
                 if (elect_one()) {
@@ -454,35 +580,71 @@ gf_mix_kernel(const Params p) {
             }
             gp0 += (uint32_t)npairs;
         }
+        GX_PROF_END(3);
     } else {
-        // ============================ producer: raw z rows of the output rows ============================
+        // ============================ producer (one elected thread issues the bulk copies) ============================
+        //  * raw-row ring: the entering row (8 quad planes + guide, columns x0-8 .. x0+55 clipped to the image) of every L1
+        //    iteration, RS stages ahead;
+        //  * z staging: the raw rows of the two OUTPUT rows of each level-1 pair (A operand of the Wc GEMM), columns x0..x0+63.
+        uint32_t rcount = 0;
+        GX_PROF_DECL;
         while (walk.next(ck)) {
             const int x0 = ck.strip * OUTW, y0 = ck.y0, rows = ck.rows;
+            const int xlo = max(0, x0 - 8), xhi = min(W, x0 + 56);              // raw columns inside the image
+            const uint32_t ring_px = (uint32_t)(xhi - xlo), ring_off = (uint32_t)(xlo - (x0 - 8));
             const int npx = min(64, W - x0);
-            const int n1 = rows + 8, npairs = (n1 + 1) >> 1;
-            for (int pl = 0; pl < npairs; ++pl) {
-                const uint32_t gpair = gp0 + (uint32_t)pl, buf = gpair & 1u;
-                const int yoA = y0 + 2 * pl - 8, yoB = yoA + 1;
-                const bool vA = yoA >= y0 && yoA < y0 + rows, vB = yoB >= y0 && yoB < y0 + rows;
-                if (!(vA || vB)) continue;
-                // the stage was last read by the MMAs of pair gpair-2, whose completion is aop_empty[buf]'s previous phase
-                mbar_wait(smem_u32(&bars->aop_empty[buf]), ((gpair >> 1) & 1u) ^ 1u);
-                if (elect_one()) {
-                    const uint32_t bar = smem_u32(&bars->z_full[buf]);
-                    const uint32_t row_bytes = (uint32_t)npx * 16;
-                    mbar_expect_tx(bar, row_bytes * 8 * ((vA ? 1 : 0) + (vB ? 1 : 0)));
-                    const uint32_t dst = smem_u32(smem + OFF_Z) + buf * Z_BYTES;
-                    const float4* src = reinterpret_cast<const float4*>(p.feat) + (size_t)ck.b * 8 * plane + x0;
+            const int n1 = rows + 8, npairs = (n1 + 1) >> 1, nt = rows + 16;
+            const float4* fsrc = reinterpret_cast<const float4*>(p.feat) + (size_t)ck.b * 8 * plane;
+            const float* gsrc = p.guide + (size_t)ck.b * plane;
+            // z staging of pair pl is issued 12 + 2 pl ring rows into the chunk: by then the MMAs of pair pl-2 (whose
+            // completion frees the stage) have normally retired, so the wait below does not hold up the ring
+            for (int t = 0; t < nt + 4 || ((t - 12) >> 1) < npairs; ++t) {
+                if (t < nt) {
+                    const int yr = y0 - 8 + t;
+                    const uint32_t st = rcount % RS;
+                    GX_WAIT(mbar_wait(smem_u32(&bars->r_empty[st]), ((rcount / RS) & 1u) ^ 1u));
+                    if (elect_one()) {
+                        const uint32_t bar = smem_u32(&bars->r_full[st]);
+                        if (yr >= 0 && yr < H) {
+                            mbar_expect_tx(bar, ring_px * (8 * 16 + 4));
+                            const uint32_t dst = smem_u32(smem + OFF_R) + st * R_BYTES;
 #pragma unroll
-                    for (int qq = 0; qq < 8; ++qq) {
-                        if (vA) bulk_g2s(dst + qq * 2048, src + qq * plane + (size_t)yoA * W, row_bytes, bar);
-                        if (vB) bulk_g2s(dst + qq * 2048 + 1024, src + qq * plane + (size_t)yoB * W, row_bytes, bar);
+                            for (int qq = 0; qq < 8; ++qq)
+                                bulk_g2s(dst + qq * 1024 + ring_off * 16, fsrc + qq * plane + (size_t)yr * W + xlo, ring_px * 16, bar);
+                            bulk_g2s(dst + 8192 + ring_off * 4, gsrc + (size_t)yr * W + xlo, ring_px * 4, bar);
+                        } else {
+                            mbar_arrive(bar);                                    // a row outside the image: no data, the phase still turns
+                        }
                     }
+                    __syncwarp();
+                    ++rcount;
                 }
-                __syncwarp();
+                const int pl = (t - 12) >> 1;
+                if (t >= 12 && ((t - 12) & 1) == 0 && pl < npairs) {
+                    const uint32_t gpair = gp0 + (uint32_t)pl, buf = gpair & 1u;
+                    const int yoA = y0 + 2 * pl - 8, yoB = yoA + 1;
+                    const bool vA = yoA >= y0 && yoA < y0 + rows, vB = yoB >= y0 && yoB < y0 + rows;
+                    // The stage was last read by the MMAs of pair gpair-2, whose completion is aop_empty[buf]'s previous
+                    // phase.  Waited for on EVERY pair (also those without an output row): a parity wait can only tell
+                    // adjacent phases apart, so the producer must never run more than one phase ahead of the issuer.
+                    GX_WAIT(mbar_wait(smem_u32(&bars->aop_empty[buf]), ((gpair >> 1) & 1u) ^ 1u));
+                    if ((vA || vB) && elect_one()) {
+                        const uint32_t bar = smem_u32(&bars->z_full[buf]);
+                        const uint32_t row_bytes = (uint32_t)npx * 16;
+                        mbar_expect_tx(bar, row_bytes * 8 * ((vA ? 1 : 0) + (vB ? 1 : 0)));
+                        const uint32_t dst = smem_u32(smem + OFF_Z) + buf * Z_BYTES;
+#pragma unroll
+                        for (int qq = 0; qq < 8; ++qq) {
+                            if (vA) bulk_g2s(dst + qq * 2048, fsrc + qq * plane + (size_t)yoA * W + x0, row_bytes, bar);
+                            if (vB) bulk_g2s(dst + qq * 2048 + 1024, fsrc + qq * plane + (size_t)yoB * W + x0, row_bytes, bar);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
-            gp0 += (uint32_t)((n1 + 1) >> 1);
+            gp0 += (uint32_t)npairs;
         }
+        GX_PROF_END(4);
     }
 
     tc_fence_before();
@@ -495,6 +657,15 @@ gf_mix_kernel(const Params p) {
 }  // namespace paif
 
 using namespace paif;
+
+#ifdef PAIF_TC_PROFILE
+extern "C" int paif_debug_gx_counters(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, gx::gx_prof, sizeof(gx::gx_prof));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(gx::gx_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 extern "C" int paif_gf_mix_supported(int C, int H, int W) { return C == 32 && H > 9 && W > 9 && W % 4 == 0; }
 

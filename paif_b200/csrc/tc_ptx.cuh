@@ -15,16 +15,28 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef PAIF_MBAR_SPIN_LIMIT
+#define PAIF_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
-    unsigned long long spins = 0;
+    unsigned int spins = 0;
     while (true) {
+#ifdef PAIF_MBAR_SUSPEND_NS
+        // with a suspend-time hint the waiting thread sleeps in hardware until the phase completes (or the hint
+        // expires) instead of re-issuing the poll: idle roles stop competing for issue slots with the busy ones
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)PAIF_MBAR_SUSPEND_NS) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
         if (ok) break;
-        if (++spins > (1ull << 26)) {          // (seconds) a lost arrival would otherwise hang the GPU box
-            printf("paif conv_tc: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n",
+        if (++spins > PAIF_MBAR_SPIN_LIMIT) {          // (seconds) a lost arrival would otherwise hang the GPU box
+#ifndef PAIF_MBAR_QUIET                                 // (a printf call on this path costs the callers registers)
+            printf("paif tcgen05 kernel: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n",
                    blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
+#endif
             __trap();
         }
     }

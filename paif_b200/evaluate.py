@@ -93,7 +93,10 @@ def compute_results(conf_total):
 
 
 def seeded_delta(shape, epsilon, seed, global_index, device):
-    """U(-eps, eps) PGD start point that depends only on (seed, global frame index)."""
+    """U(-eps, eps) PGD start point that depends only on (seed, global frame index).  ``shape`` is the shape of ONE
+    frame's batch-1 tensor ``[1, C, H, W]``; ``global_index`` may be a sequence, giving ``[len, C, H, W]``."""
+    if isinstance(global_index, (list, tuple, range)):
+        return torch.cat([seeded_delta(shape, epsilon, seed, gi, device) for gi in global_index], 0)
     g = torch.Generator(device="cpu").manual_seed((int(seed) * 1000003 + int(global_index)) % (2 ** 63 - 1))
     return ((torch.rand(shape, generator=g) * 2.0 - 1.0) * epsilon).to(device)
 
@@ -113,22 +116,43 @@ def _replay_signature(model, vis_shape, ir_shape, label_shape, device, epsilon, 
     return (tuple(vis_shape), tuple(ir_shape), tuple(label_shape), str(device), float(epsilon), float(alpha), sigs)
 
 
+def _seg_loss(seg, label, ignore_index):
+    """``Seg_loss`` of attack/attack.py:103-114 (bilinear up-sampling to the label size + cross entropy with
+    ``ignore_index=255``).  The reference averages over the valid pixels of its batch-1 input; here the per-pixel
+    losses are SUMMED and divided by the constant H*W, so that a frame's gradient does not depend on which other
+    frames share its micro-batch (PGD steps along sign(grad): a positive constant factor changes nothing)."""
+    seg = F.interpolate(seg, size=label.shape[1:], mode="bilinear", align_corners=False)
+    return F.cross_entropy(seg, label, ignore_index=ignore_index, reduction="sum") / float(label.shape[1] * label.shape[2])
+
+
+def _frame_indices(global_index, n):
+    if isinstance(global_index, (list, tuple, range)):
+        if len(global_index) != n:
+            raise ValueError("one global frame index per frame of the batch")
+        return list(global_index)
+    if n != 1:
+        raise ValueError("a batch of %d frames needs %d global frame indices" % (n, n))
+    return [global_index]
+
+
 def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255., attack_iters=10,
                     seed=0, global_index=0, ignore_index=255):
-    """``attack_both(..., attack_loss='l_seg', attack_way='PGD')`` (attack/attack.py:417-514) for one
-    frame, with a seeded start.  ``model(ir, vis) -> (fused, seg_logits)``.  Faithful to the reference
-    including its quirk of never zeroing ``delta.grad`` (the step uses the sign of the running sum of
-    gradients, attack/attack.py:501-512).  Returns :class:`PGDDelta` ``(delta_ir, delta_vis)``, the reference's order."""
+    """``attack_both(..., attack_loss='l_seg', attack_way='PGD')`` (attack/attack.py:417-514) with a seeded start,
+    for one frame or a batch of independent frames (``global_index``: one index per frame; ``model`` must not couple
+    the frames of a batch — see ``FusionSegTask.per_sample_minmax``).  ``model(ir, vis) -> (fused, seg_logits)``.
+    Faithful to the reference including its quirk of never zeroing ``delta.grad`` (the step uses the sign of the
+    running sum of gradients, attack/attack.py:501-512).  Returns :class:`PGDDelta` ``(delta_ir, delta_vis)``, the
+    reference's order."""
     dev = x_vis.device
-    d_vis = seeded_delta(x_vis.shape, epsilon, seed, 2 * global_index, dev)
-    d_ir = seeded_delta(x_ir.shape, epsilon, seed, 2 * global_index + 1, dev)
+    idx = _frame_indices(global_index, x_vis.shape[0])
+    d_vis = seeded_delta((1,) + tuple(x_vis.shape[1:]), epsilon, seed, [2 * i for i in idx], dev)
+    d_ir = seeded_delta((1,) + tuple(x_ir.shape[1:]), epsilon, seed, [2 * i + 1 for i in idx], dev)
     d_vis = torch.max(torch.min(d_vis, 1 - x_vis), 0 - x_vis).requires_grad_(True)
     d_ir = torch.max(torch.min(d_ir, 1 - x_ir), 0 - x_ir).requires_grad_(True)
     for _ in range(attack_iters):
         with torch.enable_grad():
             _, seg = model(x_ir + d_ir, x_vis + d_vis)
-            seg = F.interpolate(seg, size=label.shape[1:], mode="bilinear", align_corners=False)
-            loss = F.cross_entropy(seg, label, ignore_index=ignore_index)
+            loss = _seg_loss(seg, label, ignore_index)
         loss.backward()
         with torch.no_grad():
             for d, x in ((d_vis, x_vis), (d_ir, x_ir)):
@@ -139,10 +163,10 @@ def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255.,
 
 class GraphedPGD:
     """One PGD iteration of :func:`pgd_attack_both` (forward, loss, backward to the inputs, delta update)
-    captured once in a CUDA graph and replayed ``attack_iters`` times per frame.  Same arithmetic, same
+    captured once in a CUDA graph and replayed ``attack_iters`` times per micro-batch.  Same arithmetic, same
     kernels; what disappears is the host time of launching ~1500 small stock-PyTorch kernels per iteration of
-    the segmentation consumer (and ~75 of ours), which dominates a batch-1 PGD loop.  The fusion kernels take
-    every buffer from the caller and never synchronise, so they are capturable as they are."""
+    the segmentation consumer (and ~75 of ours).  The fusion kernels take every buffer from the caller and never
+    synchronise, so they are capturable as they are."""
 
     def __init__(self, model, vis_shape, ir_shape, label_shape, device, epsilon, alpha, ignore_index=255):
         self.eps, self.alpha = float(epsilon), float(alpha)
@@ -173,8 +197,7 @@ class GraphedPGD:
     def _iteration(self):
         with torch.enable_grad():
             _, seg = self.model(self.x_ir + self.d_ir, self.x_vis + self.d_vis)
-            seg = F.interpolate(seg, size=self.label.shape[1:], mode="bilinear", align_corners=False)
-            loss = F.cross_entropy(seg, self.label, ignore_index=self.ignore_index)
+            loss = _seg_loss(seg, self.label, self.ignore_index)
         loss.backward()
         with torch.no_grad():
             for d, x in ((self.d_vis, self.x_vis), (self.d_ir, self.x_ir)):
@@ -187,12 +210,13 @@ class GraphedPGD:
             raise RuntimeError("GraphedPGD: the captured graph no longer matches this call (input shapes changed, or "
                                "the fusion net's weights / engine switches changed after capture, so the graph "
                                "points at a stale weight pack); build a new GraphedPGD")
+        idx = _frame_indices(global_index, x_vis.shape[0])
         with torch.no_grad():
             self.x_vis.copy_(x_vis)
             self.x_ir.copy_(x_ir)
             self.label.copy_(label)
             for d, x, off in ((self.d_vis, self.x_vis, 0), (self.d_ir, self.x_ir, 1)):
-                init = seeded_delta(x.shape, self.eps, seed, 2 * global_index + off, dev)
+                init = seeded_delta((1,) + tuple(x.shape[1:]), self.eps, seed, [2 * i + off for i in idx], dev)
                 d.copy_(torch.max(torch.min(init, 1 - x), 0 - x))
                 d.grad.zero_()                      # a fresh delta per frame, as attack/attack.py:433-441
         for _ in range(attack_iters):
@@ -201,25 +225,39 @@ class GraphedPGD:
 
 
 def robust_eval(model, frames, num_classes=9, attack_iters=10, epsilon=8 / 255., alpha=2 / 255., seed=0,
-                rank=0, world_size=1, group=None, use_cuda_graph=False):
+                rank=0, world_size=1, group=None, use_cuda_graph=False, micro_batch=1, ignore_index=255):
     """Evaluate this rank's shard of ``frames`` (an indexable of ``(vis[3,H,W], ir[1,H,W], label[H,W])``
     host or device tensors) under PGD and return the all-reduced :class:`ConfusionMeter`.
-    ``attack_iters=0`` gives the clean evaluation of test_original.py:98-258."""
+    ``attack_iters=0`` gives the clean evaluation of test_original.py:98-258.
+
+    ``micro_batch`` frames are attacked and evaluated together.  It needs a ``model`` that treats the frames of a
+    batch independently (``FusionSegTask(per_sample_minmax=True)``; the reference wrapper's min-max spans the batch,
+    core/model_fusion_auto.py:721-723, so with it only ``micro_batch=1`` reproduces the reference).  Every launch
+    uses exactly ``micro_batch`` frames — a ragged tail is padded with copies of the shard's last frame whose labels
+    are all ``ignore_index`` — so the kernels see the same shapes whatever the sharding, which is what keeps the
+    all-reduced matrix bit-identical between 1 and N GPUs."""
     dev = next(model.parameters()).device
     meter = ConfusionMeter(num_classes, dev)
     runner = getattr(model, "_paif_pgd_runner", None)      # the captured graph is reused across calls
-    for gi in shard_range(len(frames), rank, world_size):
-        vis, ir, label = frames[gi]
-        vis, ir = vis.to(dev)[None].float(), ir.to(dev)[None].float()
-        label = label.to(dev)[None].long()
+    mine = list(shard_range(len(frames), rank, world_size))
+    mb = max(1, int(micro_batch))
+    for lo in range(0, len(mine), mb):
+        idx = mine[lo:lo + mb]
+        items = [frames[gi] for gi in idx]
+        pad = mb - len(idx)
+        vis = torch.stack([f[0].to(dev).float() for f in items] + [items[-1][0].to(dev).float()] * pad)
+        ir = torch.stack([f[1].to(dev).float() for f in items] + [items[-1][1].to(dev).float()] * pad)
+        label = torch.stack([f[2].to(dev).long() for f in items] +
+                            [torch.full_like(items[-1][2].to(dev).long(), ignore_index)] * pad)
+        gidx = idx + [idx[-1]] * pad
         if attack_iters > 0:
             if use_cuda_graph:
                 if runner is None or not runner.matches(vis.shape, ir.shape, label.shape, dev, epsilon, alpha):
-                    runner = GraphedPGD(model, vis.shape, ir.shape, label.shape, dev, epsilon, alpha)
+                    runner = GraphedPGD(model, vis.shape, ir.shape, label.shape, dev, epsilon, alpha, ignore_index)
                     object.__setattr__(model, "_paif_pgd_runner", runner)
-                delta = runner.attack(vis, ir, label, attack_iters, seed, gi)
+                delta = runner.attack(vis, ir, label, attack_iters, seed, gidx)
             else:
-                delta = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gi)
+                delta = pgd_attack_both(model, vis, ir, label, epsilon, alpha, attack_iters, seed, gidx, ignore_index)
             vis, ir = vis + delta.delta_vis, ir + delta.delta_ir
         with torch.no_grad():
             _, seg = model(ir, vis)

@@ -138,6 +138,12 @@ class _Runtime:
     #: kernels behind one ABI call when it is not exactly one
     _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_out_forward_bf16": 2, "paif_out_forward_tc": 2, "paif_gf_decomp_backward": 3}
 
+    def note_bytes(self, bytes_per_px):
+        """algorithmic HBM bytes per pixel of the next launch (inputs read once + outputs written once), for the
+        per-kernel roofline table of bench.py"""
+        if self.profile is not None:
+            self._meta = {"bytes": float(bytes_per_px) * self.B * self.H * self.W}
+
     def call(self, name, *args):
         self.launches += self._KERNELS_PER_CALL.get(name, 1)
         if self.profile is None:
@@ -409,6 +415,7 @@ class ECABasicBlock(_Primitive):
         rt.call("paif_eca_scale", partials.data_ptr(), partials.shape[1], p["w1d"].data_ptr(), self.k,
                 e.data_ptr(), rt.C, rt.B, rt.H, rt.W)
         out = rt.new_map()
+        rt.note_bytes((2 if rt.bf16 else 4) * rt.C * (3 + len(extras[:1])))
         rt.call("paif_eca_apply_bf16" if rt.bf16 else "paif_eca_apply", o.data_ptr(), x0.data_ptr(), e.data_ptr(),
                 a.data_ptr(), _ptr(extras[0]) if extras else None, out.data_ptr(), rt.C, rt.B, rt.H, rt.W)
         return out, (x0, o, e)
@@ -916,6 +923,7 @@ class Network_Fusion_Searched(nn.Module):
         feats, guides, gstats, feats16 = [], [], [], []
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
             f, g = rt.new_map(fp32=True), rt.new_plane()
+            rt.note_bytes(4 + 4 * C + 4 + (2 * C if bf16 else 0))
             if bf16:
                 # stems, guide and guided filter stay fp32; the bf16 copy of the stem features is the branch residual
                 f16 = rt.new_map()
@@ -933,14 +941,16 @@ class Network_Fusion_Searched(nn.Module):
                     and bool(_lib.load().paif_gf_mix_supported(C, H, W)))
         for i, (chain, packs) in enumerate(((d.chain, p["chain_ir"]), (d.chain2, p["chain_vis"]))):
             stats = torch.empty((3, B, H, W), device=ir.device, dtype=torch.float32)
+            rt.note_bytes(4 + 12)
             rt.call("paif_gf_guide_stats", guides[i].data_ptr(), stats.data_ptr(), B, H, W)
             if fused_gf:
                 x = rt.new_map()
-                rt._meta = {"bytes": (4.0 * (C + 4) + (2.0 if bf16 else 4.0) * C) * B * H * W}
+                rt.note_bytes(4 * (C + 4) + (2 if bf16 else 4) * C)
                 rt.call("paif_gf_mix_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
                         p["gfmix_w"][i].data_ptr(), p["c1x1_b"][i].data_ptr(), x.data_ptr(), int(bf16), C, B, H, W)
             else:
                 lf1, lf2 = rt.new_map(fp32=True), rt.new_map(fp32=True)
+                rt.note_bytes(4 * (C + 4) + 8 * C)
                 rt.call("paif_gf_decomp_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
                         lf1.data_ptr(), lf2.data_ptr(), C, B, H, W)
                 x = rt.conv([lf1, lf2, feats[i]], p["c1x1"][i], ch_shift=p["c1x1_b"][i], src_fp32=True)[0]
@@ -955,6 +965,7 @@ class Network_Fusion_Searched(nn.Module):
         a_f, v_f = branch_out
         agg = rt.new_map()
         scale = rt.new_plane() if save else None
+        rt.note_bytes((2 if bf16 else 4) * 3 * C + (4 if save else 0))
         if bf16:
             rt.call("paif_spa_fused_forward_bf16", p["spa_w"].data_ptr(), p["spa_k"], a_f.data_ptr(), v_f.data_ptr(),
                     agg.data_ptr(), C, B, H, W)
@@ -964,6 +975,7 @@ class Network_Fusion_Searched(nn.Module):
         f2, recs3 = self.chain.fwd(rt, p["chain"], agg, [])
         out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
         pre_out = rt.new_plane() if save else None
+        rt.note_bytes((2 if bf16 else 4) * C + 4 + (4 if save else 0))
         if rt.tc_engine() and self.out_tensor_core:
             # interior pixels as an implicit GEMM on the engine, the one-pixel border exactly from the 9-class weights
             rt.call("paif_out_forward_tc", f2.data_ptr(), (p["out_mma16"] if bf16 else p["out_mma"]).data_ptr(),

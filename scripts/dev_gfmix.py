@@ -55,3 +55,13 @@ t_new, t_new16, t_old = timeit(new), timeit(lambda: new(True)), timeit(old)
 maps = B * H * W * 128 / 1e9
 print("B=%d %dx%d: fused %.3f ms (%.0f GB/s on 2 maps), fused->bf16 %.3f ms, gf + 1x1 %.3f ms" %
       (B, H, W, t_new, 2 * maps / t_new * 1e3, t_new16, t_old))
+
+if os.environ.get("PAIF_B200_PROFILE_LIB") == "1":
+    lib = _lib.load()
+    buf = (ctypes.c_ulonglong * 16)()
+    lib.paif_debug_gx_counters(buf, 1)
+    new()
+    lib.paif_debug_gx_counters(buf, 0)
+    for i, (name, nw) in enumerate((("L1", 4), ("L2", 4), ("EP", 4), ("MMA", 1))):
+        wait, tot = buf[2 * i], buf[2 * i + 1]
+        print("%-4s waits %5.1f%% of its life (avg life %.0f cycles per warp)" % (name, 100.0 * wait / max(tot, 1), tot / (148.0 * nw)))

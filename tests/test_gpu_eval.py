@@ -50,6 +50,29 @@ def test_pgd_robust_eval_is_sharding_invariant():
     assert int(clean.sum()) == 5 * 24 * 40
 
 
+def test_micro_batched_robust_eval_is_sharding_invariant():
+    """Frames attacked in fixed-size micro-batches through the per-sample min-max task wrapper (SURVEY 8e caveat 1):
+    the confusion matrix is bit-identical between 1 rank and 2 / 3 ranks (different batch-mates, different batch
+    positions, padded tails), with and without CUDA-graph replay of the PGD iteration."""
+    from paif_b200.consumer import FusionSegTask, SegFormerLite
+    torch.manual_seed(0)
+    fusion_net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+    seg = SegFormerLite(9, 64, dims=(16, 32, 48, 64), depths=(1, 1, 1, 1), heads=(1, 2, 3, 4))
+    model = FusionSegTask(fusion_net, seg, per_sample_minmax=True).to(DEV).eval()
+    for prm in seg.parameters():
+        prm.requires_grad_(False)
+    g = torch.Generator().manual_seed(1)
+    frames = [(torch.rand(3, 64, 96, generator=g), torch.rand(1, 64, 96, generator=g),
+               torch.randint(0, 9, (64, 96), generator=g)) for _ in range(7)]
+    for graphed in (False, True):
+        kw = dict(attack_iters=2, micro_batch=3, use_cuda_graph=graphed)
+        whole = ev.robust_eval(model, frames, rank=0, world_size=1, **kw).conf.cpu()
+        for world in (2, 3):
+            parts = sum(ev.robust_eval(model, frames, rank=r, world_size=world, **kw).conf.cpu() for r in range(world))
+            assert torch.equal(whole, parts), (graphed, world)
+        assert int(whole.sum()) == 7 * 64 * 96                  # padded tail frames carry only ignore labels
+
+
 def test_fusion_cuda_graph_replay_is_bit_identical_to_eager():
     """Forward + backward-to-input of the drop-in captured in a CUDA graph and replayed returns the same bits as the
     eager call (caller-owned buffers, no hidden sync or allocation inside the library, deterministic kernels)."""
