@@ -286,6 +286,13 @@ int paif_stem_backward(const float* gpre, const float* w, float* gimg,
                        int C, int B, int H, int W, void* stream);
 
 /* ====================================================================================
+ * PGD step (attack/attack.py:504-512), in place and for one modality:
+ *   delta <- clamp(clamp(delta + alpha * sign(grad), -eps, eps), 0 - x, 1 - x)
+ * grad is delta.grad as autograd accumulated it (the reference never zeroes it).  n elements, contiguous fp32. */
+int paif_pgd_step(float* delta, const float* grad, const float* x, float alpha, float eps,
+                  long long n, void* stream);
+
+/* ====================================================================================
  * evaluation metric: 9x9 confusion matrix (sklearn.metrics.confusion_matrix(labels=0..n-1),
  * robust_test.py:207-211) accumulated on the GPU as int64; the caller all-reduces it (NCCL).
  * conf: [n][n] int64, rows = label, cols = prediction; labels/preds outside 0..n-1 ignored. */

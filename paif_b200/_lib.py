@@ -84,6 +84,7 @@ SIGNATURES = {
     "paif_stem_backward_pre": [_f, _f, _f, _f, _f, _f, _f, _i, _f, _i, _i, _i, _i, _f],
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
+    "paif_pgd_step": [_f, _f, _f, C.c_float, C.c_float, _ll, _f],
 }
 
 _lib = None

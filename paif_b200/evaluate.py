@@ -135,6 +135,19 @@ def _frame_indices(global_index, n):
     return [global_index]
 
 
+def pgd_step_(delta, x, alpha, epsilon):
+    """In-place PGD step ``delta <- clamp(clamp(delta + alpha sign(delta.grad), +-eps), 0 - x, 1 - x)``
+    (attack/attack.py:504-512) as ONE kernel (``paif_pgd_step``) instead of six elementwise launches."""
+    d, g, x = delta.data, delta.grad, x.contiguous()
+    if not (d.is_cuda and d.is_contiguous() and g.is_contiguous() and d.dtype == torch.float32
+            and g.dtype == torch.float32 and x.dtype == torch.float32 and g.shape == d.shape == x.shape):
+        raise RuntimeError("pgd_step_: contiguous fp32 CUDA tensors of one shape expected")
+    with torch.cuda.device(d.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)
+        _lib.call("paif_pgd_step", d.data_ptr(), g.data_ptr(), x.data_ptr(), float(alpha), float(epsilon), d.numel(), stream)
+    return delta
+
+
 def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255., attack_iters=10,
                     seed=0, global_index=0, ignore_index=255):
     """``attack_both(..., attack_loss='l_seg', attack_way='PGD')`` (attack/attack.py:417-514) with a seeded start,
@@ -156,8 +169,7 @@ def pgd_attack_both(model, x_vis, x_ir, label, epsilon=8 / 255., alpha=2 / 255.,
         loss.backward()
         with torch.no_grad():
             for d, x in ((d_vis, x_vis), (d_ir, x_ir)):
-                d.data = torch.clamp(d + alpha * torch.sign(d.grad), min=-epsilon, max=epsilon)
-                d.data = torch.max(torch.min(d, 1 - x), 0 - x)
+                pgd_step_(d, x, alpha, epsilon)
     return PGDDelta(delta_ir=d_ir.detach(), delta_vis=d_vis.detach())
 
 
@@ -201,8 +213,7 @@ class GraphedPGD:
         loss.backward()
         with torch.no_grad():
             for d, x in ((self.d_vis, self.x_vis), (self.d_ir, self.x_ir)):
-                step = torch.clamp(d + self.alpha * torch.sign(d.grad), min=-self.eps, max=self.eps)
-                d.copy_(torch.max(torch.min(step, 1 - x), 0 - x))
+                pgd_step_(d, x, self.alpha, self.eps)
 
     def attack(self, x_vis, x_ir, label, attack_iters, seed, global_index):
         dev = self.x_vis.device
