@@ -61,6 +61,12 @@ int paif_stem_forward(const float* img, long long stride_b, long long stride_y, 
                       const float* w, const float* slope,
                       float* feat, float* residue, int B, int H, int W, void* stream);
 
+/* paif_stem_forward reading the VISIBLE image as RGB and forming Y = .299 R + .587 G + .114 B (RGB2YCrCb,
+ * core/model_fusion_auto.py:69-92) on the fly: img points at the R plane, stride_c is the channel stride. */
+int paif_stem_forward_rgb(const float* img, long long stride_b, long long stride_c, long long stride_y, long long stride_x,
+                          const float* w, const float* slope,
+                          float* feat, float* residue, void* feat_bf16, int B, int H, int W, void* stream);
+
 /* GuidedFilter(4, eps)(residue, feat) for eps in {1e-3, 1e-4} — core/model_fusion_auto.py:522-535
  * + third-party guided_filter_pytorch (box filter radius 4, clipped borders).
  * Pass 0 computes what all 32 channels share: stats = [3][B][H][W] = mean_guide, 1/(var_guide + 1e-3),
@@ -284,6 +290,28 @@ int paif_stem_backward_pre(const float* feat, const float* slope,
 /* stem backward, pass 2: gimg = conv3x3^T(gpre) (32 -> 1); gimg: contiguous [B][H][W]. */
 int paif_stem_backward(const float* gpre, const float* w, float* gimg,
                        int C, int B, int H, int W, void* stream);
+
+/* ====================================================================================
+ * Colour / normalisation glue of the task wrappers: what Network_MM_CompModel.forward does between
+ * the fusion net and the segmentation consumer (core/model_fusion_auto.py:712-728 with RGB2YCrCb :69-92 and YCrCb2RGB
+ * :94-111) — Cr/Cb of the visible image, YCrCb -> RGB of [fused, Cr, Cb], clamp to [0,1], min-max stretch,
+ * x255, (x - mean) / std — as two passes instead of ~15 elementwise launches, and its adjoint as two passes.
+ *   fused: [B][H][W]; vis: contiguous RGB [B][3][H][W]; x, gx, gvis: [B][3][H][W]; gfused: [B][H][W]
+ *   per_sample != 0: min / max per sample (= the reference at batch 1 applied to every sample);
+ *   per_sample == 0: min / max over the whole batch, exactly as the reference wrapper.
+ *   Caller-owned scratch with nblk = paif_glue_blocks(H, W): partial [B][nblk][2] float, ties [B][nblk][2] int,
+ *   lohi [B][2] float (all three written by the forward and read by the backward), sums [B][nblk][2] float.
+ *   mean3 / std3 are HOST pointers to 3 floats.
+ * The backward follows autograd of the reference expressions: torch.where clamps pass no gradient where they clamp,
+ * torch.min / torch.max share their gradient evenly among tied elements.  gvis holds only the Cr / Cb path; the
+ * gradient through the fusion net's Y input is added by the caller (paif_stem_forward_rgb's adjoint). */
+int paif_glue_blocks(int H, int W);
+int paif_glue_forward(const float* fused, const float* vis, const float* mean3, const float* std3,
+                      float* x, float* partial, int* ties, float* lohi, int per_sample,
+                      int B, int H, int W, void* stream);
+int paif_glue_backward(const float* fused, const float* vis, const float* gx, const float* std3,
+                       const float* lohi, const int* ties, float* sums, float* gfused, float* gvis,
+                       int per_sample, int B, int H, int W, void* stream);
 
 /* ====================================================================================
  * PGD step (attack/attack.py:504-512), in place and for one modality:

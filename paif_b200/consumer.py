@@ -14,9 +14,57 @@ run and timed end to end on a GPU box where the reference checkout and its third
   (core/model_fusion_auto.py:712-729): RGB->YCrCb, fusion on Y, YCrCb->RGB, clamp, min-max over the
   batch, x255, ImageNet mean/std, consumer.  ``forward(ir, vis) -> (fused, seg_logits)``.
 """
+import ctypes
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import _lib
+
+_MEAN = (123.675, 116.28, 103.53)          # core/model_fusion_auto.py:710-711
+_STD = (58.395, 57.12, 57.375)
+
+
+class _GlueFn(torch.autograd.Function):
+    """``(fused Y, visible RGB) -> normalised consumer input`` as the two-pass kernels ``paif_glue_forward`` /
+    ``paif_glue_backward`` (csrc/glue.cu): Cr/Cb of the visible image, YCrCb -> RGB, clamp, min-max stretch, x255,
+    (x - mean) / std (core/model_fusion_auto.py:69-111, 715-727), with the gradients autograd would give."""
+
+    @staticmethod
+    def forward(ctx, fused, vis, per_sample):
+        B, _, H, W = vis.shape
+        fused, vis = fused.contiguous().float(), vis.contiguous().float()
+        dev = vis.device
+        nblk = _lib.load().paif_glue_blocks(H, W)
+        x = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+        partial = torch.empty((B, nblk, 2), device=dev, dtype=torch.float32)
+        ties = torch.empty((B, nblk, 2), device=dev, dtype=torch.int32)
+        lohi = torch.empty((B, 2), device=dev, dtype=torch.float32)
+        mean3, std3 = (ctypes.c_float * 3)(*_MEAN), (ctypes.c_float * 3)(*_STD)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.call("paif_glue_forward", fused.data_ptr(), vis.data_ptr(), mean3, std3, x.data_ptr(), partial.data_ptr(),
+                      ties.data_ptr(), lohi.data_ptr(), int(per_sample), B, H, W, stream)
+        ctx.save_for_backward(fused, vis, ties, lohi)
+        ctx.per_sample, ctx.nblk = int(per_sample), nblk
+        return x
+
+    @staticmethod
+    def backward(ctx, gx):
+        fused, vis, ties, lohi = ctx.saved_tensors
+        B, _, H, W = vis.shape
+        gx = gx.contiguous().float()
+        dev = vis.device
+        sums = torch.empty((B, ctx.nblk, 2), device=dev, dtype=torch.float32)
+        gfused = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+        gvis = torch.empty((B, 3, H, W), device=dev, dtype=torch.float32)
+        std3 = (ctypes.c_float * 3)(*_STD)
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.call("paif_glue_backward", fused.data_ptr(), vis.data_ptr(), gx.data_ptr(), std3, lohi.data_ptr(),
+                      ties.data_ptr(), sums.data_ptr(), gfused.data_ptr(), gvis.data_ptr(), ctx.per_sample, B, H, W, stream)
+        return gfused, gvis, None
 
 
 class _MixFFN(nn.Module):
@@ -118,8 +166,11 @@ class FusionSegTask(nn.Module):
     """``Network_MM_CompModel``-style task model (core/model_fusion_auto.py:698-729) around any fusion
     module with ``forward(ir, vis) -> [B,1,H,W]`` and any consumer ``[B,3,H,W] -> logits``."""
 
-    def __init__(self, fusion, consumer, consumer_autocast=None, per_sample_minmax=False):
+    def __init__(self, fusion, consumer, consumer_autocast=None, per_sample_minmax=False, fused_glue=False):
         super().__init__()
+        #: True: RGB -> Y inside the fusion net's visible stem (``forward_rgb``) and the whole output-side glue as the
+        #: two-pass kernels of csrc/glue.cu (needs the paif_b200 fusion net and CUDA tensors); False: stock PyTorch ops
+        self.fused_glue = fused_glue
         self.enhance_net = fusion
         self.denoise_net = consumer
         #: False: min-max over the whole batch, exactly as the reference wrapper (core/model_fusion_auto.py:721-723),
@@ -146,7 +197,17 @@ class FusionSegTask(nn.Module):
         b = y + 1.773 * cb
         return torch.cat([r, g, b], 1)
 
+    def _consume(self, x):
+        if self.consumer_autocast is not None:
+            with torch.autocast(device_type=x.device.type, dtype=self.consumer_autocast):
+                seg = self.denoise_net(x)
+            return seg.float()
+        return self.denoise_net(x)
+
     def forward(self, ir, vis):
+        if self.fused_glue:
+            fused = self.enhance_net.forward_rgb(ir[:, 0:1], vis)
+            return fused, self._consume(_GlueFn.apply(fused, vis, self.per_sample_minmax))
         ycc = self.rgb_to_ycrcb(vis)
         fused = self.enhance_net(ir[:, 0:1], ycc[:, 0:1])
         rgb = self.ycrcb_to_rgb(torch.cat([fused, ycc[:, 1:3]], 1)).clamp(0.0, 1.0)

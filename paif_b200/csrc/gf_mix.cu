@@ -56,7 +56,7 @@ constexpr int RS = 6;                          // raw-row ring stages (entering 
 constexpr int R_BYTES = 8 * 1024 + 256;        // 8 quad planes x 64 pixels x 16 B + 64 guide values
 constexpr int OFF_W = 0, OFF_AOP = OFF_W + W_BYTES, OFF_X = OFF_AOP + 2 * AOP_BYTES, OFF_Z = OFF_X + 2 * X_BYTES,
               OFF_R = OFF_Z + 2 * Z_BYTES, OFF_BARS = OFF_R + RS * R_BYTES, SMEM_BYTES = OFF_BARS + 1024;
-constexpr int RING_COL0 = 128, RING_SLOTS = 9;
+constexpr int RING_COL0 = 128, RING_SLOTS = 10;     // 9 rows of history + the row being written (so that the old row is read from another slot)
 
 struct Bars {
     uint64_t aop_full[2], aop_empty[2], z_full[2], x_full[2], x_empty[2], d_full, d_empty, r_full[RS], r_empty[RS];
@@ -91,6 +91,21 @@ __device__ __forceinline__ void hsum9(const float (&a)[4], float (&o)[4]) {
     o[2] = p23 + n1 + v8a;
     o[3] = a[3] + n1 + v8b;
 }
+// the same on channel pairs: FADD2 halves the adds (the kernel is issue-bound, not FP32-pipe-bound); shuffles move 32 bits
+__device__ __forceinline__ float2 shfl_down2(float2 v, int d) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, d, 16), __shfl_down_sync(0xffffffffu, v.y, d, 16));
+}
+__device__ __forceinline__ void hsum9x2(const float2 (&a)[4], float2 (&o)[4]) {
+    const float2 p01 = __fadd2_rn(a[0], a[1]), p23 = __fadd2_rn(a[2], a[3]);
+    const float2 p012 = __fadd2_rn(p01, a[2]), full = __fadd2_rn(p01, p23);
+    const float2 n1 = shfl_down2(full, 1), v8 = shfl_down2(a[0], 2), v89 = shfl_down2(p01, 2);
+    const float2 v8a = shfl_down2(p012, 2), v8b = shfl_down2(full, 2);
+    o[0] = __fadd2_rn(__fadd2_rn(full, n1), v8);
+    o[1] = __fadd2_rn(__fadd2_rn(__fadd2_rn(a[1], p23), n1), v89);
+    o[2] = __fadd2_rn(__fadd2_rn(p23, n1), v8a);
+    o[3] = __fadd2_rn(__fadd2_rn(a[3], n1), v8b);
+}
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ void hsum9c(const float (&s)[4][4], int c, float (&o)[4]) {
     const float a[4] = {s[0][c], s[1][c], s[2][c], s[3][c]};
     hsum9(a, o);
@@ -184,6 +199,36 @@ __device__ __forceinline__ void tmem_wait_ld32(float (&v)[32]) {
                  :: "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n\t"
+        "tcgen05.wait::st.sync.aligned;"          // in the same statement: the source registers are read asynchronously
+        ::"r"(taddr),
+          "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld16(float (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+                 :: "memory");
+}
+
 // one work chunk: rows [y0, y0 + rows) of strip `strip` of image b
 struct Chunk { int b, strip, y0, rows; };
 struct Walker {
@@ -235,6 +280,8 @@ gf_mix_kernel(const Params p) {
     if (tid < 32) bars->bias[tid] = p.bias ? p.bias[tid] : 0.f;
     for (int i = tid; i < W_BYTES / 16; i += NT)
         reinterpret_cast<uint4*>(smem + OFF_W)[i] = __ldg(reinterpret_cast<const uint4*>(p.wpack) + i);
+    for (int i = tid; i < RS * R_BYTES / 16; i += NT)      // ring columns outside the image are never written by the
+        reinterpret_cast<uint4*>(smem + OFF_R)[i] = make_uint4(0u, 0u, 0u, 0u);    // copies and are masked by 0 * value: keep them finite
     fence_proxy_async();                                   // the weight tiles are read by the tensor core (async proxy)
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
@@ -388,9 +435,9 @@ gf_mix_kernel(const Params p) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 co[k] = (4 * j + k < OUTW && xo + k < W) ? __frcp_rn(win_count(xo + k, W)) : 0.f;
-            float S[32];                                           // [A' | b'] x [column k][channel c]: index e*16 + k*4 + c
+            float2 SA[4][2], SB[4][2];                             // vertical running sums of A' and b': [column k][channel pair]
 #pragma unroll
-            for (int i = 0; i < 32; ++i) S[i] = 0.f;
+            for (int k = 0; k < 4; ++k) SA[k][0] = SA[k][1] = SB[k][0] = SB[k][1] = make_float2(0.f, 0.f);
             const int n1 = rows + 8;
             int slot = 0;
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);           // guide at the next output row (fetched one row ahead)
@@ -404,35 +451,42 @@ gf_mix_kernel(const Params p) {
                     mbar_arrive(smem_u32(&bars->x_empty[half]));
                     continue;
                 }
-                float od[32];
-                if (r1 >= RING_SLOTS) tmem_ld32_nowait(ring + slot * 32, od);      // the row leaving the vertical window
                 GX_WAIT(mbar_wait(smem_u32(&bars->x_full[half]), gpair & 1u));
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");      // the previous row's ring store has read its registers
                 const unsigned char* xrow = xbuf + half * X_BYTES;
-                float nw[32];
+                const bool has_old = r1 >= 9;
+                const uint32_t t_new = ring + slot * 32, t_old = ring + (slot == RING_SLOTS - 1 ? 0 : slot + 1) * 32;   // row r1 - 9
+                // the two halves (A', b') one after the other: new row from the exchange buffer, into the history ring and
+                // into the running sums; the row leaving the window out of the ring and out of the sums
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 a = *reinterpret_cast<const float4*>(xrow + q * X_PLANE + xo_slot[k]);
-                    const float4 bb = *reinterpret_cast<const float4*>(xrow + (8 + q) * X_PLANE + xo_slot[k]);
-                    nw[k * 4 + 0] = a.x; nw[k * 4 + 1] = a.y; nw[k * 4 + 2] = a.z; nw[k * 4 + 3] = a.w;
-                    nw[16 + k * 4 + 0] = bb.x; nw[16 + k * 4 + 1] = bb.y; nw[16 + k * 4 + 2] = bb.z; nw[16 + k * 4 + 3] = bb.w;
+                for (int e = 0; e < 2; ++e) {
+                    float nw[16], od[16];
+                    if (has_old) tmem_ld16_nowait(t_old + e * 16, od);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float4 a = *reinterpret_cast<const float4*>(xrow + (e * 8 + q) * X_PLANE + xo_slot[k]);
+                        nw[k * 4 + 0] = a.x; nw[k * 4 + 1] = a.y; nw[k * 4 + 2] = a.z; nw[k * 4 + 3] = a.w;
+                    }
+                    tmem_st16(t_new + e * 16, nw);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const float2 v = make_float2(nw[k * 4 + 2 * h2], nw[k * 4 + 2 * h2 + 1]);
+                            if (e == 0) SA[k][h2] = __fadd2_rn(SA[k][h2], v); else SB[k][h2] = __fadd2_rn(SB[k][h2], v);
+                        }
+                    if (has_old) {
+                        tmem_wait_ld16(od);
+                        const float2 neg = make_float2(-1.f, -1.f);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                const float2 v = make_float2(od[k * 4 + 2 * h2], od[k * 4 + 2 * h2 + 1]);
+                                if (e == 0) SA[k][h2] = __ffma2_rn(v, neg, SA[k][h2]); else SB[k][h2] = __ffma2_rn(v, neg, SB[k][h2]);
+                            }
+                    }
                 }
-                float4 cc[4];
-                if (r1 >= 8) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) cc[k] = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]);
-                }
-                if (r1 >= RING_SLOTS) {
-                    tmem_wait_ld32(od);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) S[i] += nw[i] - od[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) S[i] += nw[i];
-                }
-                tmem_st32_nowait(ring + slot * 32, nw);
                 slot = slot == RING_SLOTS - 1 ? 0 : slot + 1;
-                mbar_arrive(smem_u32(&bars->x_empty[half]));           // (A', b', C) of this row are in registers
                 const float gc[4] = {g4.x, g4.y, g4.z, g4.w};
                 {   // guide of the NEXT output row (row clamped into the chunk, columns into the image: only stored pixels
                     // use it): in flight during this row's horizontal sums
@@ -446,21 +500,23 @@ gf_mix_kernel(const Params p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) rno[k] = rcy * co[k];
                     float o[4][4];
+                    float4 cc[4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float sa[4] = {S[c], S[4 + c], S[8 + c], S[12 + c]};
-                        const float sb[4] = {S[16 + c], S[20 + c], S[24 + c], S[28 + c]};
-                        float hA[4], hb[4];
-                        hsum9(sa, hA);
-                        hsum9(sb, hb);
+                    for (int k = 0; k < 4; ++k) cc[k] = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]);
 #pragma unroll
-                        const float ccc[4] = {c == 0 ? cc[0].x : c == 1 ? cc[0].y : c == 2 ? cc[0].z : cc[0].w,
-                                              c == 0 ? cc[1].x : c == 1 ? cc[1].y : c == 2 ? cc[1].z : cc[1].w,
-                                              c == 0 ? cc[2].x : c == 1 ? cc[2].y : c == 2 ? cc[2].z : cc[2].w,
-                                              c == 0 ? cc[3].x : c == 1 ? cc[3].y : c == 2 ? cc[3].z : cc[3].w};
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const float2 sa[4] = {SA[0][h2], SA[1][h2], SA[2][h2], SA[3][h2]};
+                        const float2 sb[4] = {SB[0][h2], SB[1][h2], SB[2][h2], SB[3][h2]};
+                        float2 hA[4], hb[4];
+                        hsum9x2(sa, hA);
+                        hsum9x2(sb, hb);
                         // mean2(A') g + mean2(b') + C = (hA g + hb) / N2 + C
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) o[k][c] = __fmaf_rn(__fmaf_rn(hA[k], gc[k], hb[k]), rno[k], ccc[k]);
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 c2 = h2 == 0 ? make_float2(cc[k].x, cc[k].y) : make_float2(cc[k].z, cc[k].w);
+                            const float2 r = __ffma2_rn(__ffma2_rn(hA[k], dup2(gc[k]), hb[k]), dup2(rno[k]), c2);
+                            o[k][2 * h2] = r.x; o[k][2 * h2 + 1] = r.y;
+                        }
                     }
                     if constexpr (!OUT_BF) {
                         float* orow = static_cast<float*>(p.out) + (((size_t)ck.b * 8 + q) * plane + (size_t)yo * W) * 4;
@@ -488,6 +544,7 @@ gf_mix_kernel(const Params p) {
                         }
                     }
                 }
+                mbar_arrive(smem_u32(&bars->x_empty[half]));           // this row of the exchange buffer has been read (A', b', C)
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             gp0 += (uint32_t)((n1 + 1) >> 1);
@@ -519,16 +576,31 @@ gf_mix_kernel(const Params p) {
                 float a[32], t[32], bq[32];
                 tmem_ld32(tacc + 0, a);
                 tmem_ld32(tacc + 32, t);
+                {
+                    const float2 i12 = dup2(i1), i22 = dup2(i2);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) a[c] = __fmaf_rn(i2, t[c], i1 * a[c]);          // A' = inv1 P + inv2 Q
+                    for (int c = 0; c < 32; c += 2) {                                       // A' = inv1 P + inv2 Q
+                        const float2 r = __ffma2_rn(i22, make_float2(t[c], t[c + 1]), __fmul2_rn(i12, make_float2(a[c], a[c + 1])));
+                        a[c] = r.x; a[c + 1] = r.y;
+                    }
+                }
                 tmem_ld32(tacc + 64, bq);
+                {
+                    const float2 nmx = dup2(-mx);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) bq[c] = __fmaf_rn(-mx, a[c], bq[c]);            // b' = R - mx A'
+                    for (int c = 0; c < 32; c += 2) {                                       // b' = R - mx A'
+                        const float2 r = __ffma2_rn(nmx, make_float2(a[c], a[c + 1]), make_float2(bq[c], bq[c + 1]));
+                        bq[c] = r.x; bq[c + 1] = r.y;
+                    }
+                }
                 tmem_ld32(tacc + 96, t);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&bars->d_empty));
 #pragma unroll
-                for (int c = 0; c < 32; ++c) t[c] += bars->bias[c];
+                for (int c = 0; c < 32; c += 2) {
+                    const float2 r = __fadd2_rn(make_float2(t[c], t[c + 1]), *reinterpret_cast<const float2*>(&bars->bias[c]));
+                    t[c] = r.x; t[c + 1] = r.y;
+                }
                 GX_WAIT(mbar_wait(smem_u32(&bars->x_empty[half]), (gpair & 1u) ^ 1u));     // L2 took this row of pair gpair-1
                 unsigned char* xr_ = xbuf + xoff;
 #pragma unroll

@@ -7,8 +7,11 @@ namespace paif {
 
 constexpr int STEM_C = 32;
 
+// RGB: img points at the R plane and sc is the channel stride; the pixel value is Y = .299 R + .587 G + .114 B
+// (RGB2YCrCb, core/model_fusion_auto.py:69-92: separate multiplies and adds, in that order)
+template <bool RGB>
 __global__ void __launch_bounds__(256)
-stem_forward_kernel(const float* __restrict__ img, long long sb, long long sy, long long sx,
+stem_forward_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy, long long sx,
                     const float* __restrict__ w, const float* __restrict__ slope_p,
                     float* __restrict__ feat, float* __restrict__ residue, uint4* __restrict__ feat16, int H, int W) {
     __shared__ float sw[STEM_C * 9];
@@ -27,7 +30,11 @@ stem_forward_kernel(const float* __restrict__ img, long long sb, long long sy, l
         for (int dx = -1; dx <= 1; ++dx) {
             const int yy = y + dy, xx = x + dx;
             float v = 0.f;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = img[b * sb + yy * sy + xx * sx];
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const float* px = img + b * sb + yy * sy + xx * sx;
+                if (RGB) v = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, px[0]), __fmul_rn(0.587f, px[sc])), __fmul_rn(0.114f, px[2 * sc]));
+                else v = px[0];
+            }
             in[(dy + 1) * 3 + (dx + 1)] = v;
         }
     float vmax = -INFINITY, vmin = INFINITY;
@@ -161,7 +168,7 @@ extern "C" int paif_stem_forward(const float* img, long long sb, long long sy, l
     PAIF_REQUIRE(img && w && slope && feat && residue, "null pointer");
     PAIF_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
     dim3 grid(cdiv(W, 32), cdiv(H, 8), B), block(32, 8);
-    stem_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, sy, sx, w, slope, feat, residue, nullptr, H, W);
+    stem_forward_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, 0, sy, sx, w, slope, feat, residue, nullptr, H, W);
     return check_launch("paif_stem_forward");
 }
 
@@ -171,9 +178,20 @@ extern "C" int paif_stem_forward_bf16copy(const float* img, long long sb, long l
     PAIF_REQUIRE(img && w && slope && feat && residue && feat_bf16, "null pointer");
     PAIF_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
     dim3 grid(cdiv(W, 32), cdiv(H, 8), B), block(32, 8);
-    stem_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, sy, sx, w, slope, feat, residue,
-                                                                  static_cast<uint4*>(feat_bf16), H, W);
+    stem_forward_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, 0, sy, sx, w, slope, feat, residue,
+                                                                         static_cast<uint4*>(feat_bf16), H, W);
     return check_launch("paif_stem_forward_bf16copy");
+}
+
+extern "C" int paif_stem_forward_rgb(const float* img, long long sb, long long sc, long long sy, long long sx,
+                                     const float* w, const float* slope, float* feat, float* residue,
+                                     void* feat_bf16, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(img && w && slope && feat && residue, "null pointer");
+    PAIF_REQUIRE(B > 0 && H > 0 && W > 0, "bad shape");
+    dim3 grid(cdiv(W, 32), cdiv(H, 8), B), block(32, 8);
+    stem_forward_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(img, sb, sc, sy, sx, w, slope, feat, residue,
+                                                                        static_cast<uint4*>(feat_bf16), H, W);
+    return check_launch("paif_stem_forward_rgb");
 }
 
 extern "C" int paif_stem_backward_pre(const float* feat, const float* slope,

@@ -910,8 +910,9 @@ class Network_Fusion_Searched(nn.Module):
         return {'auto': _lib.ENGINE_AUTO, 'direct': _lib.ENGINE_DIRECT, 'tcgen05': _lib.ENGINE_TCGEN05}[self.conv_engine]
 
     # -------------------------------------------------------------------------------------
-    def _run_forward(self, ir, vis, save, capture=None):
-        """ir, vis: [B,1,H,W] fp32 CUDA views (any strides).  Returns (out[B,1,H,W], saved).
+    def _run_forward(self, ir, vis, save, capture=None, vis_rgb=False):
+        """ir, vis: [B,1,H,W] fp32 CUDA views (any strides); with ``vis_rgb`` vis is the [B,3,H,W] RGB image and the
+        stem forms Y on the fly.  Returns (out[B,1,H,W], saved).
         ``capture``: optional dict that receives the intermediate maps ``forward2`` returns (fp32 storage only)."""
         B, _, H, W = ir.shape
         p = self._packed(save)
@@ -924,7 +925,14 @@ class Network_Fusion_Searched(nn.Module):
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
             f, g = rt.new_map(fp32=True), rt.new_plane()
             rt.note_bytes(4 + 4 * C + 4 + (2 * C if bf16 else 0))
-            if bf16:
+            if vis_rgb and img is vis:
+                # RGB -> Y inside the stem (RGB2YCrCb, core/model_fusion_auto.py:69-92): no Y plane, no strided view
+                f16 = rt.new_map() if bf16 else None
+                rt.call("paif_stem_forward_rgb", img.data_ptr(), img.stride(0), img.stride(1), img.stride(2), img.stride(3),
+                        w.data_ptr(), a.data_ptr(), f.data_ptr(), g.data_ptr(), _ptr(f16), B, H, W)
+                if bf16:
+                    feats16.append(f16)
+            elif bf16:
                 # stems, guide and guided filter stay fp32; the bf16 copy of the stem features is the branch residual
                 f16 = rt.new_map()
                 rt.call("paif_stem_forward_bf16copy", img.data_ptr(), img.stride(0), img.stride(2), img.stride(3),
@@ -1093,7 +1101,17 @@ class Network_Fusion_Searched(nn.Module):
         if vis.dtype != torch.float32:
             vis = vis.float()
         with torch.cuda.device(ir.device):
-            return _FusionFn.apply(ir, vis, self)
+            return _FusionFn.apply(ir, vis, self, False)
+
+    def forward_rgb(self, ir, vis_rgb):
+        """``forward(ir, RGB2YCrCb(vis_rgb)[:, 0:1])`` with the RGB -> Y conversion of the task wrappers
+        (core/model_fusion_auto.py:69-92, 713-714) done inside the visible stem: ``vis_rgb`` is the [B,3,H,W] RGB image;
+        its gradient is the Y-path gradient spread over R, G, B."""
+        self._check_inputs(ir, vis_rgb)
+        if vis_rgb.shape[1] != 3:
+            raise ValueError("forward_rgb expects a [B,3,H,W] RGB visible image")
+        with torch.cuda.device(ir.device):
+            return _FusionFn.apply(ir.float(), vis_rgb.float(), self, True)
 
     def _loss(self, ir, vis, mask):
         logits = self(ir, vis)
@@ -1128,9 +1146,10 @@ class Network_Fusion_Searched(nn.Module):
 
 class _FusionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ir, vis, net):
+    def forward(ctx, ir, vis, net, vis_rgb=False):
         need = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])   # False under no_grad
-        out, saved = net._run_forward(ir[:, 0:1], vis[:, 0:1], need)
+        out, saved = net._run_forward(ir[:, 0:1], vis if vis_rgb else vis[:, 0:1], need, vis_rgb=vis_rgb)
+        ctx.vis_rgb = vis_rgb
         if saved is not None:
             # `out` is an output of this node: keeping it in a plain attribute would form the cycle
             # out -> grad_fn(ctx) -> saved['out'] -> out and pin ~2 GB of activations per 480x640 frame until the
@@ -1149,24 +1168,28 @@ class _FusionFn(torch.autograd.Function):
             if ctx.had_saved:
                 raise RuntimeError("Trying to backward through the paif_b200 fusion graph a second time: the saved "
                                    "activations are freed after the first backward (retain_graph is not supported)")
-            return None, None, None
+            return None, None, None, None
         g = g.contiguous().float()
         (out,) = ctx.saved_tensors
         with torch.cuda.device(g.device):
             g_ir, g_vis = net._run_backward(dict(saved, out=out), g)
         ctx.saved = None
         outs = []
-        for gi, shape, need in ((g_ir, ctx.shapes[0], ctx.needs_input_grad[0]),
-                                (g_vis, ctx.shapes[1], ctx.needs_input_grad[1])):
+        for k, (gi, shape, need) in enumerate(((g_ir, ctx.shapes[0], ctx.needs_input_grad[0]),
+                                               (g_vis, ctx.shapes[1], ctx.needs_input_grad[1]))):
             if not need:
                 outs.append(None)
+            elif k == 1 and ctx.vis_rgb:
+                # Y = .299 R + .587 G + .114 B: the Y gradient spread over the three colour planes
+                coef = torch.tensor([0.299, 0.587, 0.114], device=gi.device, dtype=gi.dtype).view(1, 3, 1, 1)
+                outs.append(gi.unsqueeze(1) * coef)
             elif shape[1] == 1:
                 outs.append(gi.view(shape))
             else:
                 full = torch.zeros(shape, device=gi.device, dtype=gi.dtype)
                 full[:, 0] = gi
                 outs.append(full)
-        return outs[0], outs[1], None
+        return outs[0], outs[1], None, None
 
 
 class Network_Fusion_Searched_showfeatures(Network_Fusion_Searched):
