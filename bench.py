@@ -275,7 +275,7 @@ def run_pgd_leg(net, seg, seg_name, args, world, rank, dev, barrier, n_total, ta
     torch.backends.cuda.matmul.allow_tf32 = True            # the stock consumer may use TF32 matmuls
     torch.backends.cudnn.allow_tf32 = True
     cast = None if args.pgd_consumer_dtype == "tf32" else torch.bfloat16
-    task = FusionSegTask(net, seg, consumer_autocast=cast, per_sample_minmax=True).to(dev).eval()
+    task = FusionSegTask(net, seg, consumer_autocast=cast, per_sample_minmax=True, fused_glue=True).to(dev).eval()
     H, W = args.height, args.width
     per_gpu = len(shard_range(n_total, 0, world))
     mb = max(1, min(args.pgd_micro_batch, per_gpu))
@@ -635,9 +635,6 @@ def run_ours(args):
         pgd = run_pgd_leg(net, seg, seg_name, args, world, rank, dev, barrier, max(args.pgd_frames, world), "strong")
     if args.pgd_weak_frames > 0:
         pgd_weak = run_pgd_leg(net, seg, seg_name, args, world, rank, dev, barrier, args.pgd_weak_frames * world, "weak")
-    for m_ in ([seg] if seg is not None else []):
-        if hasattr(m_, "_paif_pgd_runner"):
-            object.__delattr__(m_, "_paif_pgd_runner")
     torch.cuda.empty_cache()
 
     # BASELINE configs[1] as written: fusion + SegFormer inference at batch 16 (N = 1 only; the consumer is stock PyTorch)
@@ -645,7 +642,7 @@ def run_ours(args):
     if args.config_b_steps > 0 and world == 1 and seg is not None:
         from paif_b200.consumer import FusionSegTask
         cast = None if args.pgd_consumer_dtype == "tf32" else torch.bfloat16
-        task = FusionSegTask(net, seg, consumer_autocast=cast, per_sample_minmax=True).to(dev).eval()
+        task = FusionSegTask(net, seg, consumer_autocast=cast, per_sample_minmax=True, fused_glue=True).to(dev).eval()
 
         def step_b():
             with torch.no_grad():

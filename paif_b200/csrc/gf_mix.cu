@@ -229,6 +229,13 @@ __device__ __forceinline__ void tmem_wait_ld16(float (&v)[16]) {
                  :: "memory");
 }
 
+// mbarrier arrive that releases a shared-memory stage the calling thread has just READ with ordinary loads.  The loaded
+// values are operands of the statement, so the arrive cannot be scheduled before they are in registers (an arrive
+// issued while a load is still in flight would let the producer refill the stage under it).
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, float a, float b, float c, float d, float e) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e) : "memory");
+}
+
 // one work chunk: rows [y0, y0 + rows) of strip `strip` of image b
 struct Chunk { int b, strip, y0, rows; };
 struct Walker {
@@ -379,7 +386,7 @@ gf_mix_kernel(const Params p) {
                             Sz[k][c] += zn[k][c] - zq[k][c];
                             Sgz[k][c] = __fmaf_rn(-gq[k], zq[k][c], __fmaf_rn(gn[k], zn[k][c], Sgz[k][c]));
                         }
-                    mbar_arrive(smem_u32(&bars->r_empty[st]));       // after the values were consumed
+                    mbar_arrive_after_loads(smem_u32(&bars->r_empty[st]), gn[0], zn[0][3], zn[1][3], zn[2][3], zn[3][3]);
                     ++rcount;
                 }
                 if (t < 8) continue;

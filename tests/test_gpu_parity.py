@@ -99,3 +99,35 @@ def test_forward2_returns_the_reference_intermediates():
         assert a.shape == b.shape, i
         assert (a - b).abs().max().item() < (5e-4 if i in (3, 4, 6, 7) else 5e-5), (i, (a - b).abs().max().item())
 
+
+
+@pytest.mark.parametrize("storage,tol", [("fp32", 1e-3), ("bf16", 1e-2)])
+def test_config_d_shape_768x1024_matches_oracle(storage, tol):
+    """BASELINE configs[3] (M3FD shape 768x1024): the fused image of one pair — computed inside a batch of 3, so the
+    multi-chunk / multi-wave tilings of the big shape are exercised — against the CPU oracle, in both storage modes
+    (north_star: 1e-3 fp32 / 1e-2 bf16 on the [0,1] scale)."""
+    g = load_golden("seed1_random_1x48x72")
+    net = build(g["state_dict"], "auto")
+    net.storage = storage
+    torch.manual_seed(21)
+    ir, vis = torch.rand(3, 1, 768, 1024), torch.rand(3, 3, 768, 1024)
+    ref = fo.fusion_forward(g["state_dict"], paif_b200.fusion_at, ir[1:2], vis[1:2])
+    with torch.no_grad():
+        out = net(ir.to(DEV), vis.to(DEV))
+    err = (out[1:2].cpu() - ref).abs().max().item()
+    assert err <= tol, err
+
+
+def test_bench_tiling_batch16_480x640_matches_oracle():
+    """The launch geometry bench.py times (batch 16 x 480x640: 7 row chunks per conv strip, 3 chunks per guided-filter
+    strip, persistent CTAs walking several work items): two pairs of the batch against the CPU oracle."""
+    g = load_golden("seed0_default_2x40x56")
+    net = build(g["state_dict"], "auto")
+    torch.manual_seed(1)
+    ir, vis = torch.rand(16, 1, 480, 640), torch.rand(16, 3, 480, 640)
+    with torch.no_grad():
+        out = net(ir.to(DEV), vis.to(DEV)).cpu()
+    for b in (0, 11):
+        ref = fo.fusion_forward(g["state_dict"], paif_b200.fusion_at, ir[b:b + 1], vis[b:b + 1])
+        err = (out[b:b + 1] - ref).abs().max().item()
+        assert err <= 1e-3, (b, err)
