@@ -314,6 +314,19 @@ int paif_glue_backward(const float* fused, const float* vis, const float* gx, co
                        int per_sample, int B, int H, int W, void* stream);
 
 /* ====================================================================================
+ * Loss head of the attack (attack/attack.py:446-448 with Seg_loss :103-114):
+ *   up = F.interpolate(seg, size=(H, W), mode='bilinear', align_corners=False); CrossEntropyLoss(ignore_index)
+ * forward: partial[B][paif_glue_blocks(H, W)] = per-block sums of the per-pixel losses times inv_norm (the caller adds
+ *          them up: inv_norm = 1 / #valid gives the reference's mean); gup (optional) [B][K][H][W] receives the gradient
+ *          of the loss w.r.t. the UP-SAMPLED logits.
+ * backward: gseg[B][K][h][w] = *gscale (device scalar, may be null = 1) x the bilinear adjoint of gup, as a
+ *          fixed-order gather (deterministic; the stock backward scatters with float atomics). */
+int paif_segloss_forward(const float* seg, const long long* label, float* partial, float* gup,
+                         long long ignore_index, float inv_norm, int K, int B, int h, int w, int H, int W, void* stream);
+int paif_segloss_backward(const float* gup, const float* gscale, float* gseg,
+                          int K, int B, int h, int w, int H, int W, void* stream);
+
+/* ====================================================================================
  * PGD step (attack/attack.py:504-512), in place and for one modality:
  *   delta <- clamp(clamp(delta + alpha * sign(grad), -eps, eps), 0 - x, 1 - x)
  * grad is delta.grad as autograd accumulated it (the reference never zeroes it).  n elements, contiguous fp32. */

@@ -85,6 +85,8 @@ SIGNATURES = {
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
     "paif_pgd_step": [_f, _f, _f, C.c_float, C.c_float, _ll, _f],
+    "paif_segloss_forward": [_f, _f, _f, _f, _ll, C.c_float, _i, _i, _i, _i, _i, _i, _f],
+    "paif_segloss_backward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "paif_glue_blocks": [_i, _i],
     "paif_glue_forward": [_f, _f, C.POINTER(C.c_float), C.POINTER(C.c_float), _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_glue_backward": [_f, _f, _f, C.POINTER(C.c_float), _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],

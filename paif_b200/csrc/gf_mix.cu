@@ -21,7 +21,7 @@
 //              of (A', b') that the vertical running sum needs lives in TMEM (tcgen05.st / ld, 32 columns per row and
 //              warp: 9 x 32 columns next to the 128 accumulator columns); output = mean2(A') g + mean2(b') + C.
 // The level-2 history is what bounds the strip width: 9 rows x 64 values x 4 B = 2.3 KB per pixel column.
-#define PAIF_MBAR_SPIN_LIMIT (1u << 21)        // a lost arrival traps after a few seconds instead of minutes
+#define PAIF_MBAR_SPIN_LIMIT (1u << 25)        // a lost arrival traps after ~10 s of polling (compute-sanitizer runs need the slack)
 #define PAIF_MBAR_QUIET
 #define PAIF_MBAR_SUSPEND_NS 20000
 #include "tc_ptx.cuh"

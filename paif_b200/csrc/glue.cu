@@ -214,6 +214,103 @@ glue_bwd_kernel(const float* __restrict__ fused, const float* __restrict__ vis, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Loss head of the attack (attack/attack.py:446-448 + Seg_loss :103-114): bilinear up-sampling of the consumer's
+// logits to the label size (F.interpolate, align_corners=False) + cross entropy with ignore_index, and its gradient
+// w.r.t. the logits.  One pass over the label pixels computes the per-pixel loss (block partial sums in a fixed
+// order) and the gradient of the UP-SAMPLED logits; a second pass gathers it back onto the low-resolution grid —
+// every logit sums its <= 9 x 9 contributing label pixels in a fixed order, where the stock bilinear backward
+// scatters with float atomics (run-to-run differences in the last bits, which PGD's sign() turns into flipped
+// pixels).  K <= 16 classes.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SL_MAXK = 16;
+
+__device__ __forceinline__ void bilerp_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;          // area_pixel_compute_source_index, align_corners = false
+    if (src < 0.f) src = 0.f;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = src - (float)i0;
+}
+
+__global__ void __launch_bounds__(GLUE_NT)
+segloss_forward_kernel(const float* __restrict__ seg, const long long* __restrict__ label, float* __restrict__ partial,
+                       float* __restrict__ gup, int K, int h, int w, int H, int W, long long ignore_index, float inv_norm) {
+    __shared__ float sc[GLUE_NT / 32];
+    const int b = blockIdx.y;
+    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    const float* sb = seg + (size_t)b * K * h * w;
+    float acc = 0.f;
+    for (int i = blockIdx.x * GLUE_NT + threadIdx.x; i < H * W; i += gridDim.x * GLUE_NT) {
+        const int y = i / W, x = i - y * W;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilerp_src(y, sy, h, y0, y1, ly);
+        bilerp_src(x, sx, w, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        float l[SL_MAXK];
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < SL_MAXK; ++k) {
+            if (k < K) {
+                const float* p = sb + (size_t)k * h * w;
+                l[k] = hy * (hx * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * (hx * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+                m = fmaxf(m, l[k]);
+            }
+        }
+        float se = 0.f;
+#pragma unroll
+        for (int k = 0; k < SL_MAXK; ++k) if (k < K) se += expf(l[k] - m);
+        const long long lab = label[(size_t)b * H * W + i];
+        const bool valid = lab != ignore_index && lab >= 0 && lab < K;
+        const float lse = m + logf(se);
+        if (valid) {
+            float lt = 0.f;
+#pragma unroll
+            for (int k = 0; k < SL_MAXK; ++k) if (k == (int)lab) lt = l[k];
+            acc += lse - lt;
+        }
+        if (gup) {
+#pragma unroll
+            for (int k = 0; k < SL_MAXK; ++k)
+                if (k < K) gup[((size_t)b * K + k) * H * W + i] = valid ? (expf(l[k] - lse) - (k == (int)lab ? 1.f : 0.f)) * inv_norm : 0.f;
+        }
+    }
+    acc = block_reduce(acc, [](float a, float c) { return a + c; }, sc);
+    if (threadIdx.x == 0) partial[(size_t)b * gridDim.x + blockIdx.x] = acc * inv_norm;
+}
+
+// gseg[b][k][yl][xl] = gscale * sum over the label pixels whose bilinear footprint contains (yl, xl), fixed order
+__global__ void __launch_bounds__(GLUE_NT)
+segloss_backward_kernel(const float* __restrict__ gup, const float* __restrict__ gscale, float* __restrict__ gseg,
+                        int K, int h, int w, int H, int W, long long total) {
+    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    const float gs = gscale ? *gscale : 1.f;
+    const int ry = (H + h - 1) / h + 1, rx = (W + w - 1) / w + 1;           // candidate half-window in label pixels
+    for (long long i = (long long)blockIdx.x * GLUE_NT + threadIdx.x; i < total; i += (long long)gridDim.x * GLUE_NT) {
+        const int xl = (int)(i % w), yl = (int)((i / w) % h);
+        const long long bk = i / ((long long)w * h);
+        const float* g = gup + (size_t)bk * H * W;
+        const int yc = (int)(((float)yl + 0.5f) / sy), xc = (int)(((float)xl + 0.5f) / sx);
+        float acc = 0.f;
+        for (int y = max(0, yc - 2 * ry); y <= min(H - 1, yc + 2 * ry); ++y) {
+            int y0, y1; float ly;
+            bilerp_src(y, sy, h, y0, y1, ly);
+            const float wy = (y0 == yl ? 1.f - ly : 0.f) + (y1 == yl ? ly : 0.f);
+            if (y0 != yl && y1 != yl) continue;
+            for (int x = max(0, xc - 2 * rx); x <= min(W - 1, xc + 2 * rx); ++x) {
+                int x0, x1; float lx;
+                bilerp_src(x, sx, w, x0, x1, lx);
+                const float wx = (x0 == xl ? 1.f - lx : 0.f) + (x1 == xl ? lx : 0.f);
+                if (x0 != xl && x1 != xl) continue;
+                acc = fmaf(wy * wx, g[(size_t)y * W + x], acc);
+            }
+        }
+        gseg[i] = acc * gs;
+    }
+}
+
 }  // namespace paif
 
 using namespace paif;
@@ -264,4 +361,26 @@ extern "C" int paif_pgd_step(float* delta, const float* grad, const float* x, fl
     const int blocks = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
     pgd_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(delta, grad, x, alpha, eps, n);
     return check_launch("paif_pgd_step");
+}
+
+extern "C" int paif_segloss_forward(const float* seg, const long long* label, float* partial, float* gup,
+                                    long long ignore_index, float inv_norm, int K, int B, int h, int w, int H, int W,
+                                    void* stream) {
+    PAIF_REQUIRE(seg && label && partial, "null pointer");
+    PAIF_REQUIRE(K > 0 && K <= SL_MAXK, "1 <= classes <= 16");
+    PAIF_REQUIRE(B > 0 && B <= 65535 && h > 0 && w > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "bad shape");
+    dim3 grid(glue_blocks(H * W), B);
+    segloss_forward_kernel<<<grid, GLUE_NT, 0, (cudaStream_t)stream>>>(seg, label, partial, gup, K, h, w, H, W, ignore_index, inv_norm);
+    return check_launch("paif_segloss_forward");
+}
+
+extern "C" int paif_segloss_backward(const float* gup, const float* gscale, float* gseg,
+                                     int K, int B, int h, int w, int H, int W, void* stream) {
+    PAIF_REQUIRE(gup && gseg, "null pointer");
+    PAIF_REQUIRE(K > 0 && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "bad shape");
+    const long long total = (long long)B * K * h * w;
+    long long want = (total + GLUE_NT - 1) / GLUE_NT;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+    segloss_backward_kernel<<<blocks, GLUE_NT, 0, (cudaStream_t)stream>>>(gup, gscale, gseg, K, h, w, H, W, total);
+    return check_launch("paif_segloss_backward");
 }

@@ -116,11 +116,48 @@ def _replay_signature(model, vis_shape, ir_shape, label_shape, device, epsilon, 
     return (tuple(vis_shape), tuple(ir_shape), tuple(label_shape), str(device), float(epsilon), float(alpha), sigs)
 
 
+class _SegLossFn(torch.autograd.Function):
+    """Bilinear up-sampling of the logits to the label size + cross entropy (sum over the valid pixels / (H W)) as the
+    kernels ``paif_segloss_forward`` / ``paif_segloss_backward``; the gradient w.r.t. the logits is a fixed-order
+    gather, so it is reproducible bit for bit (the stock bilinear backward accumulates with float atomics)."""
+
+    @staticmethod
+    def forward(ctx, seg, label, ignore_index):
+        B, K, h, w = seg.shape
+        H, W = label.shape[1:]
+        seg = seg.contiguous().float()
+        label = label.contiguous().long()
+        dev = seg.device
+        nblk = _lib.load().paif_glue_blocks(H, W)
+        partial = torch.empty((B, nblk), device=dev, dtype=torch.float32)
+        gup = torch.empty((B, K, H, W), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(dev):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.call("paif_segloss_forward", seg.data_ptr(), label.data_ptr(), partial.data_ptr(),
+                      None if gup is None else gup.data_ptr(), int(ignore_index), 1.0 / float(H * W), K, B, h, w, H, W, stream)
+        ctx.gup, ctx.dims = gup, (K, B, h, w, H, W)
+        return partial.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        K, B, h, w, H, W = ctx.dims
+        gup = ctx.gup
+        g = g.contiguous().float()
+        gseg = torch.empty((B, K, h, w), device=gup.device, dtype=torch.float32)
+        with torch.cuda.device(gup.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(gup.device).cuda_stream)
+            _lib.call("paif_segloss_backward", gup.data_ptr(), g.data_ptr(), gseg.data_ptr(), K, B, h, w, H, W, stream)
+        return gseg, None, None
+
+
 def _seg_loss(seg, label, ignore_index):
     """``Seg_loss`` of attack/attack.py:103-114 (bilinear up-sampling to the label size + cross entropy with
     ``ignore_index=255``).  The reference averages over the valid pixels of its batch-1 input; here the per-pixel
     losses are SUMMED and divided by the constant H*W, so that a frame's gradient does not depend on which other
-    frames share its micro-batch (PGD steps along sign(grad): a positive constant factor changes nothing)."""
+    frames share its micro-batch (PGD steps along sign(grad): a positive constant factor changes nothing).
+    CUDA logits with <= 16 classes go through the fused, deterministic loss-head kernels."""
+    if seg.is_cuda and seg.shape[1] <= 16:
+        return _SegLossFn.apply(seg, label, ignore_index)
     seg = F.interpolate(seg, size=label.shape[1:], mode="bilinear", align_corners=False)
     return F.cross_entropy(seg, label, ignore_index=ignore_index, reduction="sum") / float(label.shape[1] * label.shape[2])
 

@@ -69,6 +69,31 @@ def test_pgd_step_kernel_is_the_reference_update_bit_for_bit(n):
     assert torch.equal(delta.grad, grad)                        # the running gradient sum is left to autograd
 
 
+@pytest.mark.parametrize("shape", [(2, 9, 30, 40, 120, 160), (1, 9, 12, 16, 47, 61), (3, 5, 24, 40, 24, 40)])
+def test_fused_loss_head_matches_interpolate_plus_cross_entropy(shape):
+    """paif_segloss_forward / _backward == F.interpolate(bilinear, align_corners=False) + cross entropy(ignore_index)
+    (attack/attack.py:446-448, Seg_loss :103-114), value and gradient; the gradient is reproducible bit for bit."""
+    import torch.nn.functional as F
+    B, K, h, w, H, W = shape
+    g = torch.Generator().manual_seed(B * 100 + h)
+    seg = (torch.randn(B, K, h, w, generator=g) * 2).to(DEV)
+    label = torch.randint(0, K, (B, H, W), generator=g)
+    label[torch.rand(B, H, W, generator=g) < 0.1] = 255
+    label = label.to(DEV)
+    a = seg.clone().requires_grad_(True)
+    la = ev._seg_loss(a, label, 255)
+    (3.0 * la).backward()
+    b = seg.double().clone().requires_grad_(True)
+    up = F.interpolate(b, size=(H, W), mode="bilinear", align_corners=False)
+    lb = F.cross_entropy(up, label, ignore_index=255, reduction="sum") / float(H * W)
+    (3.0 * lb).backward()
+    assert abs(la.item() - lb.item()) <= 1e-5 * max(1.0, abs(lb.item()))
+    assert (a.grad.double() - b.grad).abs().max().item() <= 1e-6 + 1e-5 * b.grad.abs().max().item()
+    c = seg.clone().requires_grad_(True)
+    (3.0 * ev._seg_loss(c, label, 255)).backward()
+    assert torch.equal(a.grad, c.grad)
+
+
 class TinyBatchTask(nn.Module):
     """Per-sample task model (what a micro-batching harness needs) with a convolutional head: every stock op on its
     path has a deterministic backward, so PGD through it is reproducible bit for bit."""
