@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PAIF_ABI_VERSION 2   /* 2: PaifConvDesc.storage, bf16 storage entry points, paif_out_forward_tc */
+#define PAIF_ABI_VERSION 3   /* 3: paif_gf_mix_forward, glue / PGD / loss-head kernels, paif_stem_forward_rgb, paif_widen_bf16_map */
 
 #define PAIF_EINVAL   (-1)   /* bad argument (null pointer, unsupported size) */
 #define PAIF_ENOTSUP  (-2)   /* configuration not supported by this build     */
@@ -312,6 +312,10 @@ int paif_glue_forward(const float* fused, const float* vis, const float* mean3, 
 int paif_glue_backward(const float* fused, const float* vis, const float* gx, const float* std3,
                        const float* lohi, const int* ties, float* sums, float* gfused, float* gvis,
                        int per_sample, int B, int H, int W, void* stream);
+
+/* bf16 C8 map [B][C/8][H][W][8] -> fp32 C4 map [B][C/4][H][W][4].  The backward-to-input chain keeps fp32 gradient
+ * maps; this is how it reads the activations a bf16-storage forward saved (net.storage = 'bf16' with requires_grad). */
+int paif_widen_bf16_map(const void* src, float* dst, int C, int B, int H, int W, void* stream);
 
 /* ====================================================================================
  * Loss head of the attack (attack/attack.py:446-448 with Seg_loss :103-114):

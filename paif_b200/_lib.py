@@ -11,7 +11,7 @@ from . import build as _build
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpaif_b200.so")
 
-ABI_VERSION = 2                                             # PAIF_ABI_VERSION of include/paif_b200.h
+ABI_VERSION = 3                                             # PAIF_ABI_VERSION of include/paif_b200.h
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 STORAGE_F32, STORAGE_BF16, STORAGE_F32_BF16 = 0, 1, 2      # PaifConvDesc.storage
 
@@ -85,6 +85,7 @@ SIGNATURES = {
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
     "paif_pgd_step": [_f, _f, _f, C.c_float, C.c_float, _ll, _f],
+    "paif_widen_bf16_map": [_f, _f, _i, _i, _i, _i, _f],
     "paif_segloss_forward": [_f, _f, _f, _f, _ll, C.c_float, _i, _i, _i, _i, _i, _i, _f],
     "paif_segloss_backward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "paif_glue_blocks": [_i, _i],

@@ -30,7 +30,11 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, profile=False):
+def build(force=False, verbose=False, profile=False, sanitize=False):
+    """profile: -DPAIF_TC_PROFILE role-timeline counters (libpaif_b200_prof.so); sanitize: a build for compute-sanitizer
+    runs (libpaif_b200_san.so: mbarrier waits poll without the suspend-time hint)."""
+    if sanitize:
+        return _build_variant("_san", ["-DPAIF_NO_SUSPEND_HINT"])
     lib = LIB.replace(".so", "_prof.so") if profile else LIB
     if profile:
         if os.path.exists(lib) and os.path.getmtime(lib) >= max(
@@ -60,5 +64,24 @@ def build(force=False, verbose=False, profile=False):
     return lib
 
 
+def _build_variant(suffix, defines):
+    lib = LIB.replace(".so", suffix + ".so")
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", suffix + ".o"))
+        procs.append(subprocess.Popen([_nvcc()] + NVCC_FLAGS + defines + ["-c", os.path.join(CSRC, src), "-o", obj],
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        objs.append(obj)
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("paif_b200: nvcc build failed:\n" + out)
+    subprocess.check_call([_nvcc(), "-shared", "-o", lib] + objs + ["-lcudart"])
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv,
+                sanitize="--sanitize" in sys.argv))

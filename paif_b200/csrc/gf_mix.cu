@@ -23,7 +23,9 @@
 // The level-2 history is what bounds the strip width: 9 rows x 64 values x 4 B = 2.3 KB per pixel column.
 #define PAIF_MBAR_SPIN_LIMIT (1u << 25)        // a lost arrival traps after ~10 s of polling (compute-sanitizer runs need the slack)
 #define PAIF_MBAR_QUIET
+#ifndef PAIF_NO_SUSPEND_HINT                   // (builds for compute-sanitizer runs define it: plain polling)
 #define PAIF_MBAR_SUSPEND_NS 20000
+#endif
 #include "tc_ptx.cuh"
 
 namespace paif {

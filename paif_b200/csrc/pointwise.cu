@@ -1239,6 +1239,29 @@ extern "C" int paif_add_act(const float* x, const float* y, const float* slope, 
     return check_launch("paif_add_act");
 }
 
+// bf16 C8 map [B][C/8][H][W][8] -> fp32 C4 map [B][C/4][H][W][4]: how the backward-to-input chain (fp32 gradient maps)
+// reads the activations a bf16-storage forward saved.  One thread = one pixel of one oct.
+__global__ void __launch_bounds__(256)
+widen_bf16_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, long long plane, long long total) {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long oct = i / plane, pix = i - oct * plane;          // oct counts (image, oct) pairs
+        float4 lo, hi;
+        bf8_unpack(__ldg(src + i), lo, hi);
+        dst[(2 * oct) * plane + pix] = lo;
+        dst[(2 * oct + 1) * plane + pix] = hi;
+    }
+}
+
+extern "C" int paif_widen_bf16_map(const void* src, float* dst, int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(src && dst, "null pointer");
+    PAIF_REQUIRE(C > 0 && C % 8 == 0 && B > 0 && H > 0 && W > 0, "bad shape");
+    const long long plane = (long long)H * W, total = plane * (C / 8) * B;
+    long long want = (total + 255) / 256;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+    widen_bf16_kernel<<<blocks, 256, 0, ST>>>(static_cast<const uint4*>(src), reinterpret_cast<float4*>(dst), plane, total);
+    return check_launch("paif_widen_bf16_map");
+}
+
 extern "C" int paif_add_maps(const float* a, const float* b, const float* c, float* out, long long n, void* stream) {
     PAIF_REQUIRE(a && b && out, "null pointer");
     PAIF_REQUIRE(n >= 0 && n % 4 == 0, "n must be a multiple of 4");

@@ -892,9 +892,6 @@ class Network_Fusion_Searched(nn.Module):
             return False
         if self.storage != 'bf16':
             raise ValueError("storage must be 'fp32' or 'bf16', not %r" % (self.storage,))
-        if save:
-            raise RuntimeError("storage='bf16' is a forward-only mode (run under torch.no_grad()); the "
-                               "backward-to-input path keeps fp32 activations: set storage='fp32' for PGD")
         if self.conv_engine == 'direct':
             raise RuntimeError("storage='bf16' runs on the tcgen05 engine; conv_engine='direct' is the exact-fp32 path")
         if self._C != 32:
@@ -1001,16 +998,28 @@ class Network_Fusion_Searched(nn.Module):
         saved = None
         if save:
             saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, gstats=gstats, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
-                         scale=scale, recs3=recs3, out=out, pre_out=pre_out, packed=p)
+                         scale=scale, recs3=recs3, out=out, pre_out=pre_out, packed=p, bf16=bf16)
         return out, saved
 
     def _run_backward(self, saved, g):
         """g: [B,1,H,W] contiguous fp32.  Returns (g_ir, g_vis) as [B,H,W] planes."""
         B, H, W, C = saved["B"], saved["H"], saved["W"], self._C
         p = saved["packed"]
-        rt = _Runtime(B, H, W, C, g.device, self._engine(), False)
+        rt = _Runtime(B, H, W, C, g.device, _lib.ENGINE_TCGEN05 if saved.get("bf16") else self._engine(), False)
         rt.profile = self.profile
         rt.dilconv_dense = self.dilconv_dense
+        if saved.get("bf16"):
+            # The forward ran with bf16 maps (storage='bf16') and saved them as such (half the memory of the fp32 mode
+            # until now); the gradient chain itself is fp32 (TF32 operands, fp32 accumulate): widen the saved
+            # activations once, and rebuild the attention plane the bf16 blend kernel does not keep.
+            saved = dict(saved)
+            for key in ("branch_recs", "recs3", "a_f", "v_f"):
+                saved[key] = self._widen(rt, saved[key])
+            scale, agg_again = rt.new_plane(), rt.new_map()
+            rt.call("paif_spa_fused_forward", p["spa_w"].data_ptr(), p["spa_k"], saved["a_f"].data_ptr(),
+                    saved["v_f"].data_ptr(), agg_again.data_ptr(), scale.data_ptr(), C, B, H, W)
+            saved["scale"] = scale
+            del agg_again
         # stem_out + tanh; if the last op of the final chain is a ResidualModule its PReLU' mask is fused here
         gf2 = rt.new_map()
         last = self.chain._ops[-1]._op
@@ -1057,6 +1066,19 @@ class Network_Fusion_Searched(nn.Module):
             grads.append(gimg)
         self.last_launches = rt.launches
         return grads[0], grads[1]
+
+    def _widen(self, rt, obj):
+        """bf16 C8 maps inside a saved-activation structure -> fp32 C4 maps (paif_widen_bf16_map); everything else as is."""
+        if isinstance(obj, torch.Tensor):
+            if obj.dtype == torch.bfloat16 and obj.dim() == 5 and obj.shape[-1] == 8:
+                b, o, h, w, _ = obj.shape
+                out = torch.empty((b, o * 2, h, w, 4), device=obj.device, dtype=torch.float32)
+                rt.call("paif_widen_bf16_map", obj.data_ptr(), out.data_ptr(), o * 8, b, h, w)
+                return out
+            return obj
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._widen(rt, o) for o in obj)
+        return obj
 
     def _chain3_bwd(self, rt, p, saved, gf2, gmasked):
         chain, packs, recs = self.chain, p["chain"], saved["recs3"]

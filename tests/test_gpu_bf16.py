@@ -224,7 +224,7 @@ def test_bf16_storage_matches_reference_golden(case):
 
 def test_bf16_storage_full_size_and_mode_rules():
     """480x640: bf16 mode against the fp32 CPU oracle (1e-2 gate) and against the module's own fp32 mode; the mode is
-    forward-only and refuses the exact-fp32 engine."""
+    refuses the exact-fp32 engine."""
     g = load_golden("seed1_random_1x48x72")
     sd = g["state_dict"]
     net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
@@ -244,8 +244,6 @@ def test_bf16_storage_full_size_and_mode_rules():
     e_32 = (out16 - out32).abs().max().item()
     assert e_ref < 1e-2 and e_32 < 1e-2, (e_ref, e_32)
     assert launches16 > 20
-    with pytest.raises(RuntimeError):                                  # forward-only
-        net(ir.to(DEV).requires_grad_(True), vis.to(DEV))
     net.conv_engine = 'direct'
     with pytest.raises(RuntimeError), torch.no_grad():
         net(ir.to(DEV), vis.to(DEV))
@@ -253,3 +251,24 @@ def test_bf16_storage_full_size_and_mode_rules():
     x = ir.to(DEV).requires_grad_(True)
     net(x, vis.to(DEV)).sum().backward()                               # fp32 mode still differentiates
     assert x.grad is not None
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES[:3])
+def test_bf16_storage_input_gradients_match_reference_golden(case):
+    """storage='bf16' with requires_grad: the forward saves bf16 activations, the backward widens them and runs the
+    fp32 (TF32) gradient chain.  Gates of BASELINE.md 6 / SURVEY 8d for the bf16 tier against the reference-autograd
+    gradients of the golden fixtures: rel-L2 <= 0.15, sign agreement >= 98 %."""
+    from test_gpu_backward import rel_l2, sign_agreement
+    g = load_golden(case)
+    net = paif_b200.Network_Fusion_Searched(32, None, paif_b200.fusion_at)
+    net.load_state_dict(g["state_dict"], strict=True)
+    net = net.to(DEV).eval()
+    net.storage = 'bf16'
+    ir = g["ir"].to(DEV).requires_grad_(True)
+    vis_full = g["vis"].to(DEV).requires_grad_(True)
+    out = net(ir, strided_vis(vis_full))
+    assert (out.detach().cpu() - g["out"]).abs().max().item() < 1e-2
+    out.backward(g["grad_out"].to(DEV))
+    for got, ref in ((ir.grad.cpu(), g["grad_ir"]), (vis_full.grad.cpu()[:, 0:1], g["grad_vis"][:, 0:1])):
+        r, s_ = rel_l2(got, ref), sign_agreement(got, ref)
+        assert r < 0.15 and s_ > 0.98, (case, r, s_)
