@@ -313,6 +313,51 @@ int paif_glue_backward(const float* fused, const float* vis, const float* gx, co
                        const float* lohi, const int* ties, float* sums, float* gfused, float* gvis,
                        int per_sample, int B, int H, int W, void* stream);
 
+/* ====================================================================================
+ * Whole-network entry point: Network_Fusion_Searched.forward(ir, vis) (core/model_fusion_auto.py:625-635) for the
+ * shipped `fusion_at` genotype (test_original.py:711-713 == robust_test.py:255-257), C = 32, eval mode, as ONE call
+ * over a caller-owned workspace.  It launches the same kernels in the same order as the per-operator entry points
+ * driven by paif_b200/fusion.py (tcgen05 engine), so results are bit-identical; no allocation, no synchronisation.
+ *   weights : device pointers to the packed parameters (what paif_b200/fusion.py::_packed builds once per parameter
+ *             version: TF32 / bf16 UMMA weight images, folded BatchNorm scale/shift, the fused-decomposition mix tiles,
+ *             the merged stem_out stencil); every conv carries its direct-engine image too (may be NULL here).
+ *   ir, vis : fp32 1-channel images with arbitrary batch / row / pixel strides (vis is the channel-last strided Y view
+ *             the reference wrappers pass, core/model_fusion_auto.py:82-91); out: contiguous [B][1][H][W] fp32.
+ *   storage : PAIF_STORAGE_F32 (TF32 MMAs, max-abs 1e-3 tier) or PAIF_STORAGE_BF16 (bf16 maps, 1e-2 tier).
+ *   workspace: >= paif_fusion_workspace_bytes(B, H, W, storage) bytes, 256-byte aligned, contents undefined on entry.
+ * Needs W % 4 == 0 (paif_gf_mix_supported); other shapes / genotypes go through the per-operator entry points. */
+typedef struct PaifFusionConv { const float* direct; const void* mma_tf32; const void* mma_bf16; } PaifFusionConv;
+typedef struct PaifFusionRDB { PaifFusionConv conv[3]; const float* slope; } PaifFusionRDB;
+typedef struct PaifFusionWeights {
+    const float* stem_w[2];          /* stem_1 / stem_2 conv weights [32][9]                         */
+    const float* stem_a[2];          /* their PReLU slopes                                            */
+    const void*  gfmix_w[2];         /* paif_gf_mix_forward weight images (conv1x1_lf / conv1x1_hf)   */
+    const float* c1x1_b[2];          /* conv1x1_lf / conv1x1_hf bias                                  */
+    PaifFusionRDB rdb[3];            /* decompation.chain._ops.0, decompation.chain2._ops.0, ._ops.1  */
+    PaifFusionConv dil_dense;        /* DilConv as one dense 3x3 (dil 2) convolution: pw[co][ci] dw[ci][t] */
+    const float* dil_scale;          /* its folded BatchNorm                                          */
+    const float* dil_shift;
+    const float* spa_w;              /* spa.spatial.conv.weight [4][k*k]                              */
+    int spa_k;
+    PaifFusionConv eca_conv1, eca_conv2;
+    const float* eca_w1d;            /* eca_layer Conv1d weight [3]                                   */
+    const float* eca_a;              /* ECABasicBlock PReLU slope                                     */
+    PaifFusionConv res_conv7, res_merged;    /* ResidualModule: 7x7, and 3x3(dil 2) merged with the 1x1 */
+    const float* res_scale;          /* its folded BatchNorm                                          */
+    const float* res_shift;
+    const float* res_a;
+    const void*  out_mma_tf32;       /* merged stem_out stencil (paif_out_forward_tc)                 */
+    const void*  out_mma_bf16;
+    const float* out_wm;
+    const float* out_a;
+} PaifFusionWeights;
+long long paif_fusion_workspace_bytes(int B, int H, int W, int storage);
+int paif_fusion_forward(const PaifFusionWeights* weights,
+                        const float* ir, long long ir_stride_b, long long ir_stride_y, long long ir_stride_x,
+                        const float* vis, long long vis_stride_b, long long vis_stride_y, long long vis_stride_x,
+                        float* out, void* workspace, long long workspace_bytes, int storage,
+                        int B, int H, int W, void* stream);
+
 /* bf16 C8 map [B][C/8][H][W][8] -> fp32 C4 map [B][C/4][H][W][4].  The backward-to-input chain keeps fp32 gradient
  * maps; this is how it reads the activations a bf16-storage forward saved (net.storage = 'bf16' with requires_grad). */
 int paif_widen_bf16_map(const void* src, float* dst, int C, int B, int H, int W, void* stream);

@@ -41,6 +41,29 @@ class ConvDesc(C.Structure):
     ]
 
 
+class FusionConv(C.Structure):
+    """Mirror of ``PaifFusionConv``."""
+    _fields_ = [("direct", _f), ("mma_tf32", _f), ("mma_bf16", _f)]
+
+
+class FusionRDB(C.Structure):
+    """Mirror of ``PaifFusionRDB``."""
+    _fields_ = [("conv", FusionConv * 3), ("slope", _f)]
+
+
+class FusionWeights(C.Structure):
+    """Mirror of ``PaifFusionWeights`` (include/paif_b200.h)."""
+    _fields_ = [
+        ("stem_w", _f * 2), ("stem_a", _f * 2), ("gfmix_w", _f * 2), ("c1x1_b", _f * 2),
+        ("rdb", FusionRDB * 3),
+        ("dil_dense", FusionConv), ("dil_scale", _f), ("dil_shift", _f),
+        ("spa_w", _f), ("spa_k", _i),
+        ("eca_conv1", FusionConv), ("eca_conv2", FusionConv), ("eca_w1d", _f), ("eca_a", _f),
+        ("res_conv7", FusionConv), ("res_merged", FusionConv), ("res_scale", _f), ("res_shift", _f), ("res_a", _f),
+        ("out_mma_tf32", _f), ("out_mma_bf16", _f), ("out_wm", _f), ("out_a", _f),
+    ]
+
+
 # name -> argtypes (restype is int unless noted); must list EVERY symbol of the header.
 SIGNATURES = {
     "paif_abi_version": [],
@@ -85,6 +108,8 @@ SIGNATURES = {
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],
     "paif_pgd_step": [_f, _f, _f, C.c_float, C.c_float, _ll, _f],
+    "paif_fusion_workspace_bytes": [_i, _i, _i, _i],
+    "paif_fusion_forward": [C.POINTER(FusionWeights), _f, _ll, _ll, _ll, _f, _ll, _ll, _ll, _f, _f, _ll, _i, _i, _i, _i, _f],
     "paif_widen_bf16_map": [_f, _f, _i, _i, _i, _i, _f],
     "paif_segloss_forward": [_f, _f, _f, _f, _ll, C.c_float, _i, _i, _i, _i, _i, _i, _f],
     "paif_segloss_backward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
@@ -119,7 +144,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name == "paif_last_error_string" else
-                      _ll if name == "paif_gf_backward_work_floats" else _i)
+                      _ll if name in ("paif_gf_backward_work_floats", "paif_fusion_workspace_bytes") else _i)
     if lib.paif_abi_version() != ABI_VERSION:
         raise PaifError("libpaif_b200.so ABI version mismatch")
     _lib = lib

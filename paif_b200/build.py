@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpaif_b200.so")
-SOURCES = ["abi.cu", "stem.cu", "gf.cu", "gf_mix.cu", "conv_direct.cu", "conv_tcgen05.cu", "pointwise.cu", "glue.cu"]
+SOURCES = ["abi.cu", "stem.cu", "gf.cu", "gf_mix.cu", "conv_direct.cu", "conv_tcgen05.cu", "pointwise.cu", "glue.cu", "fusion_net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "--extended-lambda", "-Xcompiler", "-fPIC"]
 

@@ -809,6 +809,9 @@ class Network_Fusion_Searched(nn.Module):
         self.dilconv_dense = True
         #: stem_out's merged 5x5 stencil on the tensor-core engine (False / conv_engine='direct': the FFMA kernel)
         self.out_tensor_core = True
+        #: inference (no saved activations) of the shipped genotype as ONE C-ABI call, ``paif_fusion_forward`` — the same
+        #: kernels in the same order as the per-operator path, bit-identical results, no Python between the launches
+        self.native_forward = True
         #: decomposition + folded 1x1 in one kernel (paif_gf_mix_forward: channel mix between the two box-filter levels
         #: on tcgen05, no LF maps); False / conv_engine='direct' / forward2: guided filter, then the 1x1 as a convolution
         self.gf_fused = True
@@ -835,7 +838,7 @@ class Network_Fusion_Searched(nn.Module):
         """Hashable identity of the packed weights a forward would use now (parameter versions, engine switches):
         holders of device pointers into the pack (CUDA-graph replays) compare it before reuse."""
         return (self._pack_key(need_bwd), getattr(self, "_pack_epoch", 0), self.conv_engine, self.storage,
-                self.dilconv_dense, self.out_tensor_core, self.gf_fused)
+                self.dilconv_dense, self.out_tensor_core, self.gf_fused, self.native_forward)
 
     def _load_from_state_dict(self, *args, **kwargs):
         self.invalidate_packed()
@@ -885,6 +888,75 @@ class Network_Fusion_Searched(nn.Module):
                                               "(masks are rebuilt from saved activations)")
         self._pack_cache = (key, p)
         return p
+
+    # -------------------------------------------------------------------------------------
+    def _native_weights(self, p):
+        """``PaifFusionWeights`` over the packed tensors of ``p`` (kept alive by the pack cache), or None when this
+        module is not the shipped ``fusion_at`` structure that ``paif_fusion_forward`` implements."""
+        if "native" in p:
+            return p["native"]
+        d = self.decompation
+        ok = ([type(m._op) for m in d.chain._ops] == [ResidualDenseBlock, DilConv]
+              and [type(m._op) for m in d.chain2._ops] == [ResidualDenseBlock, ResidualDenseBlock]
+              and [type(m._op) for m in self.chain._ops] == [ECABasicBlock, ResidualModule]
+              and all((o.k, o.d) == (3, 1) for o in (d.chain._ops[0]._op, d.chain2._ops[0]._op, d.chain2._ops[1]._op))
+              and (d.chain._ops[1]._op.k, d.chain._ops[1]._op.d) == (3, 2)
+              and self.chain._ops[0]._op.k == 3 and (self.chain._ops[1]._op.k, self.chain._ops[1]._op.d) == (7, 1)
+              and p["spa_k"] == 5)
+        w = None
+        if ok:
+            w = _lib.FusionWeights()
+
+            def cv(dst, cw):
+                dst.direct, dst.mma_tf32, dst.mma_bf16 = _ptr(cw.direct), _ptr(cw.mma), _ptr(cw.mma16)
+
+            for i in range(2):
+                w.stem_w[i], w.stem_a[i] = p["stem_w"][i].data_ptr(), p["stem_a"][i].data_ptr()
+                w.gfmix_w[i], w.c1x1_b[i] = p["gfmix_w"][i].data_ptr(), p["c1x1_b"][i].data_ptr()
+            for i, pk in enumerate((p["chain_ir"][0], p["chain_vis"][0], p["chain_vis"][1])):
+                for j in range(3):
+                    cv(w.rdb[i].conv[j], pk["w"][j])
+                w.rdb[i].slope = pk["a"].data_ptr()
+            dil = p["chain_ir"][1]
+            cv(w.dil_dense, dil["wdense"])
+            w.dil_scale, w.dil_shift = dil["s"].data_ptr(), dil["sh"].data_ptr()
+            w.spa_w, w.spa_k = p["spa_w"].data_ptr(), p["spa_k"]
+            eca, res = p["chain"]
+            cv(w.eca_conv1, eca["w1"])
+            cv(w.eca_conv2, eca["w2"])
+            w.eca_w1d, w.eca_a = eca["w1d"].data_ptr(), eca["a"].data_ptr()
+            cv(w.res_conv7, res["w0"])
+            cv(w.res_merged, res["wm"])
+            w.res_scale, w.res_shift, w.res_a = res["s"].data_ptr(), res["sh"].data_ptr(), res["a"].data_ptr()
+            w.out_mma_tf32, w.out_mma_bf16 = p["out_mma"].data_ptr(), p["out_mma16"].data_ptr()
+            w.out_wm, w.out_a = p["out_wm"].data_ptr(), p["out_a"].data_ptr()
+        p["native"] = w
+        return w
+
+    def _run_forward_native(self, ir, vis):
+        """The whole forward as ONE C-ABI call (``paif_fusion_forward``) over one workspace tensor; None when the
+        configuration is outside what that entry point implements (the per-operator path runs instead)."""
+        if not (self.native_forward and self.conv_engine in ('auto', 'tcgen05') and self.gf_fused and self.dilconv_dense
+                and self.out_tensor_core and self.profile is None):
+            return None
+        B, _, H, W = ir.shape
+        lib = _lib.load()
+        if not lib.paif_gf_mix_supported(self._C, H, W):
+            return None
+        p = self._packed(False)
+        w = self._native_weights(p)
+        if w is None:
+            return None
+        storage = _lib.STORAGE_BF16 if self._bf16_storage(False) else _lib.STORAGE_F32
+        need = lib.paif_fusion_workspace_bytes(B, H, W, storage)
+        ws = torch.empty((need,), device=ir.device, dtype=torch.uint8)
+        out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(ir.device).cuda_stream)
+        _lib.call("paif_fusion_forward", ctypes.byref(w), ir.data_ptr(), ir.stride(0), ir.stride(2), ir.stride(3),
+                  vis.data_ptr(), vis.stride(0), vis.stride(2), vis.stride(3), out.data_ptr(), ws.data_ptr(), need,
+                  storage, B, H, W, stream)
+        self.last_launches = 28
+        return out
 
     def _bf16_storage(self, save):
         """True when this forward runs with bf16 activation maps (``self.storage == 'bf16'``)."""
@@ -1170,7 +1242,11 @@ class _FusionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ir, vis, net, vis_rgb=False):
         need = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])   # False under no_grad
-        out, saved = net._run_forward(ir[:, 0:1], vis if vis_rgb else vis[:, 0:1], need, vis_rgb=vis_rgb)
+        out = None
+        if not need and not vis_rgb:
+            out, saved = net._run_forward_native(ir[:, 0:1], vis[:, 0:1]), None
+        if out is None:
+            out, saved = net._run_forward(ir[:, 0:1], vis if vis_rgb else vis[:, 0:1], need, vis_rgb=vis_rgb)
         ctx.vis_rgb = vis_rgb
         if saved is not None:
             # `out` is an output of this node: keeping it in a plain attribute would form the cycle

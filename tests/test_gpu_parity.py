@@ -131,3 +131,43 @@ def test_bench_tiling_batch16_480x640_matches_oracle():
         ref = fo.fusion_forward(g["state_dict"], paif_b200.fusion_at, ir[b:b + 1], vis[b:b + 1])
         err = (out[b:b + 1] - ref).abs().max().item()
         assert err <= 1e-3, (b, err)
+
+
+@pytest.mark.parametrize("storage", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 40, 56), (1, 96, 200)])
+def test_whole_network_entry_point_is_bit_identical_to_the_per_operator_path(storage, shape):
+    """paif_fusion_forward (one C-ABI call, caller-owned workspace) launches the same kernels in the same order as the
+    per-operator path driven from Python: same bits.  Also called here straight through ctypes — device pointers, sizes
+    and a stream, no fusion._Runtime — on the strided Y view the reference wrappers pass."""
+    import ctypes
+    from paif_b200 import _lib
+    B, H, W = shape
+    g = load_golden("seed1_random_1x48x72")
+    net = build(g["state_dict"], "auto")
+    net.storage = storage
+    torch.manual_seed(5)
+    ir, vis = torch.rand(B, 1, H, W).to(DEV), strided_vis(torch.rand(B, 3, H, W).to(DEV))
+    with torch.no_grad():
+        net.native_forward = False
+        per_op = net(ir, vis)
+        net.native_forward = True
+        native = net(ir, vis)
+    assert torch.equal(per_op, native)
+    lib = _lib.load()
+    st = _lib.STORAGE_BF16 if storage == "bf16" else _lib.STORAGE_F32
+    w = net._native_weights(net._packed(False))
+    need = lib.paif_fusion_workspace_bytes(B, H, W, st)
+    assert need > 0
+    ws = torch.empty(need, device=DEV, dtype=torch.uint8)
+    out = torch.empty(B, 1, H, W, device=DEV)
+    y = vis[:, 0:1]
+    rc = lib.paif_fusion_forward(ctypes.byref(w), ir.data_ptr(), ir.stride(0), ir.stride(2), ir.stride(3),
+                                 y.data_ptr(), y.stride(0), y.stride(2), y.stride(3), out.data_ptr(), ws.data_ptr(), need,
+                                 st, B, H, W, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.paif_last_error_string()
+    torch.cuda.synchronize()
+    assert torch.equal(out, per_op)
+    rc = lib.paif_fusion_forward(ctypes.byref(w), ir.data_ptr(), ir.stride(0), ir.stride(2), ir.stride(3),
+                                 y.data_ptr(), y.stride(0), y.stride(2), y.stride(3), out.data_ptr(), ws.data_ptr(), need - 1,
+                                 st, B, H, W, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc != 0 and b"workspace" in lib.paif_last_error_string()
