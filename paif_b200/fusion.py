@@ -15,6 +15,7 @@ calls into ``libpaif_b200.so``.  There is no PyTorch/CPU fallback: a missing lib
 CPU tensor raises.
 """
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -814,7 +815,7 @@ class Network_Fusion_Searched(nn.Module):
         self.native_forward = True
         #: decomposition + folded 1x1 in one kernel (paif_gf_mix_forward: channel mix between the two box-filter levels
         #: on tcgen05, no LF maps); False / conv_engine='direct' / forward2: guided filter, then the 1x1 as a convolution
-        self.gf_fused = True
+        self.gf_fused = os.environ.get("PAIF_GF_FUSED", "1") != "0"      # (the env switch exists for compute-sanitizer runs)
         self._pack_cache = None
         self._pack_epoch = 0
         self.last_launches = 0
