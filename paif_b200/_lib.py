@@ -83,6 +83,7 @@ SIGNATURES = {
     "paif_conv_num_tiles": [_i, _i, _i],
     "paif_conv_tc_kq": [_i, _i, _i],
     "paif_conv_tc_kq_bf16": [_i, _i, _i],
+    "paif_conv_set_persistent": [_i],
     "paif_dwconv_forward": [_f, _f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
     "paif_dilconv_forward": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _f],
     "paif_add_act": [_f, _f, _f, _f, _f, _ll, _f],

@@ -26,6 +26,7 @@
 //    MMA), columns outside the image are zeroed once per stage and never overwritten.
 #include "conv_epilogue.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace paif {
 
@@ -36,8 +37,9 @@ constexpr int TC_EPI_WARPS = 8;                                   // two groups 
 constexpr int TC_MMA_WARPS = 1;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_PROD_WARP = TC_EPI_WARPS + TC_MMA_WARPS;
 constexpr int TC_NT = (TC_EPI_WARPS + TC_MMA_WARPS + 1) * 32;     // 320
-constexpr int TC_SMEM_BUDGET = 222 * 1024;
+constexpr int TC_SMEM_BUDGET = 227 * 1024;   // the sm_100 opt-in maximum of dynamic shared memory per CTA
 constexpr int TC_WSLAB_MAX = 110 * 1024;
+constexpr int TC_WSLAB_RESIDENT_MAX = 196 * 1024;   // fp32 7x7: both K halves resident next to a 3-stage half-row ring
 
 struct TcPlan {
     int KQ;            // quads per pipeline unit (8 = whole source row, 4 = half)
@@ -66,6 +68,11 @@ static bool tc_make_plan(int nsrc, int k, int dil, bool in_bf16, TcPlan* p, int 
     const int pps = in_bf16 ? 4 : 8;                     // planes per source
     const int src_bytes = taps * pps * 16 * cp;          // weights of one source (32 cin x cp cout per tap)
     if (nsrc * src_bytes <= TC_WSLAB_MAX) { p->KQ = pps; p->npass = 1; p->gpp = nsrc; }
+    // fp32 7x7 32->32 (196 KB of weights): everything resident, half-row (4-plane) ring stages.  The layer is tensor-bound
+    // (28 N=224 MMAs = 3136 cycles per row), so a ring of 1.5 rows covers the HBM latency, and a single pass means
+    // tall chunks (no 16-row TMEM limit, 6 halo rows per chunk instead of per 16 rows) and no per-pass weight reload.
+    else if (!in_bf16 && cp == 32 && k == 7 && nsrc == 1 && src_bytes <= TC_WSLAB_RESIDENT_MAX &&
+             TC_SMEM_BUDGET - src_bytes - 1024 >= 3 * (pps / 2) * p->RW * 16) { p->KQ = pps / 2; p->npass = 1; p->gpp = 2; }
     else if (src_bytes <= TC_WSLAB_MAX) { p->KQ = pps; p->npass = nsrc; p->gpp = 1; }
     else if (!in_bf16 && src_bytes / 2 <= TC_WSLAB_MAX) { p->KQ = pps / 2; p->npass = nsrc * 2; p->gpp = 1; }
     else return false;
@@ -110,6 +117,8 @@ __device__ unsigned long long tc_prof[16];
 
 struct TcGeom {
     int B, H, W, nsrc, k, dil, RCH, tiles_alloc;
+    int persist;           // 1: grid = (n, 1, 1) persistent CTAs, each owning an equal share of the launch's output rows
+    int strips, rows_total;   // column strips per image; B * strips * H
     const void* src[3];
     const void* wmma;      // [K-group of KQ planes][dx][KQ/2 (K step)][2 (16-B chunk)][dy][32 cout][16 B of cin]:
                            // 4 TF32-rounded fp32 or 8 bf16 input channels per 16 bytes
@@ -127,6 +136,57 @@ struct TcBars {
     alignas(16) float ch_shift[32];
 };
 static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservation");
+
+struct TcSeg { int x0, r0, b, nrows, xs, poff, npx; };
+
+// Start of a segment (see the kernel): geometry of the next piece of this CTA's share, and — block-wide — the drain of
+// the previous segment, re-armed accumulator barriers, re-zeroed border columns.  Called by every thread of the CTA.
+template <int K, int DIL, int KQ>
+__device__ __forceinline__ void tc_seg_begin(const TcGeom& g, TcBars* bars, unsigned char* s_ring, int tid, int seg,
+                                             int& lin, int lin_end, TcSeg& sg) {
+    constexpr int pad = DIL * (K - 1) / 2, RW = TC_TW + 2 * pad;
+    if (g.persist) {
+        const int si = lin / g.H;                              // (image, strip) index
+        sg.r0 = lin - si * g.H;
+        sg.nrows = min(g.H - sg.r0, lin_end - lin);
+        sg.b = si / g.strips;
+        sg.x0 = (si - sg.b * g.strips) * TC_TW;
+        lin += sg.nrows;
+    } else {
+        sg.x0 = blockIdx.x * TC_TW; sg.r0 = blockIdx.y * g.RCH; sg.b = blockIdx.z;
+        sg.nrows = min(g.RCH, g.H - sg.r0);
+        lin = lin_end;
+    }
+    // valid x range of the halo'd row segment: columns [poff, poff + npx) of the RW-wide smem row
+    sg.xs = max(0, sg.x0 - pad);
+    const int xe = min(g.W, sg.x0 + TC_TW + pad);
+    sg.poff = sg.xs - (sg.x0 - pad);
+    sg.npx = xe - sg.xs;
+    if (seg > 0) {
+        // every role is done with the previous segment: all MMAs retired (the epilogue saw the last acc_full), no bulk
+        // copy in flight (the issuer consumed every full stage), every drained accumulator slot is zero again
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 128); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    if (sg.npx < RW) {
+        // image-border strip: zero the columns no bulk copy will ever write (the conv's zero padding)
+        const int nplanes = g.plan.stages * g.plan.upr * KQ;
+        const int nzero = RW - sg.npx;
+        for (int i = tid; i < nplanes * nzero; i += TC_NT) {
+            const int pl = i / nzero, j = i - pl * nzero;
+            const int px = j < sg.poff ? j : j + sg.npx;
+            *reinterpret_cast<float4*>(s_ring + ((size_t)pl * RW + px) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+}
 
 // K, DIL, KQ are compile-time so that the MMA issue loop unrolls into straight-line code whose descriptors differ
 // from a per-row base by immediates: the single issuing thread then sustains the tensor pipe's own rate
@@ -149,16 +209,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     TcBars* bars = reinterpret_cast<TcBars*>(s_ring + P.stages * P.stage_bytes);  // (P.unit_bytes == UNIT, set by the host)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int x0 = blockIdx.x * TC_TW, r0 = blockIdx.y * g.RCH, b = blockIdx.z;
-    const int nrows = min(g.RCH, g.H - r0);
     constexpr int k = K, dil = DIL, pad = DIL * (K - 1) / 2;
     constexpr int dsh = DIL >> 1;                              // log2(dil), dil in {1, 2}
     constexpr int RW = TC_TW + 2 * pad;                        // halo'd row width in pixels
     constexpr int UNIT = KQ * RW * 16;                         // bytes of one ring stage
-    const int nin = nrows + 2 * pad;                           // input rows touched per pass
-    // valid x range of the halo'd row segment: columns [poff, poff + npx) of the RW-wide smem row
-    const int xs = max(0, x0 - pad), xe = min(g.W, x0 + TC_TW + pad);
-    const int poff = xs - (x0 - pad), npx = xe - xs;
 
     if (tid == 0) {
         for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), TC_MMA_WARPS); }
@@ -176,24 +230,35 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (npx < RW) {
-        // image-border strip: zero the columns no bulk copy will ever write (the conv's zero padding)
-        const int nplanes = P.stages * P.upr * KQ;
-        const int nzero = RW - npx;
-        for (int i = tid; i < nplanes * nzero; i += TC_NT) {
-            const int pl = i / nzero, j = i - pl * nzero;
-            const int px = j < poff ? j : j + npx;
-            *reinterpret_cast<float4*>(s_ring + ((size_t)pl * RW + px) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        fence_proxy_async();
+    // Persistent launches (g.persist): the launch's B * strips * H output rows, linearised as (image, strip, row), are
+    // split into gridDim.x equal contiguous shares — every SM gets the same number of rows whatever the batch, so there
+    // is no partial last wave and one prologue per SM.  A share is walked as segments (the part of it inside one
+    // image strip); between segments the CTA drains (block-wide sync), re-arms the accumulator barriers and re-zeroes
+    // the border columns.  The ring barriers, the weights and the TMEM allocation live across segments.  Output bits do
+    // not depend on where a share starts: every output row accumulates its taps in input-row order from a zeroed slot.
+    int lin = 0, lin_end = 1;
+    if (g.persist) {
+        lin = (int)((long long)blockIdx.x * g.rows_total / gridDim.x);
+        lin_end = (int)((long long)(blockIdx.x + 1) * g.rows_total / gridDim.x);
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);    // warp-uniform for the compiler
+    // (each role runs its own segment loop, so that a role only carries the state it needs in registers; all three
+    //  execute the same block-wide barriers in tc_seg_begin)
+#define TC_SEG_LOOP_BEGIN                                                                                     \
+    for (int seg = 0; lin < lin_end; ++seg) {                                                                 \
+        TcSeg sg_;                                                                                            \
+        tc_seg_begin<K, DIL, KQ>(g, bars, s_ring, tid, seg, lin, lin_end, sg_);                               \
+        const int x0 = sg_.x0, r0 = sg_.r0, b = sg_.b, nrows = sg_.nrows, nin = sg_.nrows + 2 * pad;          \
+        const int xs = sg_.xs, poff = sg_.poff, npx = sg_.npx;                                                \
+        (void)x0; (void)r0; (void)b; (void)nin; (void)xs; (void)poff; (void)npx;                              \
+        if (seg == 0) tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);   /* warp-uniform for the compiler */
+    uint32_t tmem_base = 0;
 
     if (warp < TC_EPI_WARPS) {
         // ===================== epilogue: TMEM -> registers -> fused epilogue -> global =====================
+        float csum[PARTIALS ? 32 : 1];                          // (PARTIALS launches are tiled: one segment)
+#pragma unroll
+        for (int c = 0; c < (PARTIALS ? 32 : 1); ++c) csum[c] = 0.f;
+        TC_SEG_LOOP_BEGIN
         const int grp = warp >> 2, wq = warp & 3;               // row-interleaved groups; TMEM lane quarter
         const int x = x0 + wq * 32 + lane;
         const bool xin = x < g.W;
@@ -282,7 +347,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) { pn[q] = make_float4(0.f, 0.f, 0.f, 0.f); qn[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
         if (any_fetch && xin && grp < nrows) fetch_next(grp);
-        if (grp == 0) {
+        if (grp == 0 && seg == 0) {
             // accumulators start from zero: every MMA accumulates (the TMEM allocation holds garbage)
             for (int sl = 0; sl < TC_SLOTS; ++sl) {
                 if constexpr (CP == 16) tmem_zero16(tmem_base + ((uint32_t)(wq * 32) << 16) + sl * CP);
@@ -291,9 +356,6 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->zeroed));
         }
-        float csum[PARTIALS ? 32 : 1];
-#pragma unroll
-        for (int c = 0; c < (PARTIALS ? 32 : 1); ++c) csum[c] = 0.f;
         TC_PROF_DECL;
         for (int ro = grp; ro < nrows; ro += 2) {
             const int slot = tc_slot(ro, dsh), use = ro / TC_SLOTS;
@@ -401,6 +463,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             }
         }
         TC_PROF_END(0);
+        }   // segments
         if (PARTIALS) {
             // deterministic per-CTA channel sums: shuffle tree, then fixed-order cross-warp sum via smem
             float* red = reinterpret_cast<float*>(s_ring);          // the ring is idle once the last accumulator is done
@@ -418,11 +481,14 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
 #pragma unroll
                 for (int w8 = 0; w8 < TC_EPI_WARPS; ++w8) t += red[w8 * 32 + tid];
                 const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-                e.chan_partials[((size_t)b * g.tiles_alloc + tile) * 32 + tid] = t;
+                e.chan_partials[((size_t)blockIdx.z * g.tiles_alloc + tile) * 32 + tid] = t;
             }
         }
     } else if (warp < TC_PROD_WARP) {
         // ===================== MMA issuer (the warp runs the uniform loop; one elected lane issues) =====================
+        int stage = 0;                                           // ring position (valid units only) and its phase,
+        uint32_t phase = 0;                                      // carried across segments
+        TC_SEG_LOOP_BEGIN
         {
             constexpr uint32_t plane_bytes = RW * 16;
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
@@ -431,13 +497,15 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             constexpr int nk8 = KQ / 2;
             constexpr int spr = TC_SLOTS >> dsh;
             TC_PROF_DECL;
-            TC_WAIT(mbar_wait(smem_u32(&bars->zeroed), 0));
-            tc_fence_after();
-            int stage = 0;                                       // ring position (valid units only) and its phase
-            uint32_t phase = 0;
-            for (int pass = 0; pass < P.npass; ++pass) {
-                TC_WAIT(mbar_wait(smem_u32(&bars->wfull), pass & 1));
+            if (seg == 0) {
+                TC_WAIT(mbar_wait(smem_u32(&bars->zeroed), 0));
                 tc_fence_after();
+            }
+            for (int pass = 0; pass < P.npass; ++pass) {
+                if (seg == 0) {                                  // (persistent launches are single-pass: the slab stays)
+                    TC_WAIT(mbar_wait(smem_u32(&bars->wfull), pass & 1));
+                    tc_fence_after();
+                }
                 for (int ri = 0; ri < nin; ++ri) {               // input row y = r0 - pad + ri
                     const int y = r0 - pad + ri;
                     const bool yok = (y >= 0 && y < g.H);
@@ -514,18 +582,20 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             }
             TC_PROF_END(1);
         }
+        }   // segments
         __syncwarp();
     } else {
         // ===================== producer: weight slab + halo'd input rows via cp.async.bulk =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        TC_SEG_LOOP_BEGIN
         {
             const size_t plane = (size_t)g.H * g.W;
             const uint32_t row_bytes = (uint32_t)npx * 16;
             TC_PROF_DECL;
-            int stage = 0;
-            uint32_t phase = 0;
             for (int pass = 0; pass < P.npass; ++pass) {
                 if (pass > 0) mbar_wait(smem_u32(&bars->wempty), (pass - 1) & 1);
-                {
+                if (seg == 0) {
                     const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(g.wmma) + (size_t)pass * P.slab_bytes;
                     const uint32_t wdst = smem_u32(s_w), wbar = smem_u32(&bars->wfull);
                     if (elect_one()) {
@@ -562,8 +632,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             }
             TC_PROF_END(2);
         }
+        }   // segments
         __syncwarp();
     }
+#undef TC_SEG_LOOP_BEGIN
 
     tc_fence_before();
     __syncthreads();
@@ -739,6 +811,27 @@ static int tc_rows_per_cta(const PaifConvDesc& d, const TcPlan& p) {
     return best;
 }
 
+static int tc_persist_mode = -1;      // paif_conv_set_persistent / PAIF_TC_PERSIST
+
+// Persistent launch shape: single-pass plans without per-CTA channel sums (those are summed per fixed tile so that
+// the ECA statistics do not depend on the partition).  Returns the number of CTAs (0 = tiled launch).
+static int tc_persistent_ctas(const TcPlan& p, bool partials, int B, int H, int W) {
+    if (tc_persist_mode < 0) { const char* e = getenv("PAIF_TC_PERSIST"); tc_persist_mode = e ? atoi(e) : 1; }   // 0: tiled launches (A/B runs)
+    if (!tc_persist_mode || p.npass != 1 || partials) return 0;
+    const long long rows = (long long)B * cdiv(W, TC_TW) * H;
+    if (rows > 0x7fffffffLL) return 0;
+    const long long n = rows / 12;                         // at least ~12 rows per CTA: a prologue costs about 8
+    return (int)(n < 1 ? 1 : (n > tc_num_sms() ? tc_num_sms() : n));
+}
+
+static void tc_set_grid(TcGeom& g, const TcPlan& p, bool partials, dim3* grid) {
+    g.strips = cdiv(g.W, TC_TW);
+    g.rows_total = g.B * g.strips * g.H;
+    const int n = tc_persistent_ctas(p, partials, g.B, g.H, g.W);
+    g.persist = n > 0;
+    *grid = n > 0 ? dim3(n, 1, 1) : dim3(g.strips, cdiv(g.H, g.RCH), g.B);
+}
+
 int conv_tc_tiles(int H, int W) {
     // upper bound independent of the per-launch row chunk: the smallest chunk is 4 rows
     return cdiv(W, TC_TW) * cdiv(H, 4);
@@ -753,7 +846,8 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     for (int i = 0; i < 3; ++i) g.src[i] = d.src[i];
     g.wmma = d.weight_mma;
     EpiParams e = make_epi(d);
-    dim3 grid(cdiv(d.W, TC_TW), cdiv(d.H, g.RCH), d.B);
+    dim3 grid;
+    tc_set_grid(g, g.plan, d.chan_partials != nullptr, &grid);
     if (d.chan_partials) {
         // partial-sum slots beyond this launch's tile count must read as zero
         cudaError_t err = cudaMemsetAsync(d.chan_partials, 0, (size_t)d.B * conv_tc_tiles(d.H, d.W) * 32 * sizeof(float), stream);
@@ -766,10 +860,10 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
         int dev_;                                                                                                   \
         if (attr_needed(attr_done, &dev_)) {                                                                        \
             cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, false, S_>,                           \
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024); \
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET); \
             if (err == cudaSuccess)                                                                                 \
                 err = cudaFuncSetAttribute(conv_tc_kernel<K_, D_, Q_, true, S_>,                                    \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET);     \
             if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; } \
             attr_mark(attr_done, dev_);                                                                             \
         }                                                                                                           \
@@ -805,13 +899,14 @@ int out_tc_launch(const void* feat, const void* wmma, const float* slope, float*
     g.wmma = wmma;
     EpiParams e = {};
     e.slope = slope; e.post_scale = 1.f; e.out = out; e.out_pre = pre_out; e.H = H; e.W = W;
-    dim3 grid(cdiv(W, TC_TW), cdiv(H, g.RCH), B);
+    dim3 grid;
+    tc_set_grid(g, g.plan, false, &grid);
     static unsigned long long attr_done = 0;
     int dev;
     if (attr_needed(attr_done, &dev)) {
-        cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<5, 1, 8, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
+        cudaError_t err = cudaFuncSetAttribute(conv_tc_kernel<5, 1, 8, false, 0, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET);
         if (err == cudaSuccess)
-            err = cudaFuncSetAttribute(conv_tc_kernel<5, 1, 4, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 1024);
+            err = cudaFuncSetAttribute(conv_tc_kernel<5, 1, 4, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET);
         if (err != cudaSuccess) { set_error("out_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; }
         attr_mark(attr_done, dev);
     }
@@ -828,6 +923,17 @@ extern "C" int paif_debug_tc_counters(unsigned long long* out16, int reset) {
     return 0;
 }
 #endif
+
+}  // namespace paif
+
+extern "C" int paif_conv_set_persistent(int on) {
+    if (paif::tc_persist_mode < 0) { const char* e = getenv("PAIF_TC_PERSIST"); paif::tc_persist_mode = e ? atoi(e) : 1; }
+    const int prev = paif::tc_persist_mode;
+    paif::tc_persist_mode = on ? 1 : 0;
+    return prev;
+}
+
+namespace paif {
 
 int conv_tc_kq(int nsrc, int k, int dil, bool bf16) {
     TcPlan p;

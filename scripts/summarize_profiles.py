@@ -64,7 +64,10 @@ def launch_shares(rows, out_csv, out_txt):
 
 
 def read_rep(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if path.endswith(".csv"):                 # `ncu -i x.ncu-rep --page raw --csv` already run on the GPU box
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     lines = [l for l in out.splitlines(True) if l.startswith('"')]
     rd = csv.reader(io.StringIO("".join(lines)))
     head, units = next(rd), next(rd)
@@ -134,6 +137,17 @@ def main():
     if os.path.exists(lc):
         launch_shares(read_launch_csv(lc), os.path.join(dst, "%s_ncu_launches.csv" % tag),
                       os.path.join(dst, "%s_ncu_launch_shares.txt" % tag))
+    r2 = [(k, os.path.join(src, "prof_%s_%s.raw.csv" % (k, tag))) for k in ("fwd", "bwd", "bf16")]
+    if any(os.path.exists(f) for _, f in r2):            # scripts/prof_r2.sh layout: one capture per step kind
+        what = {"fwd": "one forward step, batch 16 x 480x640, fp32 storage (scripts/one_step.py fwd)",
+                "bwd": "one forward + backward-to-input step, batch 8 x 480x640 (scripts/one_step.py bwd)",
+                "bf16": "one forward step, batch 16 x 480x640, bf16 storage (scripts/one_step.py bf16)"}
+        for k, f in r2:
+            if os.path.exists(f):
+                full_summary([f], os.path.join(dst, "%s_ncu_full_%s.txt" % (tag, k)), os.path.join(dst, "%s_ncu_full_%s.json" % (tag, k)),
+                             os.path.join(dst, "conv_traffic.json") if k == "fwd" else None,
+                             "ncu --set full --clock-control none, every kernel of %s" % what[k])
+        return
     full_summary([os.path.join(src, "prof_conv_%s.ncu-rep" % tag), os.path.join(src, "prof_gf_%s.ncu-rep" % tag)],
                  os.path.join(dst, "%s_ncu_full_summary.txt" % tag), os.path.join(dst, "%s_ncu_full_summary.json" % tag),
                  os.path.join(dst, "conv_traffic.json"),

@@ -315,6 +315,35 @@ def test_conv_tcgen05_full_size_tiling(k, dil, nsrc):
         assert err < 2.0 ** -9 * max(scale, 1.0), (i, err, scale)
 
 
+@pytest.mark.parametrize("B,H,W,k,dil,nsrc", [(3, 50, 200, 3, 1, 1), (5, 61, 300, 3, 2, 1), (3, 50, 200, 7, 1, 1),
+                                               (7, 45, 130, 1, 1, 3), (3, 77, 640, 3, 1, 3), (2, 480, 640, 7, 1, 1)])
+def test_conv_tcgen05_persistent_launch_is_bit_identical_to_tiled(B, H, W, k, dil, nsrc):
+    """The persistent launch (one CTA per SM, equal contiguous shares of the B*strips*H output rows, a share crossing
+    strip / image boundaries as separate segments) against the tiled launch of the same kernel: same bits (every output
+    row accumulates its taps in the same order whatever the partition), and both against the exact-fp32 direct engine."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    xs = [torch.randn(B, 8, H, W, 4, device=DEV, generator=g) for _ in range(nsrc)]
+    r1 = torch.randn(B, 8, H, W, 4, device=DEV, generator=g)
+    w = torch.randn(32, 32 * nsrc, k, k, device=DEV, generator=g) * 0.1
+    a = torch.tensor([0.3], device=DEV)
+    cw = fusion._ConvW(w, nsrc, k, dil)
+    lib = _lib.load()
+    outs = {}
+    prev = lib.paif_conv_set_persistent(1)
+    try:
+        for mode in (1, 0):
+            lib.paif_conv_set_persistent(mode)
+            o, opre, act2, _ = rt(B, H, W, _lib.ENGINE_TCGEN05).conv(xs, cw, slope=a, post_scale=0.5, post_res=[r1],
+                                                                      want_pre=True)
+            outs[mode] = (o.clone(), opre.clone())
+    finally:
+        lib.paif_conv_set_persistent(prev)
+    assert torch.equal(outs[1][0], outs[0][0]) and torch.equal(outs[1][1], outs[0][1])
+    ref = rt(B, H, W, _lib.ENGINE_DIRECT).conv(xs, cw, slope=a, post_scale=0.5, post_res=[r1])[0]
+    scale = ref.abs().max().item()
+    assert (outs[1][0] - ref).abs().max().item() < 2.0 ** -9 * max(scale, 1.0)
+
+
 @pytest.mark.parametrize("shape", [(2, 19, 45), (1, 70, 300), (3, 33, 128)])
 def test_stem_out_on_tensor_cores_matches_ffma_kernel(shape):
     """paif_out_forward_tc (interior pixels as an implicit GEMM with TF32 / bf16 operands, border pixels exact) against
