@@ -137,6 +137,8 @@ int paif_out_forward_tc(const void* feat, const void* w_mma, const float* wm, co
  *   v += post_res[0] + post_res[1] + post_res[2]            (residual adds)
  *   out = v ; out_act2 = PReLU(v, *slope2) (optional) ;
  *   chan_partials[b][tile][c] = sum over the tile's pixels of v (optional, deterministic)
+ * The residual sums are formed in an engine-defined order (the tcgen05 engine fetches all maps of a row first and adds
+ * them afterwards); with bf16 storage the tcgen05 engine takes at most 4 residual maps per launch (pre + post).
  */
 typedef struct PaifConvDesc {
     int B, H, W;

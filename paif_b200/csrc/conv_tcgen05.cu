@@ -97,6 +97,9 @@ static bool tc_make_plan(int nsrc, int k, int dil, bool in_bf16, TcPlan* p, int 
 // so the k rows fed by one input row (ro, ro - dil, ...) occupy ascending consecutive slots.
 // dsh = log2(dil), dil in {1, 2}: shifts and masks only (a runtime integer division costs ~100 cycles on the
 // single thread that paces the tensor pipe).
+#ifdef PAIF_TC_OLD_DESC      // A/B build: descriptors as (template | start address) with the plan fields read where they are used
+#define desc_pack(lo, hi) (((uint64_t)(hi) << 32) | (uint64_t)(uint32_t)(lo))
+#endif
 __device__ __forceinline__ int tc_slot(int ro, int dsh) {
     const int spr = TC_SLOTS >> dsh;                 // slots per residue class ring
     return (ro & ((1 << dsh) - 1)) * spr + (spr - 1 - ((ro >> dsh) & (spr - 1)));
@@ -105,13 +108,16 @@ __device__ __forceinline__ int tc_slot(int ro, int dsh) {
 #ifdef PAIF_TC_PROFILE
 // development-only role timeline: wait / busy cycles summed over all CTAs (read with paif_debug_tc_counters)
 __device__ unsigned long long tc_prof[16];
-#define TC_PROF_DECL long long prof_wait = 0, prof_t0 = clock64()
+#define TC_PROF_DECL long long prof_wait = 0, prof_wait2 = 0, prof_t0 = clock64()
 #define TC_WAIT(stmt) do { const long long t_ = clock64(); stmt; prof_wait += clock64() - t_; } while (0)
+#define TC_WAIT2(stmt) do { const long long t_ = clock64(); stmt; prof_wait2 += clock64() - t_; } while (0)   /* issuer: accumulator slot */
 #define TC_PROF_END(slot) do { if ((threadIdx.x & 31) == 0) { atomicAdd(&tc_prof[(slot) * 2], (unsigned long long)prof_wait); \
-                                   atomicAdd(&tc_prof[(slot) * 2 + 1], (unsigned long long)(clock64() - prof_t0)); } } while (0)
+                                   atomicAdd(&tc_prof[(slot) * 2 + 1], (unsigned long long)(clock64() - prof_t0));            \
+                                   if (prof_wait2) atomicAdd(&tc_prof[8 + (slot)], (unsigned long long)prof_wait2); } } while (0)
 #else
 #define TC_PROF_DECL
 #define TC_WAIT(stmt) stmt
+#define TC_WAIT2(stmt) stmt
 #define TC_PROF_END(slot)
 #endif
 
@@ -208,7 +214,11 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
     unsigned char* s_ring = smem + P.slab_bytes;               // input ring
     TcBars* bars = reinterpret_cast<TcBars*>(s_ring + P.stages * P.stage_bytes);  // (P.unit_bytes == UNIT, set by the host)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // (warp-uniform for the compiler: the role branches and everything nested in them — the segment / pass / row loops
+    //  and their barrier waits — then need no divergence bookkeeping; with a plain tid >> 5 the row loop of the MMA
+    //  issuer carried BSSY / BSYNC pairs and BMOV spills of convergence barriers)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     constexpr int k = K, dil = DIL, pad = DIL * (K - 1) / 2;
     constexpr int dsh = DIL >> 1;                              // log2(dil), dil in {1, 2}
     constexpr int RW = TC_TW + 2 * pad;                        // halo'd row width in pixels
@@ -269,71 +279,85 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         const bool any_post = e.post_res[0] || e.post_res[1] || e.post_res[2];
         const bool any_pre = e.pre_res[0] || e.pre_res[1];
         const bool any_fetch = any_post || any_pre || e.mask_src;
-        // Residual and mask maps do not depend on the accumulator: for this thread's NEXT row the sum of the
-        // post-activation residuals (pn), the sum of the pre-activation residuals (qn) and the PReLU' mask
-        // (one bit per channel) are fetched while that row is still being accumulated, so global-load latency
-        // never sits between acc_full and the stores.
-        float4 pn[8], qn[8];
+        // Residual and mask maps do not depend on the accumulator: for this thread's NEXT row they are fetched while that
+        // row is still being accumulated, so global-load latency never sits between acc_full and the stores.
+        // All loads of a fetch are issued BEFORE the first instruction that depends on any of them: the first
+        // post-activation residual lands in pn, the first pre-activation residual — or, when the layer has none, the
+        // SECOND post-activation residual — in qn, a third map in temporaries that are summed into pn afterwards.
+        // (Summing map by map as the loads were issued serialised one DRAM latency per map: with three residual maps
+        // the epilogue paced the kernel, the MMA issuer waiting 70-80 % of its time for an accumulator slot.)
+        // bf16 maps (OUT_BF): the fetched rows stay PACKED (four 16-register slots: maps A, B, C and the rare D / E) and are
+        // unpacked plane pair by plane pair where they are used — unpacked sums next to the accumulators did not fit in
+        // the 168 registers a thread of this 10-warp CTA has.
+        float4 pn[OUT_BF ? 1 : 8], qn[OUT_BF ? 1 : 8];
+        uint4 sA[OUT_BF ? 4 : 1], sB[OUT_BF ? 4 : 1], sC[OUT_BF ? 4 : 1], sD[OUT_BF ? 4 : 1];
         uint32_t mbits = 0;
+        const float* mapA = e.post_res[0];
+        const float* mapB_ = any_pre ? e.pre_res[0] : e.post_res[1];
+        const float* mapC_ = any_pre ? e.post_res[1] : e.post_res[2];       // summed into pn
+        const float* mapD = any_pre ? e.post_res[2] : nullptr;             // (rare) summed into pn
+        const float* mapE = any_pre ? e.pre_res[1] : nullptr;              // (rare) summed into qn
+        // The epilogue's configuration as bits of ONE register, made opaque to the compiler: tested in the per-row code,
+        // every `if (e.mask_src)` / `if (any_pre)` ... otherwise re-reads its kernel parameter from the constant bank
+        // (LDCU -> ISETP -> BRA, ~30 such dependent triples per row inside the unrolled loops) — measured: the bf16
+        // 3x3 32->32 layer 0.223 -> 0.149 ms without them.
+        const float *mapB = mapB_, *mapC = mapC_;
+        asm volatile("" : "+l"(mapB), "+l"(mapC));            // (selected once, not per use)
+        uint32_t cfg = (mapA ? 1u : 0u) | (mapB ? 2u : 0u) | (mapC ? 4u : 0u) | (mapD ? 8u : 0u) | (mapE ? 16u : 0u) |
+                       (any_pre ? 32u : 0u) | (e.mask_src ? 64u : 0u) | (e.slope ? 128u : 0u) | (e.out_pre ? 256u : 0u) |
+                       (e.out_act2 ? 512u : 0u) | (any_fetch ? 1024u : 0u);
+        asm volatile("" : "+r"(cfg));
+        const bool fA = cfg & 1u, fB = cfg & 2u, fC = cfg & 4u, fD = cfg & 8u, fE = cfg & 16u, f_pre = cfg & 32u,
+                   f_mask = cfg & 64u, f_slope = cfg & 128u, f_outpre = cfg & 256u, f_act2 = cfg & 512u, f_fetch = cfg & 1024u;
         auto fetch_next = [&](int ro) {
             if constexpr (OUT_BF) {
                 const size_t base = (size_t)b * 4 * plane + (size_t)(r0 + ro) * g.W + x;     // 16-byte units, plane 0
-                auto add_map = [&](const float* m, float4 (&acc)[8]) {
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                const float* mapX = fD ? mapD : mapE;                  // (the launcher rejects both at once)
 #pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) {
-                        float4 lo, hi;
-                        bf8_unpack(ld_stream_u4(reinterpret_cast<const uint4*>(m) + base + pl * plane), lo, hi);
-                        acc[2 * pl] = f4_add(acc[2 * pl], lo);
-                        acc[2 * pl + 1] = f4_add(acc[2 * pl + 1], hi);
-                    }
-                };
-                if (any_post) {
+                for (int pl = 0; pl < 4; ++pl) sA[pl] = fA ? ld_stream_u4(reinterpret_cast<const uint4*>(mapA) + base + pl * plane) : z4;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int pl = 0; pl < 4; ++pl) sB[pl] = fB ? ld_stream_u4(reinterpret_cast<const uint4*>(mapB) + base + pl * plane) : z4;
 #pragma unroll
-                    for (int kk = 0; kk < 3; ++kk)
-                        if (e.post_res[kk]) add_map(e.post_res[kk], pn);
-                }
-                if (any_pre) {
+                for (int pl = 0; pl < 4; ++pl) sC[pl] = fC ? ld_stream_u4(reinterpret_cast<const uint4*>(mapC) + base + pl * plane) : z4;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) qn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int pl = 0; pl < 4; ++pl) sD[pl] = (fD || fE) ? ld_stream_u4(reinterpret_cast<const uint4*>(mapX) + base + pl * plane) : z4;
+                if (f_mask) {
+                    uint4 rm[4];
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)
-                        if (e.pre_res[kk]) add_map(e.pre_res[kk], qn);
-                }
-                if (e.mask_src) {
+                    for (int pl = 0; pl < 4; ++pl) rm[pl] = ld_stream_u4(reinterpret_cast<const uint4*>(e.mask_src) + base + pl * plane);
                     uint32_t mb = 0;
 #pragma unroll
-                    for (int pl = 0; pl < 4; ++pl) {
-                        const uint4 m = ld_stream_u4(reinterpret_cast<const uint4*>(e.mask_src) + base + pl * plane);
-                        mb |= (bf2_pos_bits(m.x) | bf2_pos_bits(m.y) << 2 | bf2_pos_bits(m.z) << 4 | bf2_pos_bits(m.w) << 6) << (8 * pl);
-                    }
+                    for (int pl = 0; pl < 4; ++pl)
+                        mb |= (bf2_pos_bits(rm[pl].x) | bf2_pos_bits(rm[pl].y) << 2 | bf2_pos_bits(rm[pl].z) << 4 | bf2_pos_bits(rm[pl].w) << 6) << (8 * pl);
                     mbits = mb;
                 }
-                return;
-            }
+            } else {
             const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;
-            if (any_post) {
+            float4 tc[8];
+            if (fA) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pn[q] = ld_stream(reinterpret_cast<const float4*>(mapA) + base + q * plane);
+            } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) pn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-                    if (e.post_res[kk]) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) pn[q] = f4_add(pn[q], ld_stream(reinterpret_cast<const float4*>(e.post_res[kk]) + base + q * plane));
-                    }
             }
-            if (any_pre) {
+            if (fB) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) qn[q] = ld_stream(reinterpret_cast<const float4*>(mapB) + base + q * plane);
+            } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) qn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk)
-                    if (e.pre_res[kk]) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) qn[q] = f4_add(qn[q], ld_stream(reinterpret_cast<const float4*>(e.pre_res[kk]) + base + q * plane));
-                    }
             }
-            if (e.mask_src) {
+            if (fC) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) tc[q] = ld_stream(reinterpret_cast<const float4*>(mapC) + base + q * plane);
+            }
+            if (fC) {                   // (a third map and a mask source do not occur together: they share registers)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pn[q] = f4_add(pn[q], tc[q]);
+            }
+            if (f_mask) {
                 uint32_t mb = 0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -343,10 +367,21 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                 }
                 mbits = mb;
             }
+            if (fD) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pn[q] = f4_add(pn[q], ld_stream(reinterpret_cast<const float4*>(mapD) + base + q * plane));
+            }
+            if (fE) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) qn[q] = f4_add(qn[q], ld_stream(reinterpret_cast<const float4*>(mapE) + base + q * plane));
+            }
+            }
         };
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { pn[q] = make_float4(0.f, 0.f, 0.f, 0.f); qn[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
-        if (any_fetch && xin && grp < nrows) fetch_next(grp);
+        for (int q = 0; q < (OUT_BF ? 1 : 8); ++q) { pn[q] = make_float4(0.f, 0.f, 0.f, 0.f); qn[q] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int pl = 0; pl < (OUT_BF ? 4 : 1); ++pl) sA[pl] = sB[pl] = sC[pl] = sD[pl] = make_uint4(0u, 0u, 0u, 0u);
+        if (f_fetch && xin && grp < nrows) fetch_next(grp);
         if (grp == 0 && seg == 0) {
             // accumulators start from zero: every MMA accumulates (the TMEM allocation holds garbage)
             for (int sl = 0; sl < TC_SLOTS; ++sl) {
@@ -369,7 +404,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                 mbar_arrive(smem_u32(&bars->acc_empty[slot]));
                 if (xin) {
                     const size_t pi = (size_t)b * plane + (size_t)(r0 + ro) * g.W + x;
-                    if (e.out_pre) e.out_pre[pi] = acc;
+                    if (f_outpre) e.out_pre[pi] = acc;
                     e.out[pi] = tanhf(prelu_f(acc, a));
                 }
                 continue;
@@ -379,11 +414,22 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             tmem_zero32(tmem_base + ((uint32_t)(wq * 32) << 16) + slot * 32);
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->acc_empty[slot]));
-            if (OUT_BF && xin) {
+            if constexpr (OUT_BF) if (xin) {
                 const size_t base = (size_t)b * 4 * plane + (size_t)(r0 + ro) * g.W + x;     // 16-byte units, plane 0
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl) {
                     float tp[8];
+                    // post- (P) and pre-activation (Q) residual sums of this plane's 8 channels from the packed slots
+                    float4 P[2], Q[2];
+                    P[0] = P[1] = Q[0] = Q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifndef PAIF_TC_TEST_NOPQ
+                    if (fA) bf8_unpack(sA[pl], P[0], P[1]);
+                    if (f_pre) bf8_unpack(sB[pl], Q[0], Q[1]);
+                    else if (fB) { float4 lo, hi; bf8_unpack(sB[pl], lo, hi); P[0] = f4_add(P[0], lo); P[1] = f4_add(P[1], hi); }
+                    if (fC) { float4 lo, hi; bf8_unpack(sC[pl], lo, hi); P[0] = f4_add(P[0], lo); P[1] = f4_add(P[1], hi); }
+                    if (fD) { float4 lo, hi; bf8_unpack(sD[pl], lo, hi); P[0] = f4_add(P[0], lo); P[1] = f4_add(P[1], hi); }
+                    else if (fE) { float4 lo, hi; bf8_unpack(sD[pl], lo, hi); Q[0] = f4_add(Q[0], lo); Q[1] = f4_add(Q[1], hi); }
+#endif
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int q = 2 * pl + h;
@@ -391,31 +437,30 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                         const float4 sh = *reinterpret_cast<const float4*>(&bars->ch_shift[q * 4]);
                         float t[4] = {fmaf(v[q * 4 + 0], sc.x, sh.x), fmaf(v[q * 4 + 1], sc.y, sh.y),
                                       fmaf(v[q * 4 + 2], sc.z, sh.z), fmaf(v[q * 4 + 3], sc.w, sh.w)};
-                        t[0] += qn[q].x; t[1] += qn[q].y; t[2] += qn[q].z; t[3] += qn[q].w;
+                        if (f_pre) { t[0] += Q[h].x; t[1] += Q[h].y; t[2] += Q[h].z; t[3] += Q[h].w; }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) tp[h * 4 + j] = t[j];
-                        if (e.mask_src) {
+                        if (f_mask) {
                             const uint32_t mq = mbits >> (4 * q);
                             t[0] *= (mq & 1u) ? 1.f : ma; t[1] *= (mq & 2u) ? 1.f : ma;
                             t[2] *= (mq & 4u) ? 1.f : ma; t[3] *= (mq & 8u) ? 1.f : ma;
-                        } else if (e.slope) {
+                        } else if (f_slope) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) t[j] = prelu_f(t[j], a);
                         }
-                        v[q * 4 + 0] = fmaf(t[0], e.post_scale, pn[q].x); v[q * 4 + 1] = fmaf(t[1], e.post_scale, pn[q].y);
-                        v[q * 4 + 2] = fmaf(t[2], e.post_scale, pn[q].z); v[q * 4 + 3] = fmaf(t[3], e.post_scale, pn[q].w);
+                        v[q * 4 + 0] = fmaf(t[0], e.post_scale, P[h].x); v[q * 4 + 1] = fmaf(t[1], e.post_scale, P[h].y);
+                        v[q * 4 + 2] = fmaf(t[2], e.post_scale, P[h].z); v[q * 4 + 3] = fmaf(t[3], e.post_scale, P[h].w);
                     }
-                    if (e.out_pre)
+                    if (f_outpre)
                         reinterpret_cast<uint4*>(e.out_pre)[base + pl * plane] =
                             bf8_pack(make_float4(tp[0], tp[1], tp[2], tp[3]), make_float4(tp[4], tp[5], tp[6], tp[7]));
                 }
-                if (any_fetch && ro + 2 < nrows) fetch_next(ro + 2);      // in flight during the next row's MMAs
 #pragma unroll
                 for (int pl = 0; pl < 4; ++pl) {
                     const float* w8 = &v[pl * 8];
                     reinterpret_cast<uint4*>(e.out)[base + pl * plane] =
                         bf8_pack(make_float4(w8[0], w8[1], w8[2], w8[3]), make_float4(w8[4], w8[5], w8[6], w8[7]));
-                    if (e.out_act2)
+                    if (f_act2)
                         reinterpret_cast<uint4*>(e.out_act2)[base + pl * plane] =
                             bf8_pack(make_float4(prelu_f(w8[0], a2), prelu_f(w8[1], a2), prelu_f(w8[2], a2), prelu_f(w8[3], a2)),
                                      make_float4(prelu_f(w8[4], a2), prelu_f(w8[5], a2), prelu_f(w8[6], a2), prelu_f(w8[7], a2)));
@@ -424,8 +469,9 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) csum[c] += v[c];
                 }
+                if (f_fetch && ro + 2 < nrows) fetch_next(ro + 2);      // in flight during the next row's MMAs
             }
-            if (!OUT_BF && xin) {
+            if constexpr (!OUT_BF) if (xin) {
                 const size_t base = (size_t)b * 8 * plane + (size_t)(r0 + ro) * g.W + x;     // float4 units, quad 0
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -434,25 +480,25 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                     const float4 sh = *reinterpret_cast<const float4*>(&bars->ch_shift[q * 4]);
                     float t[4] = {fmaf(v[q * 4 + 0], sc.x, sh.x), fmaf(v[q * 4 + 1], sc.y, sh.y),
                                   fmaf(v[q * 4 + 2], sc.z, sh.z), fmaf(v[q * 4 + 3], sc.w, sh.w)};
-                    t[0] += qn[q].x; t[1] += qn[q].y; t[2] += qn[q].z; t[3] += qn[q].w;
-                    if (e.out_pre) reinterpret_cast<float4*>(e.out_pre)[off] = make_float4(t[0], t[1], t[2], t[3]);
-                    if (e.mask_src) {
+                    if (f_pre) { t[0] += qn[q].x; t[1] += qn[q].y; t[2] += qn[q].z; t[3] += qn[q].w; }
+                    if (f_outpre) reinterpret_cast<float4*>(e.out_pre)[off] = make_float4(t[0], t[1], t[2], t[3]);
+                    if (f_mask) {
                         const uint32_t mq = mbits >> (4 * q);
                         t[0] *= (mq & 1u) ? 1.f : ma; t[1] *= (mq & 2u) ? 1.f : ma;
                         t[2] *= (mq & 4u) ? 1.f : ma; t[3] *= (mq & 8u) ? 1.f : ma;
-                    } else if (e.slope) {
+                    } else if (f_slope) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) t[j] = prelu_f(t[j], a);
                     }
                     v[q * 4 + 0] = fmaf(t[0], e.post_scale, pn[q].x); v[q * 4 + 1] = fmaf(t[1], e.post_scale, pn[q].y);
                     v[q * 4 + 2] = fmaf(t[2], e.post_scale, pn[q].z); v[q * 4 + 3] = fmaf(t[3], e.post_scale, pn[q].w);
+                    if (!f_pre) { v[q * 4 + 0] += qn[q].x; v[q * 4 + 1] += qn[q].y; v[q * 4 + 2] += qn[q].z; v[q * 4 + 3] += qn[q].w; }
                 }
-                if (any_fetch && ro + 2 < nrows) fetch_next(ro + 2);      // in flight during the next row's MMAs
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const size_t off = base + q * plane;
                     reinterpret_cast<float4*>(e.out)[off] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                    if (e.out_act2)
+                    if (f_act2)
                         reinterpret_cast<float4*>(e.out_act2)[off] =
                             make_float4(prelu_f(v[q * 4 + 0], a2), prelu_f(v[q * 4 + 1], a2), prelu_f(v[q * 4 + 2], a2), prelu_f(v[q * 4 + 3], a2));
                 }
@@ -460,6 +506,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) csum[c] += v[c];
                 }
+                if (f_fetch && ro + 2 < nrows) fetch_next(ro + 2);      // in flight during the next row's MMAs
             }
         }
         TC_PROF_END(0);
@@ -494,14 +541,26 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
             const uint32_t w_base = smem_u32(s_w), ring_base = smem_u32(s_ring);
             const uint64_t a_desc0 = make_desc(0, plane_bytes, 128);
             const uint64_t b_desc0 = make_desc(0, (uint32_t)k * CP * 16, 128);   // 16-B k-chunks are k*CP rows apart
+            // descriptor words: the start-address field (14 bits, 16-byte units) never carries into the LBO field, so a
+            // descriptor is (high word, low-word base + row offset + compile-time tap offset): one add per MMA operand
+            const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
             constexpr int nk8 = KQ / 2;
             constexpr int spr = TC_SLOTS >> dsh;
+            // plan fields used per row: pinned in registers (the compiler otherwise re-reads them from the constant bank
+            // on the issuing thread's critical path)
+            int p_upr = P.upr, p_stages = P.stages, p_gpp = P.gpp, p_npass = P.npass;
+            uint32_t p_stage16 = (uint32_t)P.stage_bytes >> 4;
+#ifndef PAIF_TC_OLD_DESC
+            asm volatile("" : "+r"(p_upr), "+r"(p_stages), "+r"(p_gpp), "+r"(p_npass), "+r"(p_stage16));
+#endif
+            const uint32_t ring16 = ring_base >> 4, w16 = w_base >> 4;
             TC_PROF_DECL;
             if (seg == 0) {
                 TC_WAIT(mbar_wait(smem_u32(&bars->zeroed), 0));
                 tc_fence_after();
             }
-            for (int pass = 0; pass < P.npass; ++pass) {
+            for (int pass = 0; pass < p_npass; ++pass) {
                 if (seg == 0) {                                  // (persistent launches are single-pass: the slab stays)
                     TC_WAIT(mbar_wait(smem_u32(&bars->wfull), pass & 1));
                     tc_fence_after();
@@ -520,17 +579,17 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                         s1 = (ro_top & (dil - 1)) * spr;                       // start of this residue class's slot ring
                         n1 = min(ndy, s1 + spr - s0);                          // taps before the ring wraps
                     }
-                    for (int gl = 0; gl < P.gpp; ++gl) {
+                    for (int gl = 0; gl < p_gpp; ++gl) {
                         if (pass == 0 && gl == 0 && ri < nrows) {
                             // output row ri starts accumulating now: its TMEM slot must have been drained and zeroed
                             const int use = ri / TC_SLOTS;
                             if (use > 0) {
-                                TC_WAIT(mbar_wait(smem_u32(&bars->acc_empty[tc_slot(ri, dsh)]), (use - 1) & 1));
+                                TC_WAIT2(mbar_wait(smem_u32(&bars->acc_empty[tc_slot(ri, dsh)]), (use - 1) & 1));
                                 tc_fence_after();
                             }
                         }
                         if (yok) {
-                            const int us = P.upr == 1 ? 0 : gl;                 // unit inside the ring stage
+                            const int us = p_upr == 1 ? 0 : gl;                 // unit inside the ring stage
                             if (us == 0) {
                                 TC_WAIT(mbar_wait(smem_u32(&bars->full[stage]), phase));
                                 tc_fence_after();
@@ -538,16 +597,16 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                             if (ndy > 0 && elect_one()) {
                                 // descriptors differ only in the 14-bit start-address field (units of 16 B); the
                                 // per-(dx, k8) offsets below are immediates after unrolling
-                                const uint32_t a_lo = (ring_base + stage * P.stage_bytes + us * UNIT) >> 4;
-                                const uint32_t w_lo = ((w_base + (uint32_t)gl * (k * nk8 * k * CP * 32)) >> 4) + dy_lo * CP;
+                                const uint32_t a_lo = a_lo0 + ring16 + (uint32_t)stage * p_stage16 + (uint32_t)us * (UNIT >> 4);
+                                const uint32_t w_lo = b_lo0 + w16 + (uint32_t)gl * (k * nk8 * k * CP * 2) + dy_lo * CP;
                                 const uint32_t d0 = tmem_base + s0 * CP;
                                 const uint32_t id0 = tc_idesc((uint32_t)CP * n1, IN_BF ? 1u : 2u);
 #pragma unroll
                                 for (int dx = 0; dx < k; ++dx)
 #pragma unroll
                                     for (int k8 = 0; k8 < nk8; ++k8) {
-                                        const uint64_t ad = a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW);
-                                        const uint64_t bd = b_desc0 | (uint64_t)(w_lo + (dx * nk8 + k8) * k * 2 * CP);
+                                        const uint64_t ad = desc_pack(a_lo + (dx * dil + k8 * 2 * RW), a_hi);
+                                        const uint64_t bd = desc_pack(w_lo + ((dx * nk8 + k8) * k * 2 * CP), b_hi);
                                         if constexpr (IN_BF) tc_mma_bf16(d0, ad, bd, id0, 1u);
                                         else tc_mma_tf32(d0, ad, bd, id0, 1u);
                                     }
@@ -559,26 +618,26 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
                                     for (int dx = 0; dx < k; ++dx)
 #pragma unroll
                                         for (int k8 = 0; k8 < nk8; ++k8) {
-                                            const uint64_t ad = a_desc0 | (uint64_t)(a_lo + dx * dil + k8 * 2 * RW);
-                                            const uint64_t bd = b_desc0 | (uint64_t)(w_l1 + (dx * nk8 + k8) * k * 2 * CP);
+                                            const uint64_t ad = desc_pack(a_lo + (dx * dil + k8 * 2 * RW), a_hi);
+                                            const uint64_t bd = desc_pack(w_l1 + ((dx * nk8 + k8) * k * 2 * CP), b_hi);
                                             if constexpr (IN_BF) tc_mma_bf16(d1, ad, bd, id1, 1u);
                                             else tc_mma_tf32(d1, ad, bd, id1, 1u);
                                         }
                                 }
                             }
                             __syncwarp();
-                            if (us == P.upr - 1) {
+                            if (us == p_upr - 1) {
                                 if (elect_one()) tc_commit(smem_u32(&bars->empty[stage]));   // stage reusable once these MMAs retire
-                                if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                                if (++stage == p_stages) { stage = 0; phase ^= 1u; }
                             }
                         }
-                        if (pass == P.npass - 1 && gl == P.gpp - 1) {
+                        if (pass == p_npass - 1 && gl == p_gpp - 1) {
                             const int rdone = ri - (k - 1) * dil;           // output row whose last tap row just passed
                             if (rdone >= 0 && rdone < nrows && elect_one()) tc_commit(smem_u32(&bars->acc_full[tc_slot(rdone, dsh)]));
                         }
                     }
                 }
-                if (pass + 1 < P.npass && elect_one()) tc_commit(smem_u32(&bars->wempty));  // weights of this pass no longer read
+                if (pass + 1 < p_npass && elect_one()) tc_commit(smem_u32(&bars->wempty));  // weights of this pass no longer read
             }
             TC_PROF_END(1);
         }
@@ -840,6 +899,11 @@ int conv_tc_tiles(int H, int W) {
 int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     TcGeom g;
     if (!tc_make_plan(d.nsrc, d.kh, d.dil, d.storage == PAIF_STORAGE_BF16, &g.plan)) { set_error("conv_tc: no plan"); return PAIF_ENOTSUP; }
+    if (d.storage != PAIF_STORAGE_F32 && (d.pre_res[0] || d.pre_res[1]) && d.post_res[2] && d.pre_res[1]) {
+        // the bf16 epilogue keeps the fetched residual rows packed in four register slots
+        set_error("conv_tc: bf16 storage takes at most 4 residual maps (3 post + 2 pre given)");
+        return PAIF_ENOTSUP;
+    }
     g.B = d.B; g.H = d.H; g.W = d.W; g.nsrc = d.nsrc; g.k = d.kh; g.dil = d.dil;
     g.RCH = tc_rows_per_cta(d, g.plan);
     g.tiles_alloc = conv_tc_tiles(d.H, d.W);

@@ -1280,8 +1280,8 @@ class _FusionFn(torch.autograd.Function):
                 outs.append(None)
             elif k == 1 and ctx.vis_rgb:
                 # Y = .299 R + .587 G + .114 B: the Y gradient spread over the three colour planes
-                coef = torch.tensor([0.299, 0.587, 0.114], device=gi.device, dtype=gi.dtype).view(1, 3, 1, 1)
-                outs.append(gi.unsqueeze(1) * coef)
+                # (no host tensor here: this runs inside CUDA-graph capture of the PGD iteration)
+                outs.append(torch.stack((gi * 0.299, gi * 0.587, gi * 0.114), dim=1))
             elif shape[1] == 1:
                 outs.append(gi.view(shape))
             else:

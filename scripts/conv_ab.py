@@ -24,6 +24,8 @@ cases = [("k3 cin32 prelu            (2 maps)", 1, 3, 1, dict(slope=a), 2),
          ("k3 cin96 +3 res           (7 maps)", 3, 3, 1, dict(post_scale=0.333, post_res=maps[3:6]), 7),
          ("k3d2 cin32 3res (DilConv) (5 maps)", 1, 3, 2, dict(post_res=maps[3:6]), 5),
          ("k3d2 cin32 prelu 2res     (4 maps)", 1, 3, 2, dict(slope=a, post_res=maps[3:5]), 4),
+         ("k3d2 cin32 no res         (2 maps)", 1, 3, 2, dict(slope=a), 2),
+         ("k3 cin32 mask + 2res bwd  (5 maps)", 1, 3, 1, dict(mask_src=maps[5], mask_slope=a, post_res=maps[3:5]), 5),
          ("k7 cin32 prelu            (2 maps)", 1, 7, 1, dict(slope=a), 2),
          ("k3 cin32 +res             (3 maps)", 1, 3, 1, dict(post_res=maps[3:4]), 3)]
 
@@ -48,7 +50,6 @@ for name, nsrc, k, dil, kw, nmaps in cases:
     for mode in (0, 1):
         lib.paif_conv_set_persistent(mode)
         res[mode] = timeit(lambda: rt.conv(maps[:nsrc], cw, **kw))
-        rt.reset() if hasattr(rt, "reset") else None
     gbs = nmaps * MAP / 1e9
     print("%-38s tiled %.3f ms (%4.0f GB/s)   persistent %.3f ms (%4.0f GB/s)  %+.1f%%" % (
         name, res[0], gbs / res[0] * 1e3, res[1], gbs / res[1] * 1e3, 100 * (res[1] / res[0] - 1)), flush=True)

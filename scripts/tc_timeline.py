@@ -36,11 +36,10 @@ for name, nsrc, k, dil, kw in cases:
     torch.cuda.synchronize()
     c = counters()
     ms = e0.elapsed_time(e1)
-    ctas = 5 * B * ((H + 31) // 32 if k != 7 else (H + 15) // 16)
-    def f(i, nw):   # per warp averages
+    def f(i):   # wait share of the role's life (summed over CTAs / segments)
         return c[2 * i] / max(c[2 * i + 1], 1)
-    print("%-30s %.3f ms | epilogue warps: wait %.0f%% of %.0f kcyc | mma warps: wait %.0f%% of %.0f kcyc | producer: wait %.0f%% of %.0f kcyc" % (
-        name, ms, 100 * f(0, 8), c[1] / (8 * ctas) / 1e3, 100 * f(1, 4), c[3] / (4 * ctas) / 1e3, 100 * f(2, 1), c[5] / ctas / 1e3), flush=True)
+    print("%-30s %.3f ms | epilogue: wait %.0f%% | issuer: waits for input %.0f%%, for an accumulator slot %.0f%% | producer: wait %.0f%%" % (
+        name, ms, 100 * f(0), 100 * f(1), 100 * c[9] / max(c[3], 1), 100 * f(2)), flush=True)
 
 # stem_out on the engine (single-output mode)
 import paif_b200
