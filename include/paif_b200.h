@@ -178,7 +178,8 @@ int paif_conv_tc_kq_bf16(int nsrc, int k, int dil);
 /* Launch shape of the tcgen05 engine.  1 (default): persistent — one CTA per SM, each owning an equal contiguous share of
  * the launch's B * strips * H output rows (no partial last wave, one prologue per SM); 0: one CTA per (strip, row chunk,
  * image) tile.  Results are bit-identical in both shapes; launches that produce chan_partials are always tiled (their
- * sums are per fixed tile).  Returns the previous setting.  A diagnostic / A-B switch, not part of the reference's API. */
+ * sums are per fixed tile), and so is the one shape measured faster tiled (fp32 3x3 32->32 with a plain epilogue) unless
+ * on == 2.  Returns the previous setting.  A diagnostic / A-B switch, not part of the reference's API. */
 int paif_conv_set_persistent(int on);
 /* number of per-image tiles the chosen engine writes into chan_partials ([B][tiles][cout]) */
 int paif_conv_num_tiles(int H, int W, int engine);
