@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PAIF_ABI_VERSION 3   /* 3: paif_gf_mix_forward, glue / PGD / loss-head kernels, paif_stem_forward_rgb, paif_widen_bf16_map */
+#define PAIF_ABI_VERSION 4   /* 4: paif_fusion_forward_save / paif_fusion_backward_input, paif_conv_set_persistent; 3: paif_gf_mix_forward, glue / PGD / loss-head kernels, paif_stem_forward_rgb, paif_widen_bf16_map */
 
 #define PAIF_EINVAL   (-1)   /* bad argument (null pointer, unsupported size) */
 #define PAIF_ENOTSUP  (-2)   /* configuration not supported by this build     */
@@ -360,6 +360,32 @@ typedef struct PaifFusionWeights {
     const float* out_a;
 } PaifFusionWeights;
 long long paif_fusion_workspace_bytes(int B, int H, int W, int storage);
+
+/* The PGD inner step (attack/attack.py:444-501: forward, loss, backward to the INPUTS) of the same genotype as two calls
+ * over one caller-owned workspace, fp32 storage: paif_fusion_forward_save leaves the activations the backward needs at
+ * fixed offsets of the workspace (~17 maps of B*H*W*128 bytes), paif_fusion_backward_input turns d loss / d out
+ * (gout: [B][1][H][W]) into d loss / d ir and d loss / d vis (contiguous [B][H][W] planes; weight gradients are not
+ * produced — nothing in the reference reads them).  Same kernels in the same order as the autograd node of
+ * paif_b200/fusion.py, so the gradients are bit-identical to it.  grad_weights: the dgrad images of every convolution
+ * (weights flipped and transposed, one PaifFusionConv per group of 32 input channels; BatchNorm scales folded).
+ * workspace: >= paif_fusion_train_workspace_bytes(B, H, W) bytes, 256-byte aligned; it must be left untouched between
+ * the two calls. */
+typedef struct PaifFusionRDBGrad { PaifFusionConv c3[3]; PaifFusionConv c2[2]; PaifFusionConv c1; } PaifFusionRDBGrad;
+typedef struct PaifFusionGradWeights {
+    PaifFusionRDBGrad rdb[3];            /* same order as PaifFusionWeights.rdb                                  */
+    PaifFusionConv dil_dense_d;          /* DilConv's dense form (BatchNorm scale folded)                        */
+    PaifFusionConv eca_conv1_d, eca_conv2_d;
+    PaifFusionConv res_conv7_d, res_merged_d;
+    PaifFusionConv c1x1_d[2][3];         /* folded decomposition 1x1 (lf / hf): groups LF_1e-3, LF_1e-4, z       */
+} PaifFusionGradWeights;
+long long paif_fusion_train_workspace_bytes(int B, int H, int W);
+int paif_fusion_forward_save(const PaifFusionWeights* weights,
+                             const float* ir, long long ir_stride_b, long long ir_stride_y, long long ir_stride_x,
+                             const float* vis, long long vis_stride_b, long long vis_stride_y, long long vis_stride_x,
+                             float* out, void* workspace, long long workspace_bytes, int B, int H, int W, void* stream);
+int paif_fusion_backward_input(const PaifFusionWeights* weights, const PaifFusionGradWeights* grad_weights,
+                               const float* gout, float* g_ir, float* g_vis,
+                               void* workspace, long long workspace_bytes, int B, int H, int W, void* stream);
 int paif_fusion_forward(const PaifFusionWeights* weights,
                         const float* ir, long long ir_stride_b, long long ir_stride_y, long long ir_stride_x,
                         const float* vis, long long vis_stride_b, long long vis_stride_y, long long vis_stride_x,

@@ -11,7 +11,7 @@ from . import build as _build
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpaif_b200.so")
 
-ABI_VERSION = 3                                             # PAIF_ABI_VERSION of include/paif_b200.h
+ABI_VERSION = 4                                             # PAIF_ABI_VERSION of include/paif_b200.h
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 STORAGE_F32, STORAGE_BF16, STORAGE_F32_BF16 = 0, 1, 2      # PaifConvDesc.storage
 
@@ -64,6 +64,21 @@ class FusionWeights(C.Structure):
     ]
 
 
+class FusionRDBGrad(C.Structure):
+    """Mirror of ``PaifFusionRDBGrad``."""
+    _fields_ = [("c3", FusionConv * 3), ("c2", FusionConv * 2), ("c1", FusionConv)]
+
+
+class FusionGradWeights(C.Structure):
+    """Mirror of ``PaifFusionGradWeights`` (include/paif_b200.h)."""
+    _fields_ = [
+        ("rdb", FusionRDBGrad * 3),
+        ("dil_dense_d", FusionConv), ("eca_conv1_d", FusionConv), ("eca_conv2_d", FusionConv),
+        ("res_conv7_d", FusionConv), ("res_merged_d", FusionConv),
+        ("c1x1_d", (FusionConv * 3) * 2),
+    ]
+
+
 # name -> argtypes (restype is int unless noted); must list EVERY symbol of the header.
 SIGNATURES = {
     "paif_abi_version": [],
@@ -111,6 +126,9 @@ SIGNATURES = {
     "paif_pgd_step": [_f, _f, _f, C.c_float, C.c_float, _ll, _f],
     "paif_fusion_workspace_bytes": [_i, _i, _i, _i],
     "paif_fusion_forward": [C.POINTER(FusionWeights), _f, _ll, _ll, _ll, _f, _ll, _ll, _ll, _f, _f, _ll, _i, _i, _i, _i, _f],
+    "paif_fusion_train_workspace_bytes": [_i, _i, _i],
+    "paif_fusion_forward_save": [C.POINTER(FusionWeights), _f, _ll, _ll, _ll, _f, _ll, _ll, _ll, _f, _f, _ll, _i, _i, _i, _f],
+    "paif_fusion_backward_input": [C.POINTER(FusionWeights), C.POINTER(FusionGradWeights), _f, _f, _f, _f, _ll, _i, _i, _i, _f],
     "paif_widen_bf16_map": [_f, _f, _i, _i, _i, _i, _f],
     "paif_segloss_forward": [_f, _f, _f, _f, _ll, C.c_float, _i, _i, _i, _i, _i, _i, _f],
     "paif_segloss_backward": [_f, _f, _f, _i, _i, _i, _i, _i, _i, _f],
@@ -145,7 +163,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch
         fn.argtypes = argtypes
         fn.restype = (C.c_char_p if name == "paif_last_error_string" else
-                      _ll if name in ("paif_gf_backward_work_floats", "paif_fusion_workspace_bytes") else _i)
+                      _ll if name in ("paif_gf_backward_work_floats", "paif_fusion_workspace_bytes",
+                                  "paif_fusion_train_workspace_bytes") else _i)
     if lib.paif_abi_version() != ABI_VERSION:
         raise PaifError("libpaif_b200.so ABI version mismatch")
     _lib = lib

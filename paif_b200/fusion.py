@@ -934,6 +934,71 @@ class Network_Fusion_Searched(nn.Module):
         p["native"] = w
         return w
 
+    def _native_grad_weights(self, p):
+        """``PaifFusionGradWeights`` over the dgrad packs of ``p`` (a backward-capable pack of the shipped genotype)."""
+        if "native_grad" in p:
+            return p["native_grad"]
+        g = _lib.FusionGradWeights()
+
+        def cv(dst, cw):
+            dst.direct, dst.mma_tf32, dst.mma_bf16 = _ptr(cw.direct), _ptr(cw.mma), _ptr(cw.mma16)
+
+        for i, pk in enumerate((p["chain_ir"][0], p["chain_vis"][0], p["chain_vis"][1])):
+            wd = pk["wd"]
+            for j in range(3):
+                cv(g.rdb[i].c3[j], wd[2][j])
+            for j in range(2):
+                cv(g.rdb[i].c2[j], wd[1][j])
+            cv(g.rdb[i].c1, wd[0][0])
+        cv(g.dil_dense_d, p["chain_ir"][1]["wdense_d"])
+        eca, res = p["chain"]
+        cv(g.eca_conv1_d, eca["w1_d"])
+        cv(g.eca_conv2_d, eca["w2_d"])
+        cv(g.res_conv7_d, res["w0_d"])
+        cv(g.res_merged_d, res["wm_d"])
+        for i in range(2):
+            for j in range(3):
+                cv(g.c1x1_d[i][j], p["c1x1_d"][i][j])
+        p["native_grad"] = g
+        return g
+
+    def _run_forward_native_save(self, ir, vis):
+        """Forward that keeps its activations for ``paif_fusion_backward_input`` as ONE C-ABI call
+        (``paif_fusion_forward_save``) over one workspace tensor; None when the configuration is outside what the
+        whole-network entry points implement (the per-operator path with saved tensors runs instead)."""
+        if not (self.native_forward and self.conv_engine in ('auto', 'tcgen05') and self.gf_fused and self.dilconv_dense
+                and self.out_tensor_core and self.profile is None and self.storage == 'fp32'):
+            return None
+        B, _, H, W = ir.shape
+        lib = _lib.load()
+        if not lib.paif_gf_mix_supported(self._C, H, W):
+            return None
+        p = self._packed(True)
+        w = self._native_weights(p)
+        if w is None:
+            return None
+        gw = self._native_grad_weights(p)
+        need = lib.paif_fusion_train_workspace_bytes(B, H, W)
+        ws = torch.empty((need,), device=ir.device, dtype=torch.uint8)
+        out = torch.empty((B, 1, H, W), device=ir.device, dtype=torch.float32)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(ir.device).cuda_stream)
+        _lib.call("paif_fusion_forward_save", ctypes.byref(w), ir.data_ptr(), ir.stride(0), ir.stride(2), ir.stride(3),
+                  vis.data_ptr(), vis.stride(0), vis.stride(2), vis.stride(3), out.data_ptr(), ws.data_ptr(), need,
+                  B, H, W, stream)
+        self.last_launches = 28
+        return out, dict(B=B, H=H, W=W, native_ws=ws, native_w=w, native_gw=gw, packed=p, out=out)
+
+    def _run_backward_native(self, saved, g):
+        B, H, W = saved["B"], saved["H"], saved["W"]
+        ws = saved["native_ws"]
+        g_ir = torch.empty((B, H, W), device=g.device, dtype=torch.float32)
+        g_vis = torch.empty((B, H, W), device=g.device, dtype=torch.float32)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+        _lib.call("paif_fusion_backward_input", ctypes.byref(saved["native_w"]), ctypes.byref(saved["native_gw"]),
+                  g.data_ptr(), g_ir.data_ptr(), g_vis.data_ptr(), ws.data_ptr(), ws.numel(), B, H, W, stream)
+        self.last_launches = 28 + 47
+        return g_ir, g_vis
+
     def _run_forward_native(self, ir, vis):
         """The whole forward as ONE C-ABI call (``paif_fusion_forward``) over one workspace tensor; None when the
         configuration is outside what that entry point implements (the per-operator path runs instead)."""
@@ -1246,6 +1311,10 @@ class _FusionFn(torch.autograd.Function):
         out = None
         if not need and not vis_rgb:
             out, saved = net._run_forward_native(ir[:, 0:1], vis[:, 0:1]), None
+        elif need and not vis_rgb:
+            res = net._run_forward_native_save(ir[:, 0:1], vis[:, 0:1])
+            if res is not None:
+                out, saved = res
         if out is None:
             out, saved = net._run_forward(ir[:, 0:1], vis if vis_rgb else vis[:, 0:1], need, vis_rgb=vis_rgb)
         ctx.vis_rgb = vis_rgb
@@ -1271,7 +1340,10 @@ class _FusionFn(torch.autograd.Function):
         g = g.contiguous().float()
         (out,) = ctx.saved_tensors
         with torch.cuda.device(g.device):
-            g_ir, g_vis = net._run_backward(dict(saved, out=out), g)
+            if "native_ws" in saved:
+                g_ir, g_vis = net._run_backward_native(saved, g)      # (tanh's output lives inside the workspace)
+            else:
+                g_ir, g_vis = net._run_backward(dict(saved, out=out), g)
         ctx.saved = None
         outs = []
         for k, (gi, shape, need) in enumerate(((g_ir, ctx.shapes[0], ctx.needs_input_grad[0]),

@@ -171,3 +171,54 @@ def test_whole_network_entry_point_is_bit_identical_to_the_per_operator_path(sto
                                  y.data_ptr(), y.stride(0), y.stride(2), y.stride(3), out.data_ptr(), ws.data_ptr(), need - 1,
                                  st, B, H, W, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc != 0 and b"workspace" in lib.paif_last_error_string()
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 56), (1, 96, 200), (3, 33, 132)])
+def test_whole_network_backward_entry_points_are_bit_identical_to_the_per_operator_path(shape):
+    """paif_fusion_forward_save + paif_fusion_backward_input (the PGD inner step as two C-ABI calls over one caller-owned
+    workspace) against the per-operator autograd node: same fused image and same input gradients, bit for bit.  Also
+    driven here straight through ctypes — pointers, sizes and a stream, no fusion._Runtime, no autograd."""
+    import ctypes
+    from paif_b200 import _lib
+    B, H, W = shape
+    g = load_golden("seed1_random_1x48x72")
+    net = build(g["state_dict"], "auto")
+    torch.manual_seed(6)
+    ir0, vis0 = torch.rand(B, 1, H, W).to(DEV), strided_vis(torch.rand(B, 3, H, W).to(DEV))
+    gout = (torch.rand(B, 1, H, W) - 0.5).to(DEV)
+    res = {}
+    for native in (False, True):
+        net.native_forward = native
+        a = ir0.clone().requires_grad_(True)
+        v = vis0.detach().requires_grad_(True)
+        out = net(a, v)
+        out.backward(gout)
+        res[native] = (out.detach().clone(), a.grad.clone(), v.grad.clone())
+    for x, y in zip(res[False], res[True]):
+        assert torch.equal(x, y)
+    assert res[True][1].abs().max().item() > 0
+    # plain ctypes
+    lib = _lib.load()
+    p = net._packed(True)
+    w, gw = net._native_weights(p), net._native_grad_weights(p)
+    need = lib.paif_fusion_train_workspace_bytes(B, H, W)
+    assert need > 0
+    ws = torch.empty(need, device=DEV, dtype=torch.uint8)
+    out = torch.empty(B, 1, H, W, device=DEV)
+    y = vis0[:, 0:1]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.paif_fusion_forward_save(ctypes.byref(w), ir0.data_ptr(), ir0.stride(0), ir0.stride(2), ir0.stride(3),
+                                      y.data_ptr(), y.stride(0), y.stride(2), y.stride(3), out.data_ptr(), ws.data_ptr(),
+                                      need, B, H, W, st)
+    assert rc == 0, lib.paif_last_error_string()
+    g_ir, g_vis = torch.empty(B, H, W, device=DEV), torch.empty(B, H, W, device=DEV)
+    out.zero_()                                   # the backward must not depend on the caller's copy of the output
+    rc = lib.paif_fusion_backward_input(ctypes.byref(w), ctypes.byref(gw), gout.data_ptr(), g_ir.data_ptr(),
+                                        g_vis.data_ptr(), ws.data_ptr(), need, B, H, W, st)
+    assert rc == 0, lib.paif_last_error_string()
+    torch.cuda.synchronize()
+    assert torch.equal(g_ir, res[False][1][:, 0])
+    assert torch.equal(g_vis, res[False][2][:, 0])
+    rc = lib.paif_fusion_backward_input(ctypes.byref(w), ctypes.byref(gw), gout.data_ptr(), g_ir.data_ptr(),
+                                        g_vis.data_ptr(), ws.data_ptr(), need - 1, B, H, W, st)
+    assert rc != 0 and b"workspace" in lib.paif_last_error_string()
