@@ -175,11 +175,11 @@ int paif_conv_tc_kq(int nsrc, int k, int dil);
 /* the same for PAIF_STORAGE_BF16: bf16 values, [K-group of KQ 8-channel planes][dx][KQ/2][2][dy][32 cout][8 cin];
  * KQ = 4 (a whole 32-channel source), 0 = not supported. */
 int paif_conv_tc_kq_bf16(int nsrc, int k, int dil);
-/* Launch shape of the tcgen05 engine.  1 (default): persistent — one CTA per SM, each owning an equal contiguous share of
- * the launch's B * strips * H output rows (no partial last wave, one prologue per SM); 0: one CTA per (strip, row chunk,
- * image) tile.  Results are bit-identical in both shapes; launches that produce chan_partials are always tiled (their
- * sums are per fixed tile), and so is the one shape measured faster tiled (fp32 3x3 32->32 with a plain epilogue) unless
- * on == 2.  Returns the previous setting.  A diagnostic / A-B switch, not part of the reference's API. */
+/* Launch shape of the tcgen05 engine.  1 (default): persistent — one CTA per SM; the launch's image rows are split into
+ * equal bands and the CTAs of a band walk the same rows, one 128-pixel column strip each (no partial last wave, one
+ * prologue per SM, neighbouring strips share their border in L2); 0: one CTA per (strip, row chunk, image) tile.
+ * Results are bit-identical in both shapes; launches that produce chan_partials are always tiled (their sums are per
+ * fixed tile).  Returns the previous setting.  A diagnostic / A-B switch, not part of the reference's API. */
 int paif_conv_set_persistent(int on);
 /* number of per-image tiles the chosen engine writes into chan_partials ([B][tiles][cout]) */
 int paif_conv_num_tiles(int H, int W, int engine);

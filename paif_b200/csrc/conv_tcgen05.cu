@@ -929,14 +929,16 @@ static int tc_persistent_ctas(const TcPlan& p, bool partials, int B, int H, int 
     return (int)(n < 1 ? 1 : (n > tc_num_sms() ? tc_num_sms() : n));
 }
 
-static void tc_set_grid(TcGeom& g, const TcPlan& p, bool partials, dim3* grid, bool prefer_tiled = false) {
+static void tc_set_grid(TcGeom& g, const TcPlan& p, bool partials, dim3* grid) {
     g.strips = cdiv(g.W, TC_TW);
     g.rows_total = g.B * g.strips * g.H;
-    int n = prefer_tiled ? 0 : tc_persistent_ctas(p, partials, g.B, g.H, g.W);
+    int n = tc_persistent_ctas(p, partials, g.B, g.H, g.W);
     g.persist = n > 0;
     static int banded = -1;
     if (banded < 0) { const char* e = getenv("PAIF_TC_BANDS"); banded = e ? atoi(e) : 1; }       // 0: linear shares (A/B runs)
-    if (n > 0 && banded && g.strips <= n) {
+    // (the tensor-bound shapes — 7x7, the 5x5 single-output stencil — keep the linear form: every SM busy is worth more
+    //  to them than L2 hits; 148 vs 145 CTAs at 5 strips)
+    if (n > 0 && banded && g.strips <= n && g.k < 5) {
         long long nb = n / g.strips;                            // bands of image rows; `strips` CTAs per band
         const long long most = ((long long)g.B * g.H) / 12;
         if (nb > most) nb = most < 1 ? 1 : most;
@@ -966,13 +968,7 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
     g.wmma = d.weight_mma;
     EpiParams e = make_epi(d);
     dim3 grid;
-    // One measured exception to the persistent launch: the fp32 3x3 32->32 layer with the plain epilogue (conv1 of a dense
-    // block; the launch closest to the HBM roofline, 5.7 TB/s tiled) runs 12-15 % slower persistent, at any CTA count
-    // (148 ... 592); every other shape, and the same shape with bf16 maps, is 2-12 % faster persistent.
-    const bool plain = !d.ch_scale && !d.ch_shift && !d.pre_res[0] && !d.pre_res[1] && !d.post_res[0] && !d.post_res[1] &&
-                       !d.post_res[2] && !d.mask_src && !d.out_pre && !d.out_act2 && d.post_scale == 1.f;
-    tc_set_grid(g, g.plan, d.chan_partials != nullptr, &grid,
-                plain && d.storage == PAIF_STORAGE_F32 && d.nsrc == 1 && d.kh == 3 && d.dil == 1 && tc_persist_mode != 2);
+    tc_set_grid(g, g.plan, d.chan_partials != nullptr, &grid);
     if (d.chan_partials) {
         // partial-sum slots beyond this launch's tile count must read as zero
         cudaError_t err = cudaMemsetAsync(d.chan_partials, 0, (size_t)d.B * conv_tc_tiles(d.H, d.W) * 32 * sizeof(float), stream);
@@ -1054,7 +1050,7 @@ extern "C" int paif_debug_tc_counters(unsigned long long* out16, int reset) {
 extern "C" int paif_conv_set_persistent(int on) {
     if (paif::tc_persist_mode < 0) { const char* e = getenv("PAIF_TC_PERSIST"); paif::tc_persist_mode = e ? atoi(e) : 1; }
     const int prev = paif::tc_persist_mode;
-    paif::tc_persist_mode = on == 2 ? 2 : (on ? 1 : 0);      // 2: also the shapes that default to tiled
+    paif::tc_persist_mode = on ? 1 : 0;
     return prev;
 }
 

@@ -48,7 +48,7 @@ for name, nsrc, k, dil, kw, nmaps in cases:
     cw = fusion._ConvW(w, nsrc, k, dil)
     res = {}
     for mode in (0, 1):
-        lib.paif_conv_set_persistent(2 if mode else 0)
+        lib.paif_conv_set_persistent(mode)
         res[mode] = timeit(lambda: rt.conv(maps[:nsrc], cw, **kw))
     gbs = nmaps * MAP / 1e9
     print("%-38s tiled %.3f ms (%4.0f GB/s)   persistent %.3f ms (%4.0f GB/s)  %+.1f%%" % (

@@ -332,7 +332,7 @@ def test_conv_tcgen05_persistent_launch_is_bit_identical_to_tiled(B, H, W, k, di
     prev = lib.paif_conv_set_persistent(1)
     try:
         for mode in (1, 0):
-            lib.paif_conv_set_persistent(2 if mode else 0)      # 2: persistent for every single-pass shape
+            lib.paif_conv_set_persistent(mode)
             o, opre, act2, _ = rt(B, H, W, _lib.ENGINE_TCGEN05).conv(xs, cw, slope=a, post_scale=0.5, post_res=[r1],
                                                                       want_pre=True)
             outs[mode] = (o.clone(), opre.clone())
