@@ -32,9 +32,10 @@ def needs_build():
 
 def build(force=False, verbose=False, profile=False, sanitize=False):
     """profile: -DPAIF_TC_PROFILE role-timeline counters (libpaif_b200_prof.so); sanitize: a build for compute-sanitizer
-    runs (libpaif_b200_san.so: mbarrier waits poll without the suspend-time hint)."""
+    runs (libpaif_b200_san.so: mbarrier waits poll without the suspend-time hint; the conv engine's block barrier is a
+    non-inlined function so that synccheck sees one barrier instruction)."""
     if sanitize:
-        return _build_variant("_san", ["-DPAIF_NO_SUSPEND_HINT"])
+        return _build_variant("_san", ["-DPAIF_NO_SUSPEND_HINT", "-DPAIF_SANITIZER_BUILD"])
     lib = LIB.replace(".so", "_prof.so") if profile else LIB
     if profile:
         if os.path.exists(lib) and os.path.getmtime(lib) >= max(

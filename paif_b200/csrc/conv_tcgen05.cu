@@ -145,6 +145,19 @@ static_assert(sizeof(TcBars) <= 1024, "barrier block must fit its 1 KB reservati
 
 struct TcSeg { int x0, r0, b, nrows, xs, poff, npx; };
 
+// Block-wide barrier of the segment loops.  Each warp role runs its own (inlined) copy of tc_seg_begin, so the three roles
+// arrive at three different bar.sync instructions.  The hardware barrier counts arriving warps whatever their program
+// counter, but that is outside the documented contract of __syncthreads() and compute-sanitizer's synccheck reports it
+// as "divergent thread(s) in block".  The sanitizer build (python -m paif_b200.build --sanitize: -DPAIF_SANITIZER_BUILD)
+// therefore keeps the barrier in a non-inlined function — every thread executes the SAME instruction, synccheck is clean
+// (profiles/r2_sanitizer_synccheck.log) — while the production build inlines it: the mere presence of a call in the
+// kernel cost every conv layer 12-17 % (measured; values no longer stay in uniform registers across the issue loop).
+#ifdef PAIF_SANITIZER_BUILD
+__device__ __noinline__ void tc_block_sync() { __syncthreads(); }
+#else
+__device__ __forceinline__ void tc_block_sync() { __syncthreads(); }
+#endif
+
 // Start of a segment (see the kernel): geometry of the next piece of this CTA's share, and — block-wide — the drain of
 // the previous segment, re-armed accumulator barriers, re-zeroed border columns.  Called by every thread of the CTA.
 template <int K, int DIL, int KQ>
@@ -178,7 +191,7 @@ __device__ __forceinline__ void tc_seg_begin(const TcGeom& g, TcBars* bars, unsi
         // every role is done with the previous segment: all MMAs retired (the epilogue saw the last acc_full), no bulk
         // copy in flight (the issuer consumed every full stage), every drained accumulator slot is zero again
         tc_fence_before();
-        __syncthreads();
+        tc_block_sync();
         if (tid == 0) {
             for (int i = 0; i < TC_SLOTS; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 128); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -196,7 +209,7 @@ __device__ __forceinline__ void tc_seg_begin(const TcGeom& g, TcBars* bars, unsi
         fence_proxy_async();
     }
     tc_fence_before();
-    __syncthreads();
+    tc_block_sync();
     tc_fence_after();
 }
 
