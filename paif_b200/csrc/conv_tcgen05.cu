@@ -287,7 +287,7 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         tc_seg_begin<K, DIL, KQ>(g, bars, s_ring, tid, seg, lin, lin_end, sg_);                               \
         const int x0 = sg_.x0, r0 = sg_.r0, b = sg_.b, nrows = sg_.nrows, nin = sg_.nrows + 2 * pad;          \
         const int xs = sg_.xs, poff = sg_.poff, npx = sg_.npx;                                                \
-        (void)x0; (void)r0; (void)b; (void)nin; (void)xs; (void)poff; (void)npx;                              \
+        (void)x0; (void)r0; (void)b; (void)nrows; (void)nin; (void)xs; (void)poff; (void)npx;                              \
         if (seg == 0) tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);   /* warp-uniform for the compiler */
     uint32_t tmem_base = 0;
 
@@ -805,7 +805,7 @@ dilconv_tc_kernel(const float* __restrict__ xin, const float* __restrict__ dw, c
     __shared__ __align__(16) float s_sh[32];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int x = blockIdx.x * 128 + tid, r0 = blockIdx.y * DC_ROWS, b = blockIdx.z;
     const int nrows = min(DC_ROWS, H - r0);
     for (int i = tid; i < 1024; i += 128) {

@@ -316,7 +316,8 @@ def test_conv_tcgen05_full_size_tiling(k, dil, nsrc):
 
 
 @pytest.mark.parametrize("B,H,W,k,dil,nsrc", [(3, 50, 200, 3, 1, 1), (5, 61, 300, 3, 2, 1), (3, 50, 200, 7, 1, 1),
-                                               (7, 45, 130, 1, 1, 3), (3, 77, 640, 3, 1, 3), (2, 480, 640, 7, 1, 1)])
+                                               (7, 45, 130, 1, 1, 3), (3, 77, 640, 3, 1, 3), (2, 480, 640, 7, 1, 1),
+                                               (3, 77, 300, 3, 2, 1), (5, 53, 520, 5, 1, 1), (4, 480, 640, 3, 2, 1)])
 def test_conv_tcgen05_persistent_launch_is_bit_identical_to_tiled(B, H, W, k, dil, nsrc):
     """The persistent launch (one CTA per SM, equal contiguous shares of the B*strips*H output rows, a share crossing
     strip / image boundaries as separate segments) against the tiled launch of the same kernel: same bits (every output
