@@ -44,6 +44,7 @@ __device__ unsigned long long gx_prof[16];
 #define GX_PROF_END(slot)
 #endif
 
+__device__ __align__(64) const float gx_zero[16] = {0.f};      // what out-of-image lanes and absent leaving rows load
 constexpr int OUTW = 48;                       // output columns per strip (64 raw -> 56 level-1 -> 48 output)
 constexpr int NWARPS = 14, NT = NWARPS * 32;
 constexpr int MMA_WARP = 12;            // warp 13: producer
@@ -79,6 +80,11 @@ struct Params {
 __device__ __forceinline__ float win_count(int p, int n) {
     const int lo = p - 4 < 0 ? 0 : p - 4, hi = p + 4 > n - 1 ? n - 1 : p + 4;
     return (float)(hi - lo + 1);
+}
+// 1 / win_count(p, n) for n > 9 (5..9 rows or columns in the window): the correctly rounded constants __frcp_rn returns
+__device__ __forceinline__ float rcp_count(int p, int n) {
+    const int lo = p - 4 < 0 ? 0 : p - 4, hi = p + 4 > n - 1 ? n - 1 : p + 4, c = hi - lo + 1;
+    return c == 9 ? 1.f / 9.f : c == 8 ? 1.f / 8.f : c == 7 ? 1.f / 7.f : c == 6 ? 1.f / 6.f : 1.f / 5.f;
 }
 // o[k] = sum of columns (4j+k) .. (4j+k+8) of the per-lane column quadruples a[0..3]; 16-lane segments
 __device__ __forceinline__ void hsum9(const float (&a)[4], float (&o)[4]) {
@@ -231,11 +237,14 @@ __device__ __forceinline__ void tmem_wait_ld16(float (&v)[16]) {
                  :: "memory");
 }
 
-// mbarrier arrive that releases a shared-memory stage the calling thread has just READ with ordinary loads.  The loaded
-// values are operands of the statement, so the arrive cannot be scheduled before they are in registers (an arrive
-// issued while a load is still in flight would let the producer refill the stage under it).
-__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, float a, float b, float c, float d, float e) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e) : "memory");
+// mbarrier arrive that releases a shared-memory stage the calling thread has just READ with ordinary loads.  The arrive
+// must not be issued while a load is still in flight (the producer would refill the stage under it), and an inline-asm
+// operand that the instruction does not use is no dependency for ptxas.  So the barrier ADDRESS is made to depend on
+// one register of every load: (bits of the loaded values) & rt_zero, where rt_zero is a run-time zero the compiler
+// cannot see through (blockIdx.y of a 1-D grid).
+__device__ __forceinline__ void mbar_arrive_after_loads(uint32_t bar, uint32_t rt_zero, float a, float b, float c, float d, float e) {
+    const uint32_t dep = (__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c) | __float_as_uint(d) | __float_as_uint(e)) & rt_zero;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar + dep) : "memory");
 }
 
 // one work chunk: rows [y0, y0 + rows) of strip `strip` of image b
@@ -308,6 +317,8 @@ gf_mix_kernel(const Params p) {
     if (warp < 4) {
         // ============================ L1: level-1 statistics -> A operand ============================
         const int h = lane >> 4, j = lane & 15, q = 2 * warp + h;
+        const int rot = (j >> 1) & 3;
+        const uint32_t rt_zero = blockIdx.y;                   // 0 at run time, opaque to the compiler (mbar_arrive_after_loads)
         unsigned char* aop = smem + OFF_AOP;
         // byte offset of row m = half*64 + 4j + k inside a plane: (m >> 3) * SBO + (m & 7) * 16
         const int aoff = (j >> 1) * AOP_SBO + (j & 1) * 64;
@@ -317,19 +328,20 @@ gf_mix_kernel(const Params p) {
         while (walk.next(ck)) {
             const int x0 = ck.strip * OUTW, y0 = ck.y0, rows = ck.rows;
             const int xr = x0 - 8 + 4 * j, xs = xr + 4;
-            const float* zp = p.feat + ((size_t)ck.b * 8 + q) * plane * 4;
-            const float* gp = p.guide + (size_t)ck.b * plane;
-            const float* mxp = p.stats + (size_t)ck.b * plane;
+            // x0, xr, xs and W are multiples of 4: the 4 raw columns of a lane are all inside the image or all outside.
+            // Out-of-image lanes (and leaving rows that do not exist) read a 64-byte page of zeros instead of being
+            // masked value by value, and every address is one 32-bit element offset from a per-lane base.
+            const bool cin = xr >= 0 && xr < W;
+            const float4* zcol = reinterpret_cast<const float4*>(p.feat) + ((size_t)ck.b * 8 + q) * plane + (cin ? xr : 0);
+            const float* gcol = p.guide + (size_t)ck.b * plane + (cin ? xr : 0);
+            const float* mcol = p.stats + (size_t)ck.b * plane + ((xs >= 0 && xs < W) ? xs : 0);
+            const float4* zero4 = reinterpret_cast<const float4*>(gx_zero);
             float cs[4];
-            bool cin[4];                                           // raw column inside the image
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k)
                 cs[k] = (xs + k >= 0 && xs + k < W && 4 * j + k < 56) ? __frcp_rn(win_count(xs + k, W)) : 0.f;
-                cin[k] = xr + k >= 0 && xr + k < W;
-            }
             float Sz[4][4], Sgz[4][4];
-            float4 zq4[4], gq4, mx4;                               // leaving row / mean_g of the next iteration, unmasked
-            bool lvq = false;                                      // ... and whether that leaving row exists
+            float4 zq4[4], gq4, mx4;                               // leaving row (zeros where it does not exist) / mean_g of the next iteration
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 zq4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -340,27 +352,21 @@ gf_mix_kernel(const Params p) {
             const int n1 = rows + 8, nt = rows + 16;
             for (int t = 0; t < nt; ++t) {
                 const int yr = y0 - 8 + t;
-                // ---- leaving row (fetched from global memory one iteration ago): masks applied here, at the use
-                float zq[4][4], gq[4];
-                {
-                    const float gqr[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool m = lvq && cin[k];
-                        gq[k] = m ? gqr[k] : 0.f;
-                        zq[k][0] = m ? zq4[k].x : 0.f; zq[k][1] = m ? zq4[k].y : 0.f;
-                        zq[k][2] = m ? zq4[k].z : 0.f; zq[k][3] = m ? zq4[k].w : 0.f;
-                    }
-                }
+                // ---- leaving row (fetched from global memory one iteration ago; zeros where there is none)
+                const float zq[4][4] = {{zq4[0].x, zq4[0].y, zq4[0].z, zq4[0].w}, {zq4[1].x, zq4[1].y, zq4[1].z, zq4[1].w},
+                                        {zq4[2].x, zq4[2].y, zq4[2].z, zq4[2].w}, {zq4[3].x, zq4[3].y, zq4[3].z, zq4[3].w}};
+                const float gq[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
                 const float mxc[4] = {mx4.x, mx4.y, mx4.z, mx4.w};     // mean_g of the level-1 row this iteration completes
-                {   // global loads for iteration t+1: leaving row yr-8 (an L2 hit: it entered 9 rows ago), mean_g of row yr-3.
-                    // Always issued, with row and column clamped into the image: whether they count is decided at the use.
+                {   // global loads for iteration t+1: leaving row yr-8 (an L2 hit: it entered 9 rows ago), mean_g of row yr-3
+                    // (row clamped into the image: whether it counts is decided by the window count at the use)
                     const int yl = yr - 8, ysn = yr - 3;
-                    lvq = t + 1 < nt && t + 1 >= 9 && yl >= 0 && yl < H;
-                    const int ylc = min(max(yl, 0), H - 1), ysc = min(max(ysn, 0), H - 1);
-                    ld_quad_raw(zp + (size_t)ylc * W * 4, xr, W, zq4);
-                    gq4 = ld_cols4_raw(gp + (size_t)ylc * W, xr, W);
-                    mx4 = ld_cols4_raw(mxp + (size_t)ysc * W, xs, W);
+                    const bool lv = t + 1 < nt && t + 1 >= 9 && yl >= 0 && yl < H && cin;
+                    const unsigned rowl = (unsigned)(min(max(yl, 0), H - 1) * W), rowm = (unsigned)(min(max(ysn, 0), H - 1) * W);
+                    const float4* zl = lv ? zcol + rowl : zero4;
+                    const float4* gl = lv ? reinterpret_cast<const float4*>(gcol + rowl) : zero4;
+                    zq4[0] = __ldg(zl); zq4[1] = __ldg(zl + 1); zq4[2] = __ldg(zl + 2); zq4[3] = __ldg(zl + 3);
+                    gq4 = __ldg(gl);
+                    mx4 = __ldg(reinterpret_cast<const float4*>(mcol + rowm));
                 }
                 // ---- entering row: from the shared-memory ring the producer fills a few rows ahead
                 float zn[4][4], gn[4];
@@ -370,12 +376,25 @@ gf_mix_kernel(const Params p) {
                     if (yr >= 0 && yr < H) {
                         const unsigned char* rs_ = ring + st * R_BYTES;
                         const float4 g4 = *reinterpret_cast<const float4*>(rs_ + 8192 + j * 16);
-                        gn[0] = cin[0] ? g4.x : 0.f; gn[1] = cin[1] ? g4.y : 0.f; gn[2] = cin[2] ? g4.z : 0.f; gn[3] = cin[3] ? g4.w : 0.f;
+                        // ring columns outside the image hold zeros (the producer clears them at the start of the chunk).
+                        // A lane's 4 pixels are 64 contiguous bytes, so "pixel k of every lane" is a 4-way bank conflict:
+                        // the k-th load of lane j takes pixel (k + j/2) % 4 instead (8 consecutive lanes then cover the 8
+                        // 16-byte slots of a 128-byte line) and two select stages put the pixels back in order.
+                        gn[0] = g4.x; gn[1] = g4.y; gn[2] = g4.z; gn[3] = g4.w;
+                        float4 v[4], w[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            v[k] = *reinterpret_cast<const float4*>(rs_ + q * 1024 + j * 64 + (((k + rot) & 3) << 4));
+                        const bool r1b = rot & 1, r2b = rot & 2;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const float4 v = *reinterpret_cast<const float4*>(rs_ + q * 1024 + (4 * j + k) * 16);
-                            zn[k][0] = cin[k] ? v.x : 0.f; zn[k][1] = cin[k] ? v.y : 0.f;
-                            zn[k][2] = cin[k] ? v.z : 0.f; zn[k][3] = cin[k] ? v.w : 0.f;
+                            const float4 x = v[k], y = v[(k + 3) & 3];
+                            w[k] = make_float4(r1b ? y.x : x.x, r1b ? y.y : x.y, r1b ? y.z : x.z, r1b ? y.w : x.w);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float4 x = w[k], y = w[(k + 2) & 3];
+                            zn[k][0] = r2b ? y.x : x.x; zn[k][1] = r2b ? y.y : x.y; zn[k][2] = r2b ? y.z : x.z; zn[k][3] = r2b ? y.w : x.w;
                         }
                     } else {
 #pragma unroll
@@ -388,7 +407,7 @@ gf_mix_kernel(const Params p) {
                             Sz[k][c] += zn[k][c] - zq[k][c];
                             Sgz[k][c] = __fmaf_rn(-gq[k], zq[k][c], __fmaf_rn(gn[k], zn[k][c], Sgz[k][c]));
                         }
-                    mbar_arrive_after_loads(smem_u32(&bars->r_empty[st]), gn[0], zn[0][3], zn[1][3], zn[2][3], zn[3][3]);
+                    mbar_arrive_after_loads(smem_u32(&bars->r_empty[st]), rt_zero, gn[0], zn[0][3], zn[1][3], zn[2][3], zn[3][3]);
                     ++rcount;
                 }
                 if (t < 8) continue;
@@ -396,7 +415,7 @@ gf_mix_kernel(const Params p) {
                 const uint32_t gpair = gp0 + (uint32_t)(r1 >> 1), buf = gpair & 1u;
                 float rn[4];
                 {
-                    const float rcy = (ys >= 0 && ys < H) ? __frcp_rn(win_count(ys, H)) : 0.f;
+                    const float rcy = (ys >= 0 && ys < H) ? rcp_count(ys, H) : 0.f;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) rn[k] = rcy * cs[k];
                 }
@@ -430,6 +449,7 @@ gf_mix_kernel(const Params p) {
     } else if (warp < 8) {
         // ============================ L2: level-2 box filters -> output ============================
         const int w2 = warp & 3, h = lane >> 4, j = lane & 15, q = 2 * w2 + h;
+        const uint32_t rt_zero = blockIdx.y;
         const unsigned char* xbuf = smem + OFF_X;
         const uint32_t ring = tmem_base + ((uint32_t)(w2 * 32) << 16) + RING_COL0;
         int xo_slot[4];
@@ -497,6 +517,7 @@ gf_mix_kernel(const Params p) {
                 }
                 slot = slot == RING_SLOTS - 1 ? 0 : slot + 1;
                 const float gc[4] = {g4.x, g4.y, g4.z, g4.w};
+                float cdep[4] = {0.f, 0.f, 0.f, 0.f};
                 {   // guide of the NEXT output row (row clamped into the chunk, columns into the image: only stored pixels
                     // use it): in flight during this row's horizontal sums
                     const int yon = min(max(y0 + r1 - 7, y0), y0 + rows - 1);
@@ -511,7 +532,7 @@ gf_mix_kernel(const Params p) {
                     float o[4][4];
                     float4 cc[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) cc[k] = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]);
+                    for (int k = 0; k < 4; ++k) { cc[k] = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]); cdep[k] = cc[k].w; }
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2) {
                         const float2 sa[4] = {SA[0][h2], SA[1][h2], SA[2][h2], SA[3][h2]};
@@ -553,7 +574,9 @@ gf_mix_kernel(const Params p) {
                         }
                     }
                 }
-                mbar_arrive(smem_u32(&bars->x_empty[half]));           // this row of the exchange buffer has been read (A', b', C)
+                // this row of the exchange buffer has been read (A', b', C): the A' / b' loads were consumed by the TMEM stores
+                // above (completed by their wait), the C loads are made operands of the arrive
+                mbar_arrive_after_loads(smem_u32(&bars->x_empty[half]), rt_zero, cdep[0], cdep[1], cdep[2], cdep[3], cdep[0]);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             gp0 += (uint32_t)((n1 + 1) >> 1);
@@ -684,6 +707,20 @@ gf_mix_kernel(const Params p) {
                     const int yr = y0 - 8 + t;
                     const uint32_t st = rcount % RS;
                     GX_WAIT(mbar_wait(smem_u32(&bars->r_empty[st]), ((rcount / RS) & 1u) ^ 1u));
+                    if (t < RS && ring_px < 64u) {
+                        // first use of this stage in the chunk: the columns the copies of this chunk never write (outside
+                        // the image) may hold rows of another strip — clear them, so that L1 needs no column masks.  The
+                        // stores are ordered before L1's reads by the __syncwarp + the elected lane's arrive on r_full.
+                        unsigned char* dstz = smem + OFF_R + st * R_BYTES;
+                        const uint32_t nstale = 64u - ring_px;                     // columns [0, ring_off) and [ring_off + ring_px, 64)
+                        for (uint32_t i = lane; i < nstale * 9u; i += 32u) {
+                            const uint32_t pl9 = i / nstale, ci = i - pl9 * nstale;
+                            const uint32_t col = ci < ring_off ? ci : ci + ring_px;
+                            if (pl9 < 8u) *reinterpret_cast<float4*>(dstz + pl9 * 1024 + col * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            else *reinterpret_cast<float*>(dstz + 8192 + col * 4) = 0.f;
+                        }
+                        __syncwarp();
+                    }
                     if (elect_one()) {
                         const uint32_t bar = smem_u32(&bars->r_full[st]);
                         if (yr >= 0 && yr < H) {
