@@ -26,6 +26,7 @@
 #ifndef PAIF_NO_SUSPEND_HINT                   // (builds for compute-sanitizer runs define it: plain polling)
 #define PAIF_MBAR_SUSPEND_NS 20000
 #endif
+#include <cstddef>
 #include "tc_ptx.cuh"
 
 namespace paif {
@@ -237,6 +238,16 @@ __device__ __forceinline__ void tmem_wait_ld16(float (&v)[16]) {
                  :: "memory");
 }
 
+// shared-memory accesses by 32-bit shared-window address (the level-1 role: no generic-to-shared conversion per access)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 // mbarrier arrive that releases a shared-memory stage the calling thread has just READ with ordinary loads.  The arrive
 // must not be issued while a load is still in flight (the producer would refill the stage under it), and an inline-asm
 // operand that the instruction does not use is no dependency for ptxas.  So the barrier ADDRESS is made to depend on
@@ -277,7 +288,12 @@ __global__ void __launch_bounds__(NT, 1)    // 14 warps = up to 4 per SM sub-par
 gf_mix_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     Bars* bars = reinterpret_cast<Bars*>(smem + OFF_BARS);
-    const int tid = threadIdx.x, lane = tid & 31;
+    // threadIdx.x and the shared-memory window base through volatile asm: the compiler cannot re-read the special
+    // registers inside the row loops (S2R / S2UR have ~25 cycles of latency, and the level-1 warp is latency-bound)
+    uint32_t tid_op, sbase;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid_op));
+    asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(smem_u32(smem)));
+    const int tid = (int)tid_op, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler: the role branches do not diverge
     const int H = p.H, W = p.W;
     const size_t plane = (size_t)H * W;
@@ -319,10 +335,10 @@ gf_mix_kernel(const Params p) {
         const int h = lane >> 4, j = lane & 15, q = 2 * warp + h;
         const int rot = (j >> 1) & 3;
         const uint32_t rt_zero = blockIdx.y;                   // 0 at run time, opaque to the compiler (mbar_arrive_after_loads)
-        unsigned char* aop = smem + OFF_AOP;
+        const uint32_t aop = sbase + OFF_AOP;
         // byte offset of row m = half*64 + 4j + k inside a plane: (m >> 3) * SBO + (m & 7) * 16
         const int aoff = (j >> 1) * AOP_SBO + (j & 1) * 64;
-        const unsigned char* ring = smem + OFF_R;
+        const uint32_t ring = sbase + OFF_R;
         uint32_t rcount = 0;                                   // raw rows taken from the ring so far
         GX_PROF_DECL;
         while (walk.next(ck)) {
@@ -357,25 +373,14 @@ gf_mix_kernel(const Params p) {
                                         {zq4[2].x, zq4[2].y, zq4[2].z, zq4[2].w}, {zq4[3].x, zq4[3].y, zq4[3].z, zq4[3].w}};
                 const float gq[4] = {gq4.x, gq4.y, gq4.z, gq4.w};
                 const float mxc[4] = {mx4.x, mx4.y, mx4.z, mx4.w};     // mean_g of the level-1 row this iteration completes
-                {   // global loads for iteration t+1: leaving row yr-8 (an L2 hit: it entered 9 rows ago), mean_g of row yr-3
-                    // (row clamped into the image: whether it counts is decided by the window count at the use)
-                    const int yl = yr - 8, ysn = yr - 3;
-                    const bool lv = t + 1 < nt && t + 1 >= 9 && yl >= 0 && yl < H && cin;
-                    const unsigned rowl = (unsigned)(min(max(yl, 0), H - 1) * W), rowm = (unsigned)(min(max(ysn, 0), H - 1) * W);
-                    const float4* zl = lv ? zcol + rowl : zero4;
-                    const float4* gl = lv ? reinterpret_cast<const float4*>(gcol + rowl) : zero4;
-                    zq4[0] = __ldg(zl); zq4[1] = __ldg(zl + 1); zq4[2] = __ldg(zl + 2); zq4[3] = __ldg(zl + 3);
-                    gq4 = __ldg(gl);
-                    mx4 = __ldg(reinterpret_cast<const float4*>(mcol + rowm));
-                }
                 // ---- entering row: from the shared-memory ring the producer fills a few rows ahead
                 float zn[4][4], gn[4];
                 {
                     const uint32_t st = rcount % RS;
-                    GX_WAIT(mbar_wait(smem_u32(&bars->r_full[st]), (rcount / RS) & 1u));
+                    GX_WAIT(mbar_wait((sbase + OFF_BARS + (uint32_t)offsetof(Bars, r_full) + 8u * (st)), (rcount / RS) & 1u));
                     if (yr >= 0 && yr < H) {
-                        const unsigned char* rs_ = ring + st * R_BYTES;
-                        const float4 g4 = *reinterpret_cast<const float4*>(rs_ + 8192 + j * 16);
+                        const uint32_t rs_ = ring + st * R_BYTES;
+                        const float4 g4 = lds128(rs_ + 8192 + j * 16);
                         // ring columns outside the image hold zeros (the producer clears them at the start of the chunk).
                         // A lane's 4 pixels are 64 contiguous bytes, so "pixel k of every lane" is a 4-way bank conflict:
                         // the k-th load of lane j takes pixel (k + j/2) % 4 instead (8 consecutive lanes then cover the 8
@@ -384,7 +389,7 @@ gf_mix_kernel(const Params p) {
                         float4 v[4], w[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            v[k] = *reinterpret_cast<const float4*>(rs_ + q * 1024 + j * 64 + (((k + rot) & 3) << 4));
+                            v[k] = lds128(rs_ + q * 1024 + j * 64 + (((k + rot) & 3) << 4));
                         const bool r1b = rot & 1, r2b = rot & 2;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -407,8 +412,21 @@ gf_mix_kernel(const Params p) {
                             Sz[k][c] += zn[k][c] - zq[k][c];
                             Sgz[k][c] = __fmaf_rn(-gq[k], zq[k][c], __fmaf_rn(gn[k], zn[k][c], Sgz[k][c]));
                         }
-                    mbar_arrive_after_loads(smem_u32(&bars->r_empty[st]), rt_zero, gn[0], zn[0][3], zn[1][3], zn[2][3], zn[3][3]);
+                    mbar_arrive_after_loads((sbase + OFF_BARS + (uint32_t)offsetof(Bars, r_empty) + 8u * (st)), rt_zero, gn[0], zn[0][3], zn[1][3], zn[2][3], zn[3][3]);
                     ++rcount;
+                }
+                {   // global loads for iteration t+1, issued once this iteration's leaving row has been consumed (the registers are
+                    // reused without copies; most of an iteration is still ahead to cover the L2 latency): leaving row yr-8 (an L2
+                    // hit: it entered 9 rows ago), mean_g of row yr-3
+                    // (row clamped into the image: whether it counts is decided by the window count at the use)
+                    const int yl = yr - 8, ysn = yr - 3;
+                    const bool lv = t + 1 < nt && t + 1 >= 9 && yl >= 0 && yl < H && cin;
+                    const unsigned rowl = (unsigned)(min(max(yl, 0), H - 1) * W), rowm = (unsigned)(min(max(ysn, 0), H - 1) * W);
+                    const float4* zl = lv ? zcol + rowl : zero4;
+                    const float4* gl = lv ? reinterpret_cast<const float4*>(gcol + rowl) : zero4;
+                    zq4[0] = __ldg(zl); zq4[1] = __ldg(zl + 1); zq4[2] = __ldg(zl + 2); zq4[3] = __ldg(zl + 3);
+                    gq4 = __ldg(gl);
+                    mx4 = __ldg(reinterpret_cast<const float4*>(mcol + rowm));
                 }
                 if (t < 8) continue;
                 const int r1 = t - 8, ys = yr - 4, half = r1 & 1;
@@ -431,16 +449,16 @@ gf_mix_kernel(const Params p) {
                         cov[k][c] = __fmaf_rn(-mxc[k], mz[k][c], bg[k] * rn[k]);
                     }
                 }
-                if (half == 0) GX_WAIT(mbar_wait(smem_u32(&bars->aop_empty[buf]), ((gpair >> 1) & 1u) ^ 1u));
-                unsigned char* base = aop + buf * AOP_BYTES + half * (8 * AOP_SBO) + aoff;
+                if (half == 0) GX_WAIT(mbar_wait((sbase + OFF_BARS + (uint32_t)offsetof(Bars, aop_empty) + 8u * (buf)), ((gpair >> 1) & 1u) ^ 1u));
+                const uint32_t base = aop + buf * AOP_BYTES + half * (8 * AOP_SBO) + aoff;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    *reinterpret_cast<float4*>(base + q * AOP_PLANE + k * 16) = make_float4(cov[k][0], cov[k][1], cov[k][2], cov[k][3]);
-                    *reinterpret_cast<float4*>(base + (8 + q) * AOP_PLANE + k * 16) = make_float4(mz[k][0], mz[k][1], mz[k][2], mz[k][3]);
+                    sts128(base + q * AOP_PLANE + k * 16, cov[k][0], cov[k][1], cov[k][2], cov[k][3]);
+                    sts128(base + (8 + q) * AOP_PLANE + k * 16, mz[k][0], mz[k][1], mz[k][2], mz[k][3]);
                 }
                 if (half == 1 || r1 == n1 - 1) {
                     fence_proxy_async();
-                    mbar_arrive(smem_u32(&bars->aop_full[buf]));
+                    mbar_arrive((sbase + OFF_BARS + (uint32_t)offsetof(Bars, aop_full) + 8u * (buf)));
                 }
             }
             gp0 += (uint32_t)((n1 + 1) >> 1);
