@@ -468,7 +468,7 @@ gf_mix_kernel(const Params p) {
         // ============================ L2: level-2 box filters -> output ============================
         const int w2 = warp & 3, h = lane >> 4, j = lane & 15, q = 2 * w2 + h;
         const uint32_t rt_zero = blockIdx.y;
-        const unsigned char* xbuf = smem + OFF_X;
+        const uint32_t xbuf = sbase + OFF_X;
         const uint32_t ring = tmem_base + ((uint32_t)(w2 * 32) << 16) + RING_COL0;
         int xo_slot[4];
 #pragma unroll
@@ -477,7 +477,10 @@ gf_mix_kernel(const Params p) {
         while (walk.next(ck)) {
             const int x0 = ck.strip * OUTW, y0 = ck.y0, rows = ck.rows;
             const int xo = x0 + 4 * j;
-            const float* gp = p.guide + (size_t)ck.b * plane;
+            // per-chunk bases; inside the row loop every address is base + one 32-bit row offset
+            const float* gcol = p.guide + (size_t)ck.b * plane + ((xo >= 0 && xo < W) ? xo : 0);
+            float4* const o32 = reinterpret_cast<float4*>(p.out) + ((size_t)ck.b * 8 + q) * plane + xo;
+            uint4* const o16 = reinterpret_cast<uint4*>(p.out) + ((size_t)ck.b * 4 + w2) * plane + xo;
             float co[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -494,12 +497,12 @@ gf_mix_kernel(const Params p) {
                 if (r1 >= n1) {
                     // odd row count: the second row of the last pair does not exist, but EP hands over both rows of
                     // every pair — take it and give it back so that the barrier phases stay in step
-                    GX_WAIT(mbar_wait(smem_u32(&bars->x_full[half]), gpair & 1u));
-                    mbar_arrive(smem_u32(&bars->x_empty[half]));
+                    GX_WAIT(mbar_wait((sbase + OFF_BARS + (uint32_t)offsetof(Bars, x_full) + 8u * (half)), gpair & 1u));
+                    mbar_arrive((sbase + OFF_BARS + (uint32_t)offsetof(Bars, x_empty) + 8u * (half)));
                     continue;
                 }
-                GX_WAIT(mbar_wait(smem_u32(&bars->x_full[half]), gpair & 1u));
-                const unsigned char* xrow = xbuf + half * X_BYTES;
+                GX_WAIT(mbar_wait((sbase + OFF_BARS + (uint32_t)offsetof(Bars, x_full) + 8u * (half)), gpair & 1u));
+                const uint32_t xrow = xbuf + half * X_BYTES;
                 const bool has_old = r1 >= 9;
                 const uint32_t t_new = ring + slot * 32, t_old = ring + (slot == RING_SLOTS - 1 ? 0 : slot + 1) * 32;   // row r1 - 9
                 // the two halves (A', b') one after the other: new row from the exchange buffer, into the history ring and
@@ -510,7 +513,7 @@ gf_mix_kernel(const Params p) {
                     if (has_old) tmem_ld16_nowait(t_old + e * 16, od);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float4 a = *reinterpret_cast<const float4*>(xrow + (e * 8 + q) * X_PLANE + xo_slot[k]);
+                        const float4 a = lds128(xrow + (e * 8 + q) * X_PLANE + xo_slot[k]);
                         nw[k * 4 + 0] = a.x; nw[k * 4 + 1] = a.y; nw[k * 4 + 2] = a.z; nw[k * 4 + 3] = a.w;
                     }
                     tmem_st16(t_new + e * 16, nw);
@@ -539,7 +542,7 @@ gf_mix_kernel(const Params p) {
                 {   // guide of the NEXT output row (row clamped into the chunk, columns into the image: only stored pixels
                     // use it): in flight during this row's horizontal sums
                     const int yon = min(max(y0 + r1 - 7, y0), y0 + rows - 1);
-                    g4 = ld_cols4_raw(gp + (size_t)yon * W, xo, W);
+                    g4 = __ldg(reinterpret_cast<const float4*>(gcol + (unsigned)(yon * W)));
                 }
                 if (r1 >= 8) {
                     const int yo = y0 + r1 - 8;
@@ -550,7 +553,7 @@ gf_mix_kernel(const Params p) {
                     float o[4][4];
                     float4 cc[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { cc[k] = *reinterpret_cast<const float4*>(xrow + (16 + q) * X_PLANE + xo_slot[k]); cdep[k] = cc[k].w; }
+                    for (int k = 0; k < 4; ++k) { cc[k] = lds128(xrow + (16 + q) * X_PLANE + xo_slot[k]); cdep[k] = cc[k].w; }
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2) {
                         const float2 sa[4] = {SA[0][h2], SA[1][h2], SA[2][h2], SA[3][h2]};
@@ -567,11 +570,10 @@ gf_mix_kernel(const Params p) {
                         }
                     }
                     if constexpr (!OUT_BF) {
-                        float* orow = static_cast<float*>(p.out) + (((size_t)ck.b * 8 + q) * plane + (size_t)yo * W) * 4;
+                        float4* orow = o32 + (unsigned)(yo * W);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (co[k] > 0.f)
-                                *reinterpret_cast<float4*>(orow + (size_t)(xo + k) * 4) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
+                            if (co[k] > 0.f) orow[k] = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
                     } else {
                         // C8 bf16 pixel vectors: the two half-warps hold the two quads of oct w2; lanes of half 0
                         // assemble columns 0-1, lanes of half 1 columns 2-3
@@ -581,20 +583,22 @@ gf_mix_kernel(const Params p) {
 #pragma unroll
                             for (int c = 0; c < 4; ++c)
                                 r[i][c] = __shfl_xor_sync(0xffffffffu, h == 0 ? o[2 + i][c] : o[i][c], 16);
-                        uint4* orow = static_cast<uint4*>(p.out) + ((size_t)ck.b * 4 + w2) * plane + (size_t)yo * W;
+                        uint4* orow = o16 + (unsigned)(yo * W);
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             const int kk = h == 0 ? i : 2 + i;
-                            const float4 mine = make_float4(o[kk][0], o[kk][1], o[kk][2], o[kk][3]);
+                            // (static register indices: a run-time o[kk] would put the array in local memory)
+                            const float4 mine = h == 0 ? make_float4(o[i][0], o[i][1], o[i][2], o[i][3])
+                                                       : make_float4(o[2 + i][0], o[2 + i][1], o[2 + i][2], o[2 + i][3]);
                             const float4 peer = make_float4(r[i][0], r[i][1], r[i][2], r[i][3]);
                             const bool ok = (4 * j + kk < OUTW) && (xo + kk < W);
-                            if (ok) orow[xo + kk] = h == 0 ? bf8_pack(mine, peer) : bf8_pack(peer, mine);
+                            if (ok) orow[kk] = h == 0 ? bf8_pack(mine, peer) : bf8_pack(peer, mine);
                         }
                     }
                 }
                 // this row of the exchange buffer has been read (A', b', C): the A' / b' loads were consumed by the TMEM stores
                 // above (completed by their wait), the C loads are made operands of the arrive
-                mbar_arrive_after_loads(smem_u32(&bars->x_empty[half]), rt_zero, cdep[0], cdep[1], cdep[2], cdep[3], cdep[0]);
+                mbar_arrive_after_loads((sbase + OFF_BARS + (uint32_t)offsetof(Bars, x_empty) + 8u * (half)), rt_zero, cdep[0], cdep[1], cdep[2], cdep[3], cdep[0]);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             gp0 += (uint32_t)((n1 + 1) >> 1);
@@ -668,7 +672,7 @@ gf_mix_kernel(const Params p) {
         // ============================ MMA issuer ============================
         const uint32_t w_base = smem_u32(smem + OFF_W), aop_base = smem_u32(smem + OFF_AOP), z_base = smem_u32(smem + OFF_Z);
         const uint32_t id64 = tc_idesc(64u, 2u), id32 = tc_idesc(32u, 2u);
-        uint32_t zcnt[2] = {0u, 0u};
+        uint32_t zc0 = 0u, zc1 = 0u;                           // completed z-staging phases per buffer (scalars: no local array)
         GX_PROF_DECL;
         while (walk.next(ck)) {
             const int n1 = ck.rows + 8, npairs = (n1 + 1) >> 1;
@@ -677,7 +681,7 @@ gf_mix_kernel(const Params p) {
                 const bool zvalid = 2 * pl + 1 >= 8 && 2 * pl - 8 < ck.rows;      // any of the two output rows inside the chunk
                 GX_WAIT(mbar_wait(smem_u32(&bars->aop_full[buf]), (gpair >> 1) & 1u));
                 if (gpair > 0) GX_WAIT(mbar_wait(smem_u32(&bars->d_empty), (gpair - 1) & 1u));
-                if (zvalid) { mbar_wait(smem_u32(&bars->z_full[buf]), zcnt[buf] & 1u); ++zcnt[buf]; }
+                if (zvalid) { mbar_wait(smem_u32(&bars->z_full[buf]), (buf ? zc1 : zc0) & 1u); if (buf) ++zc1; else ++zc0; }
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a0 = aop_base + buf * AOP_BYTES;
@@ -703,7 +707,7 @@ gf_mix_kernel(const Params p) {
             gp0 += (uint32_t)npairs;
         }
         GX_PROF_END(3);
-    } else {
+    } else if (warp == MMA_WARP + 1) {
         // ============================ producer (one elected thread issues the bulk copies) ============================
         //  * raw-row ring: the entering row (8 quad planes + guide, columns x0-8 .. x0+55 clipped to the image) of every L1
         //    iteration, RS stages ahead;
