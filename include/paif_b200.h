@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PAIF_ABI_VERSION 4   /* 4: paif_fusion_forward_save / paif_fusion_backward_input, paif_conv_set_persistent; 3: paif_gf_mix_forward, glue / PGD / loss-head kernels, paif_stem_forward_rgb, paif_widen_bf16_map */
+#define PAIF_ABI_VERSION 5   /* 5: paif_gf_mix_forward_save / paif_gf_decomp_backward_saved (direct guide term of the adjoint from the forward's mean2(A')); 4: paif_fusion_forward_save / paif_fusion_backward_input, paif_conv_set_persistent; 3: paif_gf_mix_forward, glue / PGD / loss-head kernels, paif_stem_forward_rgb, paif_widen_bf16_map */
 
 #define PAIF_EINVAL   (-1)   /* bad argument (null pointer, unsupported size) */
 #define PAIF_ENOTSUP  (-2)   /* configuration not supported by this build     */
@@ -88,6 +88,11 @@ int paif_gf_decomp_forward(const float* feat, const float* residue, const float*
 int paif_gf_mix_supported(int C, int H, int W);
 int paif_gf_mix_forward(const float* feat, const float* residue, const float* stats, const void* wpack,
                         const float* bias, void* out, int out_bf16, int C, int B, int H, int W, void* stream);
+/* The same, also writing mean_a = mean2(A') (fp32 C4 map [B][8][H][W][4]): d out_o / d residue at fixed window
+ * statistics, which paif_gf_decomp_backward_saved reads instead of re-running the forward filter. */
+int paif_gf_mix_forward_save(const float* feat, const float* residue, const float* stats, const void* wpack,
+                             const float* bias, void* out, int out_bf16, float* mean_a,
+                             int C, int B, int H, int W, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * bf16 storage mode (forward only; north_star's 1e-2 tier).  Stems, guide and guided-filter
@@ -288,6 +293,14 @@ int paif_gf_decomp_backward(const float* feat, const float* residue, const float
                             const float* glf1, const float* glf2,
                             float* gfeat, float* gres_partial, float* work,
                             int C, int B, int H, int W, void* stream);
+/* The adjoint of the FUSED forward (paif_gf_mix_forward_save, autograd of core/model_fusion_auto.py:509-535): gx is the
+ * gradient w.r.t. the fused kernel's output (fp32 C4 map), glf1 / glf2 its images under the transposed 1x1
+ * (Wa^T gx, Wb^T gx), mean_a the map the forward saved.  The direct guide term sum_o gx_o mean2(A'_o) replaces
+ * the forward recompute of paif_gf_decomp_backward (two marching passes + one pointwise pass instead of three). */
+int paif_gf_decomp_backward_saved(const float* feat, const float* residue, const float* stats,
+                                  const float* glf1, const float* glf2, const float* gx, const float* mean_a,
+                                  float* gfeat, float* gres_partial, float* work,
+                                  int C, int B, int H, int W, void* stream);
 
 /* stem backward, pass 1: total = sum of up to 4 gradient maps + route(sum_q gres_partial) to the
  * arg-max / arg-min channel of feat (first index on ties); gpre = total * PReLU'(feat). */

@@ -11,7 +11,7 @@ from . import build as _build
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpaif_b200.so")
 
-ABI_VERSION = 4                                             # PAIF_ABI_VERSION of include/paif_b200.h
+ABI_VERSION = 5                                             # PAIF_ABI_VERSION of include/paif_b200.h
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 STORAGE_F32, STORAGE_BF16, STORAGE_F32_BF16 = 0, 1, 2      # PaifConvDesc.storage
 
@@ -94,6 +94,7 @@ SIGNATURES = {
     "paif_gf_decomp_forward": [_f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_gf_mix_supported": [_i, _i, _i],
     "paif_gf_mix_forward": [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f],
+    "paif_gf_mix_forward_save": [_f, _f, _f, _f, _f, _f, _i, _f, _i, _i, _i, _i, _f],
     "paif_conv_forward": [C.POINTER(ConvDesc), _f],
     "paif_conv_num_tiles": [_i, _i, _i],
     "paif_conv_tc_kq": [_i, _i, _i],
@@ -120,6 +121,7 @@ SIGNATURES = {
     "paif_gf_backward_work_floats": [_i, _i, _i, _i],
     "paif_gf_guide_parts": [_i],
     "paif_gf_decomp_backward": [_f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
+    "paif_gf_decomp_backward_saved": [_f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f],
     "paif_stem_backward_pre": [_f, _f, _f, _f, _f, _f, _f, _i, _f, _i, _i, _i, _i, _f],
     "paif_stem_backward": [_f, _f, _f, _i, _i, _i, _i, _f],
     "paif_confusion_accumulate": [_f, _f, _ll, _i, _f, _f],

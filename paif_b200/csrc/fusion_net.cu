@@ -140,6 +140,7 @@ int run(const PaifFusionWeights* w, const float* ir, long long ir_sb, long long 
 // ---------------------------------------------------------------------------------------------
 struct TrainBufs {
     float *feat[2], *guide[2], *gstats[2];
+    float *gf_ma[2];                        // mean2(A') of the fused decomposition (direct guide term of its adjoint)
     float *rx1[3], *rx2[3], *rpre3[3];      // RDB records: IR chain RDB, VIS chain RDB 1 / 2
     float *s1;                              // IR chain: RDB output (DilConv's input: its ReLU' mask source)
     float *a_f, *v_f, *scale;               // branch outputs, attention plane
@@ -154,7 +155,7 @@ size_t train_layout(int B, int H, int W, unsigned char* base, TrainBufs* tb) {
     const size_t m = (size_t)B * H * W * 32 * 4, pl = (size_t)B * H * W * 4;
     auto map = [&]() { return static_cast<float*>(a.take(m)); };
     auto plane = [&](int n = 1) { return static_cast<float*>(a.take(n * pl)); };
-    for (int i = 0; i < 2; ++i) { tb->feat[i] = map(); tb->guide[i] = plane(); tb->gstats[i] = plane(3); }
+    for (int i = 0; i < 2; ++i) { tb->feat[i] = map(); tb->guide[i] = plane(); tb->gstats[i] = plane(3); tb->gf_ma[i] = map(); }
     for (int i = 0; i < 3; ++i) { tb->rx1[i] = map(); tb->rx2[i] = map(); tb->rpre3[i] = map(); }
     tb->s1 = map(); tb->a_f = map(); tb->v_f = map(); tb->scale = plane();
     tb->eca_x0 = map(); tb->eca_o = map(); tb->res_pre = map(); tb->pre_out = plane(); tb->out_copy = plane();
@@ -245,7 +246,7 @@ int train_forward(const PaifFusionWeights* w, const float* ir, long long ir_sb, 
     for (int i = 0; i < 2; ++i) {
         TRY(paif_gf_guide_stats(tb.guide[i], tb.gstats[i], B, H, W, stream));
         float* x = tb.t[0];
-        TRY(paif_gf_mix_forward(tb.feat[i], tb.guide[i], tb.gstats[i], w->gfmix_w[i], w->c1x1_b[i], x, 0, 32, B, H, W, stream));
+        TRY(paif_gf_mix_forward_save(tb.feat[i], tb.guide[i], tb.gstats[i], w->gfmix_w[i], w->c1x1_b[i], x, 0, tb.gf_ma[i], 32, B, H, W, stream));
         if (i == 0) {
             TRY(rdb_save(c, w->rdb[0], x, tb.rx1[0], tb.rx2[0], tb.rpre3[0], tb.s1, nullptr, nullptr, tb.t[1], tb.zero));
             CArgs a; a.src[0] = tb.t[1]; a.post[0] = tb.s1; a.post[1] = x; a.post[2] = tb.feat[0];
@@ -321,7 +322,7 @@ int train_backward(const PaifFusionWeights* w, const PaifFusionGradWeights* wd, 
         { CArgs a; a.src[0] = gx; TRY(convx(c, wd->c1x1_d[i][0], 1, 1, 1, glf1, a)); }
         { CArgs a; a.src[0] = gx; TRY(convx(c, wd->c1x1_d[i][1], 1, 1, 1, glf2, a)); }
         { CArgs a; a.src[0] = gx; TRY(convx(c, wd->c1x1_d[i][2], 1, 1, 1, gz, a)); }
-        TRY(paif_gf_decomp_backward(tb.feat[i], tb.guide[i], tb.gstats[i], glf1, glf2, gfeat, tb.gres, tb.work, 32, B, H, W, stream));
+        TRY(paif_gf_decomp_backward_saved(tb.feat[i], tb.guide[i], tb.gstats[i], glf1, glf2, gx, tb.gf_ma[i], gfeat, tb.gres, tb.work, 32, B, H, W, stream));
         float* gstem = t[0];
         TRY(paif_stem_backward_pre(tb.feat[i], w->stem_a[i], gb, gz, gfeat, nullptr, tb.gres, tb.nparts, gstem, 32, B, H, W, stream));
         TRY(paif_stem_backward(gstem, w->stem_w[i], gimg[i], 32, B, H, W, stream));

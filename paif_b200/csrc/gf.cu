@@ -680,10 +680,25 @@ extern "C" long long paif_gf_backward_work_floats(int C, int B, int H, int W) {
     return (long long)B * H * W * (2LL * C + 2LL * (C / GF_NCH));
 }
 
-extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, const float* stats,
-                                       const float* glf1, const float* glf2,
-                                       float* gfeat, float* gres_partial, float* work,
-                                       int C, int B, int H, int W, void* stream) {
+// Direct guide term of the adjoint from the fused forward's saved mean2(A') (paif_gf_mix_forward_save):
+//   d out_o / d guide (at fixed window statistics) = mean2(A'_o)  =>  gxd[q][b][pixel] = sum_{o in quad q} gx_o * mean2(A'_o).
+// gx, ma: fp32 C4 maps [B][Q][H*W][4]; gxd: [Q][B][H*W] (the layout pass C reads).
+__global__ void __launch_bounds__(256)
+gf_direct_ma_kernel(const float4* __restrict__ gx, const float4* __restrict__ ma, float* __restrict__ gxd, int Q, int B, long long npix) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= npix) return;
+    const int q = blockIdx.y, b = blockIdx.z;
+    const size_t src = ((size_t)b * Q + q) * (size_t)npix + (size_t)i;
+    const float4 g = __ldg(gx + src), m = __ldg(ma + src);
+    gxd[((size_t)q * B + b) * (size_t)npix + (size_t)i] = fmaf(g.x, m.x, fmaf(g.y, m.y, fmaf(g.z, m.z, g.w * m.w)));
+}
+
+// `gx` / `mean_a` non-null: the direct guide term comes from the fused forward's saved mean2(A') (pass B') instead of a
+// forward recompute (pass B)
+static int gf_decomp_backward_impl(const float* feat, const float* residue, const float* stats,
+                                   const float* glf1, const float* glf2, const float* gx, const float* mean_a,
+                                   float* gfeat, float* gres_partial, float* work,
+                                   int C, int B, int H, int W, void* stream) {
     PAIF_REQUIRE(feat && residue && stats && glf1 && glf2 && gfeat && gres_partial && work, "null pointer");
     PAIF_REQUIRE(C > 0 && C % 4 == 0, "C must be a multiple of 4");
     PAIF_REQUIRE(H > 9 && W > 9, "guided filter needs H, W > 2r+1 = 9");
@@ -710,6 +725,15 @@ extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, 
                                                                   P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
         if (int r = check_launch("paif_gf_decomp_backward(level 2)")) return r;
     }
+    if (mean_a) {   // pass B': direct guide term from the saved mean2(A'): gxd[q] = sum_{o in quad q} gx_o * mean2(A'_o)
+        PAIF_REQUIRE(gx && C == 32, "saved mean2(A') needs the fused decomposition (C = 32)");
+        PAIF_REQUIRE(B <= 65535, "B out of range");
+        const long long npix = (long long)H * W;
+        dim3 grid((unsigned)((npix + 255) / 256), Q, B);
+        gf_direct_ma_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(gx), reinterpret_cast<const float4*>(mean_a),
+                                                  gres_partial, Q, B, npix);
+        if (int r = check_launch("paif_gf_decomp_backward(direct term, saved)")) return r;
+    } else
     {   // pass B: direct guide term (forward recompute of mean_A)
         const int nstrips = cdiv(W, GM_OUTW);
         const long long nitems = (long long)B * P * nstrips * nchunks;
@@ -732,4 +756,20 @@ extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, 
                                                                   P, Q, B, H, W, RC, nstrips, nchunks, (int)nitems);
     }
     return check_launch("paif_gf_decomp_backward");
+}
+
+extern "C" int paif_gf_decomp_backward(const float* feat, const float* residue, const float* stats,
+                                       const float* glf1, const float* glf2,
+                                       float* gfeat, float* gres_partial, float* work,
+                                       int C, int B, int H, int W, void* stream) {
+    return gf_decomp_backward_impl(feat, residue, stats, glf1, glf2, nullptr, nullptr, gfeat, gres_partial, work, C, B, H, W, stream);
+}
+
+extern "C" int paif_gf_decomp_backward_saved(const float* feat, const float* residue, const float* stats,
+                                             const float* glf1, const float* glf2, const float* gx, const float* mean_a,
+                                             float* gfeat, float* gres_partial, float* work,
+                                             int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(gx && mean_a, "null pointer");
+    PAIF_REQUIRE(((reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(mean_a)) & 15) == 0, "pointers must be 16-byte aligned");
+    return gf_decomp_backward_impl(feat, residue, stats, glf1, glf2, gx, mean_a, gfeat, gres_partial, work, C, B, H, W, stream);
 }

@@ -73,6 +73,7 @@ static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 struct Params {
     const float* feat; const float* guide; const float* stats; const void* wpack; const float* bias;
     void* out;
+    float* mean_a;             // SAVE_MA: mean2(A') of every output pixel, fp32 C4 map (the adjoint's direct guide term)
     int B, H, W, nstrips;
     int RC, nchunks;           // rows per chunk / chunks per strip: a function of the shape only (see the launcher)
     int nitems;                // B * nstrips * nchunks work items, split into contiguous ranges over the CTAs
@@ -283,7 +284,7 @@ struct Walker {
 // p per phase) and the 4-columns-per-lane readers (8 consecutive j per phase) touch 8 distinct bank groups
 __device__ __forceinline__ int xslot(int j, int k) { return (k << 4) + (j ^ (k << 1)); }
 
-template <bool OUT_BF>
+template <bool OUT_BF, bool SAVE_MA>
 __global__ void __launch_bounds__(NT, 1)    // 14 warps = up to 4 per SM sub-partition (16 K registers each): 128 registers per thread
 gf_mix_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -481,6 +482,7 @@ gf_mix_kernel(const Params p) {
             const float* gcol = p.guide + (size_t)ck.b * plane + ((xo >= 0 && xo < W) ? xo : 0);
             float4* const o32 = reinterpret_cast<float4*>(p.out) + ((size_t)ck.b * 8 + q) * plane + xo;
             uint4* const o16 = reinterpret_cast<uint4*>(p.out) + ((size_t)ck.b * 4 + w2) * plane + xo;
+            float4* const oma = reinterpret_cast<float4*>(p.mean_a) + ((size_t)ck.b * 8 + q) * plane + xo;
             float co[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -551,6 +553,7 @@ gf_mix_kernel(const Params p) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) rno[k] = rcy * co[k];
                     float o[4][4];
+                    [[maybe_unused]] float ma[4][4];
                     float4 cc[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) { cc[k] = lds128(xrow + (16 + q) * X_PLANE + xo_slot[k]); cdep[k] = cc[k].w; }
@@ -567,7 +570,15 @@ gf_mix_kernel(const Params p) {
                             const float2 c2 = h2 == 0 ? make_float2(cc[k].x, cc[k].y) : make_float2(cc[k].z, cc[k].w);
                             const float2 r = __ffma2_rn(__ffma2_rn(hA[k], dup2(gc[k]), hb[k]), dup2(rno[k]), c2);
                             o[k][2 * h2] = r.x; o[k][2 * h2 + 1] = r.y;
+                            if constexpr (SAVE_MA) { const float2 m = __fmul2_rn(hA[k], dup2(rno[k])); ma[k][2 * h2] = m.x; ma[k][2 * h2 + 1] = m.y; }
                         }
+                    }
+                    if constexpr (SAVE_MA) {
+                        // mean2(A'): d out_o / d guide at fixed statistics; the adjoint's direct term is sum_o gx_o * mean2(A'_o)
+                        float4* mrow = oma + (unsigned)(yo * W);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (co[k] > 0.f) mrow[k] = make_float4(ma[k][0], ma[k][1], ma[k][2], ma[k][3]);
                     }
                     if constexpr (!OUT_BF) {
                         float4* orow = o32 + (unsigned)(yo * W);
@@ -809,23 +820,27 @@ extern "C" int paif_debug_gx_counters(unsigned long long* out16, int reset) {
 
 extern "C" int paif_gf_mix_supported(int C, int H, int W) { return C == 32 && H > 9 && W > 9 && W % 4 == 0; }
 
-extern "C" int paif_gf_mix_forward(const float* feat, const float* residue, const float* stats, const void* wpack,
-                                   const float* bias, void* out, int out_bf16, int C, int B, int H, int W, void* stream) {
+static int gf_mix_launch(const float* feat, const float* residue, const float* stats, const void* wpack,
+                         const float* bias, void* out, int out_bf16, float* mean_a, int C, int B, int H, int W, void* stream,
+                         const char* what) {
     PAIF_REQUIRE(feat && residue && stats && wpack && out, "null pointer");
     PAIF_REQUIRE(B > 0 && H > 9 && W > 9, "guided filter needs H, W > 2r+1 = 9");
-    if (!paif_gf_mix_supported(C, H, W)) { set_error("paif_gf_mix_forward: needs C = 32 and W %% 4 == 0"); return PAIF_ENOTSUP; }
+    if (!paif_gf_mix_supported(C, H, W)) { set_error("%s: needs C = 32 and W %% 4 == 0", what); return PAIF_ENOTSUP; }
     PAIF_REQUIRE(((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(residue) | reinterpret_cast<uintptr_t>(stats) |
-                   reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "pointers must be 16-byte aligned");
+                   reinterpret_cast<uintptr_t>(wpack) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mean_a)) & 15) == 0,
+                 "pointers must be 16-byte aligned");
     static unsigned long long attr_done = 0;
     int dev;
     if (attr_needed(attr_done, &dev)) {
-        cudaError_t e = cudaFuncSetAttribute(gx::gf_mix_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gx::SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gx::gf_mix_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gx::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gx::gf_mix_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gx::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gx::gf_mix_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gx::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gx::gf_mix_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gx::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gx::gf_mix_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gx::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("gf_mix smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_mark(attr_done, dev);
     }
     gx::Params p;
-    p.feat = feat; p.guide = residue; p.stats = stats; p.wpack = wpack; p.bias = bias; p.out = out;
+    p.feat = feat; p.guide = residue; p.stats = stats; p.wpack = wpack; p.bias = bias; p.out = out; p.mean_a = mean_a;
     p.B = B; p.H = H; p.W = W; p.nstrips = cdiv(W, gx::OUTW);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -844,8 +859,26 @@ extern "C" int paif_gf_mix_forward(const float* feat, const float* residue, cons
     p.nchunks = cdiv(H, p.RC);
     PAIF_REQUIRE(strips * p.nchunks < (1ll << 30), "problem too large");
     p.nitems = (int)(strips * p.nchunks);
-    int grid = p.nitems < sms ? p.nitems : sms;
-    if (out_bf16) gx::gf_mix_kernel<true><<<grid, gx::NT, gx::SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    else gx::gf_mix_kernel<false><<<grid, gx::NT, gx::SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    return check_launch("paif_gf_mix_forward");
+    const int grid = p.nitems < sms ? p.nitems : sms;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mean_a) {
+        if (out_bf16) gx::gf_mix_kernel<true, true><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
+        else gx::gf_mix_kernel<false, true><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
+    } else {
+        if (out_bf16) gx::gf_mix_kernel<true, false><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
+        else gx::gf_mix_kernel<false, false><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
+    }
+    return check_launch(what);
+}
+
+extern "C" int paif_gf_mix_forward(const float* feat, const float* residue, const float* stats, const void* wpack,
+                                   const float* bias, void* out, int out_bf16, int C, int B, int H, int W, void* stream) {
+    return gf_mix_launch(feat, residue, stats, wpack, bias, out, out_bf16, nullptr, C, B, H, W, stream, "paif_gf_mix_forward");
+}
+
+extern "C" int paif_gf_mix_forward_save(const float* feat, const float* residue, const float* stats, const void* wpack,
+                                        const float* bias, void* out, int out_bf16, float* mean_a,
+                                        int C, int B, int H, int W, void* stream) {
+    PAIF_REQUIRE(mean_a, "null pointer");
+    return gf_mix_launch(feat, residue, stats, wpack, bias, out, out_bf16, mean_a, C, B, H, W, stream, "paif_gf_mix_forward_save");
 }

@@ -137,7 +137,8 @@ class _Runtime:
         return torch.empty(shape, device=self.device, dtype=torch.float32)
 
     #: kernels behind one ABI call when it is not exactly one
-    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_out_forward_bf16": 2, "paif_out_forward_tc": 2, "paif_gf_decomp_backward": 3}
+    _KERNELS_PER_CALL = {"paif_out_forward": 2, "paif_out_forward_bf16": 2, "paif_out_forward_tc": 2, "paif_gf_decomp_backward": 3,
+                         "paif_gf_decomp_backward_saved": 3}
 
     def note_bytes(self, bytes_per_px):
         """algorithmic HBM bytes per pixel of the next launch (inputs read once + outputs written once), for the
@@ -1056,7 +1057,7 @@ class Network_Fusion_Searched(nn.Module):
         rt.profile = self.profile
         rt.dilconv_dense = self.dilconv_dense
         C = self._C
-        feats, guides, gstats, feats16 = [], [], [], []
+        feats, guides, gstats, feats16, gf_ma = [], [], [], [], []
         for img, w, a in ((ir, p["stem_w"][0], p["stem_a"][0]), (vis, p["stem_w"][1], p["stem_a"][1])):
             f, g = rt.new_map(fp32=True), rt.new_plane()
             rt.note_bytes(4 + 4 * C + 4 + (2 * C if bf16 else 0))
@@ -1089,8 +1090,17 @@ class Network_Fusion_Searched(nn.Module):
             if fused_gf:
                 x = rt.new_map()
                 rt.note_bytes(4 * (C + 4) + (2 if bf16 else 4) * C)
-                rt.call("paif_gf_mix_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
-                        p["gfmix_w"][i].data_ptr(), p["c1x1_b"][i].data_ptr(), x.data_ptr(), int(bf16), C, B, H, W)
+                if save:
+                    # also keep mean2(A'): the adjoint's direct guide term, instead of a forward recompute in the backward
+                    ma = rt.new_map(fp32=True)
+                    rt.note_bytes(4 * (C + 4) + (2 if bf16 else 4) * C + 4 * C)
+                    rt.call("paif_gf_mix_forward_save", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
+                            p["gfmix_w"][i].data_ptr(), p["c1x1_b"][i].data_ptr(), x.data_ptr(), int(bf16), ma.data_ptr(),
+                            C, B, H, W)
+                    gf_ma.append(ma)
+                else:
+                    rt.call("paif_gf_mix_forward", feats[i].data_ptr(), guides[i].data_ptr(), stats.data_ptr(),
+                            p["gfmix_w"][i].data_ptr(), p["c1x1_b"][i].data_ptr(), x.data_ptr(), int(bf16), C, B, H, W)
             else:
                 lf1, lf2 = rt.new_map(fp32=True), rt.new_map(fp32=True)
                 rt.note_bytes(4 * (C + 4) + 8 * C)
@@ -1100,6 +1110,7 @@ class Network_Fusion_Searched(nn.Module):
                 if capture is not None:
                     capture.setdefault("lf", []).append((lf1, lf2))
                 del lf1, lf2
+                gf_ma.append(None)
             gstats.append(stats if save else None)
             del stats
             o, recs = chain.fwd(rt, packs, x, [feats16[i] if bf16 else feats[i]])
@@ -1135,7 +1146,7 @@ class Network_Fusion_Searched(nn.Module):
             capture.update(feats=feats, guides=guides, branch_out=branch_out)
         saved = None
         if save:
-            saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, gstats=gstats, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
+            saved = dict(B=B, H=H, W=W, feats=feats, guides=guides, gstats=gstats, gf_ma=gf_ma, branch_recs=branch_recs, a_f=a_f, v_f=v_f,
                          scale=scale, recs3=recs3, out=out, pre_out=pre_out, packed=p, bf16=bf16)
         return out, saved
 
@@ -1191,9 +1202,15 @@ class Network_Fusion_Searched(nn.Module):
             nparts = _lib.load().paif_gf_guide_parts(C)
             gres = torch.empty((nparts, B, H, W), device=g.device, dtype=torch.float32)
             work = torch.empty((_lib.load().paif_gf_backward_work_floats(C, B, H, W),), device=g.device, dtype=torch.float32)
-            rt.call("paif_gf_decomp_backward", saved["feats"][i].data_ptr(), saved["guides"][i].data_ptr(),
-                    saved["gstats"][i].data_ptr(), glf1.data_ptr(), glf2.data_ptr(), gfeat.data_ptr(), gres.data_ptr(),
-                    work.data_ptr(), C, B, H, W)
+            ma = saved["gf_ma"][i]
+            if ma is not None:
+                rt.call("paif_gf_decomp_backward_saved", saved["feats"][i].data_ptr(), saved["guides"][i].data_ptr(),
+                        saved["gstats"][i].data_ptr(), glf1.data_ptr(), glf2.data_ptr(), gx.data_ptr(), ma.data_ptr(),
+                        gfeat.data_ptr(), gres.data_ptr(), work.data_ptr(), C, B, H, W)
+            else:
+                rt.call("paif_gf_decomp_backward", saved["feats"][i].data_ptr(), saved["guides"][i].data_ptr(),
+                        saved["gstats"][i].data_ptr(), glf1.data_ptr(), glf2.data_ptr(), gfeat.data_ptr(), gres.data_ptr(),
+                        work.data_ptr(), C, B, H, W)
             del work
             gstem = rt.new_map()
             rt.call("paif_stem_backward_pre", saved["feats"][i].data_ptr(), p["stem_a"][i].data_ptr(),

@@ -66,6 +66,58 @@ def test_guided_filter_adjoint(shape, smooth):
     assert e_z < 2e-3 and e_g < 2e-3, (e_z, e_g)
 
 
+@pytest.mark.parametrize("shape,smooth", [((1, 40, 56), False), ((2, 33, 48), True), ((1, 200, 236), False)])
+def test_fused_decomposition_adjoint_from_saved_mean(shape, smooth):
+    """paif_gf_mix_forward_save + paif_gf_decomp_backward_saved (the direct guide term from the forward's mean2(A')) against
+    fp64 autograd of conv1x1(cat[LF, HF]) (core/model_fusion_auto.py:509-535) and against the forward-recompute adjoint."""
+    from paif_b200 import fusion
+    B, H, W = shape
+    torch.manual_seed(5)
+    z = torch.rand(B, 32, H, W, dtype=torch.float64)
+    if smooth:
+        z = torch.nn.functional.avg_pool2d(z, 9, 1, 4)
+    w = torch.randn(32, 128, 1, 1, dtype=torch.float64) * 0.15
+    bias = torch.randn(32, dtype=torch.float64) * 0.1
+    guide = fo.get_residue(z).detach().requires_grad_(True)
+    zr = z.clone().requires_grad_(True)
+    lf1, lf2 = fo.guided_filter(guide, zr, 4, 1e-3), fo.guided_filter(guide, zr, 4, 1e-4)
+    x = torch.nn.functional.conv2d(torch.cat([lf1, lf2, zr - lf1, zr - lf2], 1), w, bias)
+    gx = torch.randn_like(x)
+    gz_ref, gg_ref = torch.autograd.grad(x, [zr, guide], gx)
+    wa, wb, wc = fusion._fold_decomp_1x1(w, double=True)
+    g1 = torch.einsum("oc,bohw->bchw", wa, gx)          # the transposed 1x1 (three K groups), as the module's backward forms them
+    g2 = torch.einsum("oc,bohw->bchw", wb, gx)
+    gzd = torch.einsum("oc,bohw->bchw", wc, gx)
+    zc, gc = to_c4(z.float()).to(DEV), guide.detach().float()[:, 0].contiguous().to(DEV)
+    g1c, g2c, gxc = to_c4(g1.float()).to(DEV), to_c4(g2.float()).to(DEV), to_c4(gx.float()).to(DEV)
+    stats = torch.empty(3, B, H, W, device=DEV)
+    _lib.call("paif_gf_guide_stats", gc.data_ptr(), stats.data_ptr(), B, H, W, stream())
+    wp, bd = fusion._pack_gf_mix(w.float().to(DEV)), bias.float().to(DEV)
+    out, out2, ma = torch.empty_like(zc), torch.empty_like(zc), torch.empty_like(zc)
+    _lib.call("paif_gf_mix_forward_save", zc.data_ptr(), gc.data_ptr(), stats.data_ptr(), wp.data_ptr(), bd.data_ptr(),
+              out.data_ptr(), 0, ma.data_ptr(), 32, B, H, W, stream())
+    _lib.call("paif_gf_mix_forward", zc.data_ptr(), gc.data_ptr(), stats.data_ptr(), wp.data_ptr(), bd.data_ptr(),
+              out2.data_ptr(), 0, 32, B, H, W, stream())
+    assert torch.equal(out, out2)                        # saving mean2(A') does not change the output
+    nparts = _lib.load().paif_gf_guide_parts(32)
+    work = torch.empty(_lib.load().paif_gf_backward_work_floats(32, B, H, W), device=DEV)
+    res = []
+    for saved in (True, False):
+        gfeat, gres = torch.empty_like(zc), torch.empty(nparts, B, H, W, device=DEV)
+        if saved:
+            _lib.call("paif_gf_decomp_backward_saved", zc.data_ptr(), gc.data_ptr(), stats.data_ptr(), g1c.data_ptr(), g2c.data_ptr(),
+                      gxc.data_ptr(), ma.data_ptr(), gfeat.data_ptr(), gres.data_ptr(), work.data_ptr(), 32, B, H, W, stream())
+        else:
+            _lib.call("paif_gf_decomp_backward", zc.data_ptr(), gc.data_ptr(), stats.data_ptr(), g1c.data_ptr(), g2c.data_ptr(),
+                      gfeat.data_ptr(), gres.data_ptr(), work.data_ptr(), 32, B, H, W, stream())
+        res.append((from_c4(gfeat).cpu().double() + gzd, gres.sum(0).cpu().double()))
+    (gz_s, gg_s), (gz_r, gg_r) = res
+    assert torch.equal(gz_s, gz_r)                       # the feature gradient does not involve the direct term
+    e_z, e_g, e_gr = rel_l2(gz_s, gz_ref), rel_l2(gg_s, gg_ref[:, 0]), rel_l2(gg_r, gg_ref[:, 0])
+    # TF32 operand rounding of the mix inside mean2(A') (the forward's own rounding) bounds the guide-gradient error
+    assert e_z < 2e-3 and e_g < 5e-3 and e_gr < 2e-3, (e_z, e_g, e_gr)
+
+
 # (engine, fused-image gate, gradient rel-L2 gate, sign-agreement gate): the exact-fp32 engine is held to the
 # reference's own fp32-vs-fp64 noise floor, the TF32 tensor-core engine to SURVEY.md 8d's TF32 gates
 GRAD_GATES = [("direct", 5e-5, 1e-2, 0.999), ("tcgen05", 1e-3, 5e-2, 0.995)]

@@ -152,7 +152,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "library lacks %s" % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.paif_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.paif_abi_version() == _lib.ABI_VERSION == 5
     assert ctypes.sizeof(_lib.ConvDesc) > 0
 
 
