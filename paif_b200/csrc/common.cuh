@@ -3,7 +3,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
-#include <stdlib.h>
 #include "../../include/paif_b200.h"
 
 namespace paif {
@@ -17,39 +16,6 @@ inline int check_launch(const char* what) {
         return (int)e;
     }
     return 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Programmatic dependent launch (PDL).  The persistent tensor-core kernels are launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may become resident while the previous kernel of the
-// stream is still draining (as its CTAs exit and free shared memory), run the part of their prologue that touches no
-// global memory (mbarrier init, TMEM allocation) and then block in pdl_wait() until the previous grid has completed and
-// flushed.  Every global access of such a kernel comes after pdl_wait(); kernels launched without the attribute are
-// ordered as usual.  pdl_trigger() in a kernel lets the NEXT launch start that early.  Off under stream capture (the
-// PGD iteration graphs keep plain edges) and with PAIF_NO_PDL=1.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-inline bool pdl_allowed(cudaStream_t st) {
-    static int env = -1;
-    if (env < 0) { const char* v = getenv("PAIF_NO_PDL"); env = (v && v[0] == '1') ? 0 : 1; }
-    if (!env) return false;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
-    return cs == cudaStreamCaptureStatusNone;
-}
-
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl_allowed(st) ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors are picked up by check_launch()
 }
 
 #define PAIF_REQUIRE(cond, msg)                                      \

@@ -252,14 +252,10 @@ conv_tc_kernel(TcGeom g, EpiParams e) {
         mbar_init(smem_u32(&bars->zeroed), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // (PDL, common.cuh) up to here nothing touched global memory: let the next launch start its own prologue, and wait
-    // for the previous grid before the first global access
-    pdl_trigger();
     if (warp == TC_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    pdl_wait();
     if (tid >= 32 && tid < 64) {
         bars->ch_scale[tid - 32] = e.ch_scale ? e.ch_scale[tid - 32] : 1.f;
         bars->ch_shift[tid - 32] = e.ch_shift ? e.ch_shift[tid - 32] : 0.f;
@@ -1028,8 +1024,8 @@ int conv_tc_launch(const PaifConvDesc& d, cudaStream_t stream) {
             if (err != cudaSuccess) { set_error("conv_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; } \
             attr_mark(attr_done, dev_);                                                                             \
         }                                                                                                           \
-        if (d.chan_partials) launch_pdl(conv_tc_kernel<K_, D_, Q_, true, S_>, grid, dim3(TC_NT), g.plan.smem_bytes, stream, g, e); \
-        else launch_pdl(conv_tc_kernel<K_, D_, Q_, false, S_>, grid, dim3(TC_NT), g.plan.smem_bytes, stream, g, e);              \
+        if (d.chan_partials) conv_tc_kernel<K_, D_, Q_, true, S_><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e); \
+        else conv_tc_kernel<K_, D_, Q_, false, S_><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);              \
         return check_launch("paif_conv_forward(tcgen05)");                                                          \
     }
     TC_CASE(1, 1, 8, 0) TC_CASE(3, 1, 8, 0) TC_CASE(3, 2, 8, 0) TC_CASE(5, 1, 8, 0) TC_CASE(5, 2, 8, 0)
@@ -1071,8 +1067,8 @@ int out_tc_launch(const void* feat, const void* wmma, const float* slope, float*
         if (err != cudaSuccess) { set_error("out_tc smem attr: %s", cudaGetErrorString(err)); return (int)err; }
         attr_mark(attr_done, dev);
     }
-    if (bf16) launch_pdl(conv_tc_kernel<5, 1, 4, false, 1, 16>, grid, dim3(TC_NT), g.plan.smem_bytes, stream, g, e);
-    else launch_pdl(conv_tc_kernel<5, 1, 8, false, 0, 16>, grid, dim3(TC_NT), g.plan.smem_bytes, stream, g, e);
+    if (bf16) conv_tc_kernel<5, 1, 4, false, 1, 16><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);
+    else conv_tc_kernel<5, 1, 8, false, 0, 16><<<grid, TC_NT, g.plan.smem_bytes, stream>>>(g, e);
     return check_launch("paif_out_forward_tc");
 }
 

@@ -25,7 +25,6 @@ __device__ __forceinline__ float win_count(int p, int n) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gf_guide_stats_kernel(const float* __restrict__ guide, float* __restrict__ stats, int B, int H, int W) {
-    pdl_trigger();                                 // (PDL, common.cuh) a tensor-core kernel launched next may start its prologue
     __shared__ float sg[40][41];
     __shared__ float h1[40][33], h2[40][33];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32, b = blockIdx.z;

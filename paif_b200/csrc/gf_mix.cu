@@ -316,9 +316,6 @@ gf_mix_kernel(const Params p) {
         mbar_init(smem_u32(&bars->d_empty), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // (PDL, common.cuh) nothing above touches global memory: the next launch may start, this one waits for the previous grid
-    pdl_trigger();
-    pdl_wait();
     if (tid < 32) bars->bias[tid] = p.bias ? p.bias[tid] : 0.f;
     for (int i = tid; i < W_BYTES / 16; i += NT)
         reinterpret_cast<uint4*>(smem + OFF_W)[i] = __ldg(reinterpret_cast<const uint4*>(p.wpack) + i);
@@ -869,11 +866,11 @@ static int gf_mix_launch(const float* feat, const float* residue, const float* s
     const int grid = p.nitems < sms ? p.nitems : sms;
     cudaStream_t st = (cudaStream_t)stream;
     if (mean_a) {
-        if (out_bf16) launch_pdl(gx::gf_mix_kernel<true, true>, dim3(grid), dim3(gx::NT), gx::SMEM_BYTES, st, p);
-        else launch_pdl(gx::gf_mix_kernel<false, true>, dim3(grid), dim3(gx::NT), gx::SMEM_BYTES, st, p);
+        if (out_bf16) gx::gf_mix_kernel<true, true><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
+        else gx::gf_mix_kernel<false, true><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
     } else {
-        if (out_bf16) launch_pdl(gx::gf_mix_kernel<true, false>, dim3(grid), dim3(gx::NT), gx::SMEM_BYTES, st, p);
-        else launch_pdl(gx::gf_mix_kernel<false, false>, dim3(grid), dim3(gx::NT), gx::SMEM_BYTES, st, p);
+        if (out_bf16) gx::gf_mix_kernel<true, false><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
+        else gx::gf_mix_kernel<false, false><<<grid, gx::NT, gx::SMEM_BYTES, st>>>(p);
     }
     return check_launch(what);
 }

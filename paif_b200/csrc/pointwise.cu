@@ -318,7 +318,6 @@ __global__ void __launch_bounds__(256)
 eca_apply_kernel(const float* __restrict__ o, const float* __restrict__ xin, const float* __restrict__ e,
                  const float* __restrict__ slope_p, const float* __restrict__ post_res,
                  float* __restrict__ out, int Q, int H, int W) {
-    pdl_trigger();                                 // (PDL, common.cuh) a tensor-core kernel launched next may start its prologue
     const int q = blockIdx.z % Q, b = blockIdx.z / Q;
     PIX_SETUP();
     if (x >= W || y >= H) return;
@@ -916,7 +915,6 @@ template <bool BF>
 __global__ void __launch_bounds__(256)
 spa_fused32_kernel(const float* __restrict__ w, int k, const void* __restrict__ a, const void* __restrict__ v,
                    void* __restrict__ agg, float* __restrict__ scale_out, int H, int W) {
-    pdl_trigger();                                 // (PDL, common.cuh) a tensor-core kernel launched next may start its prologue
     __shared__ float4 sw[49];
     __shared__ float4 sp[(SR_TY + 6) * (SR_TX + 6)];            // pooled (max_a, mean_a, max_v, mean_v), halo <= 3
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;

@@ -14,9 +14,14 @@ __global__ void __launch_bounds__(256)
 stem_forward_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy, long long sx,
                     const float* __restrict__ w, const float* __restrict__ slope_p,
                     float* __restrict__ feat, float* __restrict__ residue, uint4* __restrict__ feat16, int H, int W) {
-    __shared__ float sw[STEM_C * 9];
+    // weights as channel pairs [pair][tap] = (w[2p][t], w[2p+1][t]): the 288 multiply-adds of a pixel are 144 packed
+    // FFMA2 (the kernel is instruction-issue bound; each component is the same fused multiply-add as before)
+    __shared__ float2 sw2[(STEM_C / 2) * 9];
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < STEM_C * 9; i += 256) sw[i] = w[i];
+    for (int i = tid; i < (STEM_C / 2) * 9; i += 256) {
+        const int pr = i / 9, t = i - pr * 9;
+        sw2[i] = make_float2(w[(2 * pr) * 9 + t], w[(2 * pr + 1) * 9 + t]);
+    }
     __syncthreads();
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
@@ -37,6 +42,9 @@ stem_forward_kernel(const float* __restrict__ img, long long sb, long long sc, l
             }
             in[(dy + 1) * 3 + (dx + 1)] = v;
         }
+    float2 in2[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) in2[t] = make_float2(in[t], in[t]);
     float vmax = -INFINITY, vmin = INFINITY;
     const size_t plane = (size_t)H * W;
     float4* out = reinterpret_cast<float4*>(feat) + (size_t)b * (STEM_C / 4) * plane + (size_t)y * W + x;
@@ -45,15 +53,15 @@ stem_forward_kernel(const float* __restrict__ img, long long sb, long long sc, l
     for (int q = 0; q < STEM_C / 4; ++q) {
         float r[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float* wc = sw + (q * 4 + j) * 9;
-            float acc = 0.f;
+        for (int jp = 0; jp < 2; ++jp) {
+            const float2* wc = sw2 + (q * 2 + jp) * 9;
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < 9; ++t) acc = fmaf(in[t], wc[t], acc);
-            acc = prelu_f(acc, a);
-            vmax = fmaxf(vmax, acc);
-            vmin = fminf(vmin, acc);
-            r[j] = acc;
+            for (int t = 0; t < 9; ++t) acc = __ffma2_rn(in2[t], wc[t], acc);
+            const float v0 = prelu_f(acc.x, a), v1 = prelu_f(acc.y, a);
+            vmax = fmaxf(vmax, fmaxf(v0, v1));
+            vmin = fminf(vmin, fminf(v0, v1));
+            r[2 * jp] = v0; r[2 * jp + 1] = v1;
         }
         out[q * plane] = make_float4(r[0], r[1], r[2], r[3]);
         if (feat16) {                 // bf16 C8 copy for the bf16 storage mode (residual of the decomposition branch)
