@@ -21,13 +21,35 @@ def _nvcc():
     return "nvcc"
 
 
+def _deps():
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    deps.append(os.path.join(HERE, "..", "include", "paif_b200.h"))
+    return deps
+
+
+def _src_hash():
+    """sha256 over the sources, the header and the compiler flags: what the library was built from."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
+    """The library is rebuilt when its sources changed.  Decided by content (a hash written next to the library), not by
+    file times: a snapshot of the tree on another machine (gpurun) does not keep them, and the library that travelled
+    with it would be rebuilt for nothing in every process."""
     if not os.path.exists(LIB):
         return True
+    stamp = LIB + ".srchash"
+    if os.path.exists(stamp):
+        with open(stamp) as f:
+            return f.read().strip() != _src_hash()
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(HERE, "..", "include", "paif_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force=False, verbose=False, profile=False, sanitize=False):
@@ -62,6 +84,9 @@ def build(force=False, verbose=False, profile=False, sanitize=False):
     if failed:
         raise RuntimeError("paif_b200: nvcc build failed")
     subprocess.check_call([_nvcc(), "-shared", "-o", lib] + objs + ["-lcudart"])
+    if lib == LIB:
+        with open(LIB + ".srchash", "w") as f:
+            f.write(_src_hash() + "\n")
     return lib
 
 
