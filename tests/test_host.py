@@ -191,3 +191,29 @@ def test_bf16_storage_mode_rules():
     alt.storage = 'bf16'
     with pytest.raises(NotImplementedError):
         alt._bf16_storage(False)
+
+
+def test_rebuild_is_decided_by_source_content_not_file_times(tmp_path, monkeypatch):
+    """paif_b200.build.needs_build: a library that travelled with a snapshot of the tree (file times lost) is used as
+    is when the hash written next to it matches the sources, and rebuilt when a source changed."""
+    import os
+    from paif_b200 import build
+    csrc = tmp_path / "csrc"
+    csrc.mkdir()
+    (csrc / "a.cu").write_text("// kernel a\n")
+    inc = tmp_path / "include"
+    inc.mkdir()
+    (inc / "paif_b200.h").write_text("// header\n")
+    pkg = tmp_path / "pkg"
+    pkg.mkdir()
+    lib = pkg / "libpaif_b200.so"
+    monkeypatch.setattr(build, "CSRC", str(csrc))
+    monkeypatch.setattr(build, "HERE", str(pkg))
+    monkeypatch.setattr(build, "LIB", str(lib))
+    assert build.needs_build()                                  # no library yet
+    lib.write_bytes(b"\x7fELF")
+    (pkg / "libpaif_b200.so.srchash").write_text(build._src_hash() + "\n")
+    os.utime(str(csrc / "a.cu"), None)                          # a newer file time alone does not trigger a rebuild
+    assert not build.needs_build()
+    (csrc / "a.cu").write_text("// kernel a, edited\n")
+    assert build.needs_build()
