@@ -376,7 +376,7 @@ long long paif_fusion_workspace_bytes(int B, int H, int W, int storage);
 
 /* The PGD inner step (attack/attack.py:444-501: forward, loss, backward to the INPUTS) of the same genotype as two calls
  * over one caller-owned workspace, fp32 storage: paif_fusion_forward_save leaves the activations the backward needs at
- * fixed offsets of the workspace (~17 maps of B*H*W*128 bytes), paif_fusion_backward_input turns d loss / d out
+ * fixed offsets of the workspace (~19 maps of B*H*W*128 bytes, two of them the mean2(A') maps of the fused decomposition), paif_fusion_backward_input turns d loss / d out
  * (gout: [B][1][H][W]) into d loss / d ir and d loss / d vis (contiguous [B][H][W] planes; weight gradients are not
  * produced — nothing in the reference reads them).  Same kernels in the same order as the autograd node of
  * paif_b200/fusion.py, so the gradients are bit-identical to it.  grad_weights: the dgrad images of every convolution
