@@ -21,6 +21,12 @@
 //              of (A', b') that the vertical running sum needs lives in TMEM (tcgen05.st / ld, 32 columns per row and
 //              warp: 9 x 32 columns next to the 128 accumulator columns); output = mean2(A') g + mean2(b') + C.
 // The level-2 history is what bounds the strip width: 9 rows x 64 values x 4 B = 2.3 KB per pixel column.
+// Details that carry the performance ("second pass"): the level-1 ring reads are rotated per lane so that
+// they are bank-conflict free; columns outside the image read zeros (a zero page in global memory for the leaving row,
+// ring columns cleared by the producer for the entering row) instead of being masked; every address is a 32-bit offset
+// from a per-chunk base; thread index and shared-window base are kept out of the row loops; a ring stage / exchange row
+// is released by an arrive whose ADDRESS depends on the loaded registers (mbar_arrive_after_loads).
+// SAVE_MA (paif_gf_mix_forward_save): also writes mean2(A'), the direct guide term of the adjoint (gf.cu).
 #ifdef PAIF_SANITIZER_BUILD
 #define PAIF_MBAR_SPIN_LIMIT 0xffffffffu        // compute-sanitizer slows the busy roles by orders of magnitude: no poll-count watchdog
 #else
