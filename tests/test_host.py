@@ -217,3 +217,38 @@ def test_rebuild_is_decided_by_source_content_not_file_times(tmp_path, monkeypat
     assert not build.needs_build()
     (csrc / "a.cu").write_text("// kernel a, edited\n")
     assert build.needs_build()
+
+
+def test_direct_guide_term_of_the_fused_adjoint_is_a_dot_with_mean2_of_the_mixed_A():
+    """The algebra behind paif_gf_mix_forward_save / paif_gf_decomp_backward_saved, in fp64 on the oracle's operators:
+    with out = conv1x1(cat[LF1, LF2, z - LF1, z - LF2]) (core/model_fusion_auto.py:509-535) and the guided filter
+    LF_e = mean2(A_e) g + mean2(b_e), the derivative of out w.r.t. the guide g AT FIXED window statistics is
+    mean2(A'_o), A' = Wa A_1 + Wb A_2 (the folded 1x1 applied between the two box-filter levels).  So the adjoint's direct
+    term sum_c sum_e gLF_e,c mean2(A_e,c) equals sum_o gx_o mean2(A'_o): one saved map and a dot product."""
+    from oracle import fusion_oracle as fo
+    torch.manual_seed(11)
+    B, C, H, W = 1, 32, 24, 28
+    z = torch.rand(B, C, H, W, dtype=torch.float64)
+    g = fo.get_residue(z)
+    w = torch.randn(C, 4 * C, 1, 1, dtype=torch.float64) * 0.2
+    gx = torch.randn(B, C, H, W, dtype=torch.float64)
+    wa, wb, _ = fusion._fold_decomp_1x1(w, double=True)
+    N = fo.box_filter(g.new_ones((1, 1, H, W)))
+    mx = fo.box_filter(g) / N
+    var = fo.box_filter(g * g) / N - mx * mx
+    mz = fo.box_filter(z) / N
+    cov = fo.box_filter(g * z) / N - mx * mz
+    mean_a = [fo.box_filter(cov / (var + eps)) / N for eps in (1e-3, 1e-4)]
+    # three-pass adjoint: gLF_e = W_e^T gx, direct term = sum_c sum_e gLF_e,c mean2(A_e,c)
+    glf = [torch.einsum("oc,bohw->bchw", we, gx) for we in (wa, wb)]
+    direct_old = sum((gl * ma).sum(1) for gl, ma in zip(glf, mean_a))
+    # fused form: A' = Wa A_1 + Wb A_2 mixed BEFORE the level-2 mean (linearity), direct term = sum_o gx_o mean2(A'_o)
+    a_mixed = sum(torch.einsum("oc,bchw->bohw", we, cov / (var + eps)) for we, eps in ((wa, 1e-3), (wb, 1e-4)))
+    direct_new = (gx * (fo.box_filter(a_mixed) / N)).sum(1)
+    assert torch.allclose(direct_old, direct_new, rtol=1e-10, atol=1e-12)
+    # and it IS the partial derivative: perturb g only where it multiplies mean2(A) (autograd with the statistics detached)
+    gd = g.clone().requires_grad_(True)
+    lf = [ma.detach() * gd + (fo.box_filter(mz - (cov / (var + eps)) * mx) / N).detach() for ma, eps in zip(mean_a, (1e-3, 1e-4))]
+    out = torch.nn.functional.conv2d(torch.cat([lf[0], lf[1], z - lf[0], z - lf[1]], 1), w)
+    (gg,) = torch.autograd.grad(out, gd, gx)
+    assert torch.allclose(gg[:, 0], direct_new, rtol=1e-9, atol=1e-11)
