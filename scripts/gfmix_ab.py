@@ -1,5 +1,6 @@
-"""Development A/B of paif_gf_mix_forward builds: every library named on the command line (built with
--DPAIF_TC_PROFILE) against the first one — bit-identity of the fp32 and bf16 outputs at several shapes (edge strips,
+"""Development A/B of paif_gf_mix_forward builds: every library named on the command line (built by
+scripts/build_gfmix_variant.sh, i.e. with -DPAIF_TC_PROFILE; e.g. one from `git stash` / an older commit as the base)
+against the first one — bit-identity of the fp32 and bf16 outputs at several shapes (edge strips,
 odd row counts, small batches), time at the bench shape and the role timeline (wait share per role)."""
 import ctypes as C
 import os
